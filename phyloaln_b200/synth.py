@@ -1,0 +1,88 @@
+"""Seeded synthetic workloads: profiles, reads and transcripts.
+
+Used by bench.py and the tests; nothing here is on the search path itself.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .hmmbuild_lite import AMINO_BG, DNA_BG, finish_hmm
+from .hmmio import AMINO, DNA, HMM
+
+# one codon per amino acid for back-translation (standard code)
+_CODON = {"A": "GCT", "C": "TGT", "D": "GAT", "E": "GAA", "F": "TTT", "G": "GGT", "H": "CAT", "I": "ATT",
+          "K": "AAA", "L": "CTG", "M": "ATG", "N": "AAT", "P": "CCT", "Q": "CAA", "R": "CGT", "S": "TCT",
+          "T": "ACT", "V": "GTT", "W": "TGG", "Y": "TAT"}
+
+
+def random_hmm(name: str, M: int, rng: np.random.Generator, abc: str = "amino") -> HMM:
+    """BUSCO-like random profile: Dirichlet match emissions mixed 50/50 with background."""
+    bg = AMINO_BG if abc == "amino" else DNA_BG
+    K = len(bg)
+    mat = np.zeros((M + 1, K))
+    d = rng.dirichlet(0.3 * bg * K, size=M)
+    mat[1:] = 0.5 * d + 0.5 * bg
+    mat[1:] /= mat[1:].sum(1, keepdims=True)
+    t = np.zeros((M + 1, 7))
+    mi = rng.uniform(0.005, 0.025, M + 1)
+    md = rng.uniform(0.005, 0.025, M + 1)
+    t[:, 0], t[:, 1], t[:, 2] = 1.0 - mi - md, mi, md
+    ii = rng.uniform(0.3, 0.5, M + 1)
+    t[:, 3], t[:, 4] = 1.0 - ii, ii
+    dd = rng.uniform(0.25, 0.45, M + 1)
+    t[:, 5], t[:, 6] = 1.0 - dd, dd
+    t[M, 0:3] = [1.0 - mi[M], mi[M], 0.0]
+    t[M, 5:7] = [1.0, 0.0]
+    t[0, 5:7] = [1.0, 0.0]
+    ins = np.tile(bg, (M + 1, 1))
+    return finish_hmm(name, abc, mat, ins, t)
+
+
+def busco_lengths(n: int, rng: np.random.Generator, mu: float = 420.0, sigma: float = 0.5, lo: int = 100,
+                  hi: int = 2000) -> np.ndarray:
+    return np.clip(np.rint(rng.lognormal(np.log(mu), sigma, n)), lo, hi).astype(int)
+
+
+def sample_protein(hmm: HMM, rng: np.random.Generator, start: int = 1, end: int | None = None) -> str:
+    """Emit match states start..end of the profile (no indels) -> a homologous fragment."""
+    end = end or hmm.M
+    p = np.exp(-hmm.mat[start:end + 1])
+    p /= p.sum(1, keepdims=True)
+    alphabet = AMINO if hmm.abc == "amino" else DNA
+    return "".join(alphabet[rng.choice(len(alphabet), p=row)] for row in p)
+
+
+def back_translate(prot: str) -> str:
+    return "".join(_CODON[a] for a in prot)
+
+
+def random_reads(n: int, length: int, rng: np.random.Generator, n_frac: float = 0.001) -> np.ndarray:
+    """(n, length) uint8 ASCII matrix of iid ACGT with a sprinkle of N."""
+    arr = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=(n, length))]
+    if n_frac > 0:
+        mask = rng.random((n, length)) < n_frac
+        arr = np.where(mask, np.uint8(ord("N")), arr)
+    return np.ascontiguousarray(arr)
+
+
+def plant_reads(reads: np.ndarray, hmms: list[HMM], frac: float, rng: np.random.Generator, sub_rate: float = 0.05):
+    """Overwrite a fraction of reads with back-translated profile fragments (random strand)."""
+    n, length = reads.shape
+    idx = rng.choice(n, size=int(n * frac), replace=False)
+    comp = bytes.maketrans(b"ACGT", b"TGCA")
+    for r in idx:
+        h = hmms[rng.integers(len(hmms))]
+        naa = length // 3
+        if h.M < naa + 2:
+            continue
+        s = int(rng.integers(1, h.M - naa + 1))
+        nt = back_translate(sample_protein(h, rng, s, s + naa - 1))
+        off = int(rng.integers(0, length - len(nt) + 1))
+        b = bytearray(reads[r].tobytes())
+        b[off:off + len(nt)] = nt.encode()
+        for i in np.nonzero(rng.random(length) < sub_rate)[0]:
+            b[i] = b"ACGT"[rng.integers(4)]
+        if rng.random() < 0.5:
+            b = bytearray(bytes(b).translate(comp)[::-1])
+        reads[r] = np.frombuffer(bytes(b), dtype=np.uint8)
+    return idx
