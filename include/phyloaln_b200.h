@@ -1,0 +1,146 @@
+/*
+ * phyloaln_b200.h -- C ABI of libphyloaln_b200.so, the B200 (sm_100a) replacement for
+ * the search hot path of PhyloAln.
+ *
+ * Plain C, caller-owned buffers, integer return codes (0 = ok, <0 = error; message via
+ * pa_last_error), no exceptions and no exit() across the boundary.  One pa_ctx per GPU;
+ * calls on one ctx must be serialised by the caller; contexts are independent.
+ *
+ * What each entry point replaces in the reference (/root/reference):
+ *   pa_add_hmm / pa_commit_hmms  the `ref_hmm/{g}.hmm` argument of the hmmsearch command line
+ *                                (lib/aln.py:664-666); parsing of the ASCII file stays in the
+ *                                Python host (phyloaln_b200/hmmio.py), arrays cross the ABI.
+ *   pa_load_reads                raw2target(): six-frame / codon translation or reverse
+ *                                complement of a chunk of reads (lib/aln.py:233-259) fused with
+ *                                HMMER's digitisation of all.target.fasta.
+ *   pa_load_proteins             hmmsearch reading an already-protein target file.
+ *   pa_search                    the `hmmsearch` child process per alignment
+ *                                (lib/aln.py:664-667): MSV/SSV -> bias -> Viterbi -> Forward ->
+ *                                domain definition -> optimal-accuracy alignment, for ALL
+ *                                loaded profiles against the loaded target chunk.
+ *   pa_get_hits                  the information extract_reads() pulls out of the hmmsearch
+ *                                text report via Bio.SearchIO (lib/aln.py:511-558).
+ *   pa_map_hits                  pretreat_hits()'s terminal trimming + read_hit.__init__'s
+ *                                column walk (lib/assemble.py:767-873, 13-306; extend_pos=0).
+ *   pa_score_all                 (no reference equivalent) raw filter scores for every
+ *                                (profile, target) pair: E-value calibration and parity tests.
+ */
+#ifndef PHYLOALN_B200_H
+#define PHYLOALN_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PA_ABI_VERSION 1
+#define PA_AMINO 0
+#define PA_DNA 1
+
+/* moltype of pa_load_reads */
+#define PA_TRANSLATE 0 /* prot / codon / dna_codon modes: translate frames            */
+#define PA_NUCLEOTIDE 1 /* dna modes: forward (+ reverse complement) nucleotide targets */
+
+typedef struct pa_ctx pa_ctx;
+
+typedef struct {
+  double F1, F2, F3; /* MSV, Viterbi, Forward filter P-value thresholds (0.02, 1e-3, 1e-5) */
+  int do_bias;       /* bias filter on (default 1; --nobias -> 0)                          */
+  int do_null2;      /* null2 score correction (default 1; --nonull2 -> 0)                 */
+  int do_max;        /* --max: all filters off                                             */
+  int reserved;
+} pa_opts;
+
+typedef struct {
+  int32_t hmm;    /* profile index (order of pa_add_hmm)                                   */
+  int32_t target; /* target index in the loaded chunk: read*nframes + frame               */
+  int32_t ndom_in_seq, dom_idx;
+  int32_t ienv, jenv, iali, jali, hmmfrom, hmmto; /* 1-based inclusive                      */
+  float envsc, domcorrection, oasc, dombias, dom_bits;
+  double dom_lnP;
+  float seq_bits, pre_bits, seqbias, fwdsc, nullsc;
+  double seq_lnP;
+  int32_t ali_off, ali_len; /* into the model/target string pools of pa_get_hits            */
+  int32_t multidomain_region;
+} pa_hit;
+
+typedef struct {
+  uint64_t n_pairs;    /* (profile, target) pairs entering the MSV stage                    */
+  uint64_t n_cells;    /* sum of L*M over those pairs                                       */
+  uint64_t n_past_ssv; /* pairs whose SSV score required the full MSV recurrence            */
+  uint64_t n_past_msv, n_past_bias, n_past_vit, n_past_fwd;
+  uint64_t n_domains;
+  uint64_t kernel_launches;                                /* CUDA kernels launched so far  */
+  float ms_translate, ms_msv, ms_bias, ms_vit, ms_fwd, ms_domain; /* last call, CUDA events */
+  float ms_h2d, ms_total;
+} pa_stats;
+
+/* per-hit column mapping result (pa_map_hits) */
+typedef struct {
+  int32_t keep;                 /* 0 = dropped by pretreat_hits                             */
+  int32_t qstart, qend;         /* reference columns after trimming                         */
+  int32_t ali_from, ali_to;     /* target coordinates after trimming (residue units)        */
+  int32_t start_trim, end_trim;
+  int32_t read_from, read_to;   /* 1-based nucleotide interval on the raw read              */
+  int32_t strand;               /* +1 / -1                                                  */
+  int32_t col_off, ncols;       /* into base/codon pools: ncols = qend-qstart+1             */
+  int32_t unmap_off, n_unmap;   /* into the unmapped-position pool                          */
+} pa_maprec;
+
+int pa_abi_version(void);
+pa_ctx *pa_create(int device, char *err, int errlen);
+void pa_destroy(pa_ctx *ctx);
+const char *pa_last_error(pa_ctx *ctx);
+int pa_set_opts(pa_ctx *ctx, const pa_opts *opts);
+
+/* Profiles. Arrays are the numbers of the HMMER3/f file: -ln(p), +inf for '*'.
+ * mat, ins: (M+1)*K row-major (row 0 = node-0 line; mat row 0 ignored); t: (M+1)*7 in file order
+ * MM MI MD IM II DM DD; compo: K values or NULL; cons: M consensus letters or NULL;
+ * evparam: {MSV mu, lambda, VITERBI mu, lambda, FORWARD tau, lambda}. Returns profile index. */
+int pa_add_hmm(pa_ctx *ctx, const char *name, int abc, int M, const double *mat, const double *ins,
+               const double *t, const double *compo, const char *cons, const float *evparam);
+int pa_set_evparam(pa_ctx *ctx, int hmm, const float *evparam);
+int pa_commit_hmms(pa_ctx *ctx);
+int pa_num_hmms(pa_ctx *ctx);
+
+/* Targets. nt: concatenated ASCII nucleotides, off[nreads+1] byte offsets (HOST memory).
+ * Produces nreads*nframes targets: TRANSLATE: frames pos1..3 (+ rev_pos1..3 unless no_reverse;
+ * only pos1 if codon_only); NUCLEOTIDE: read (+ reverse complement). Returns #targets or <0.
+ * -2: invalid nucleotide character (Biopython would raise TranslationError). */
+int64_t pa_load_reads(pa_ctx *ctx, const char *nt, const uint64_t *off, uint32_t nreads, int moltype,
+                      int gencode, int no_reverse, int codon_only);
+int64_t pa_load_proteins(pa_ctx *ctx, const char *aa, const uint64_t *off, uint32_t nseq, int abc);
+int pa_num_frames(pa_ctx *ctx);
+/* copy the device-resident target residues back as ASCII: out_off[ntargets+1], out (cap bytes) */
+int64_t pa_get_targets(pa_ctx *ctx, char *out, uint64_t cap, uint64_t *out_off);
+
+/* Search every committed profile against the loaded targets. Returns #hits (domains) or <0. */
+int64_t pa_search(pa_ctx *ctx);
+int64_t pa_get_hits(pa_ctx *ctx, pa_hit *hits, int64_t cap, char *model_pool, char *target_pool,
+                    int64_t poolcap);
+int64_t pa_hit_pool_bytes(pa_ctx *ctx); /* bytes needed for each string pool of pa_get_hits */
+int pa_get_stats(pa_ctx *ctx, pa_stats *st);
+
+/* Raw filter scores (nats) of profile `hmm` for all loaded targets; any output may be NULL.
+ * msv_raw: final xJ byte (-1 overflow); vit_raw: final xC word (32767 overflow). */
+int pa_score_all(pa_ctx *ctx, int hmm, float *msv, int32_t *msv_raw, float *vit, int32_t *vit_raw,
+                 float *fwd, float *bias);
+
+/* Hit -> reference-column mapping (extend_pos = 0). For hit h: model/aligned strings (PhyloAln
+ * form: upper case, '-' for gaps) at ali_off[h]..ali_off[h+1]; raw read nucleotides at
+ * read_off[h]..; hmm_from/to, ali_from/to 1-based; frame 0..2 or -1 (nucleotide mode);
+ * strand +1 / -1 ('rev'). site_freq: per hit pointer index into comp tables:
+ * comp[(comp_off[h] + (col-1))*32 + sym] = count of symbol `sym` (A=0..Z=25, '-'=26,'*'=27)
+ * in reference column col; outputs rec[nhits] and pools (base per column, 3 nt per column,
+ * unmapped 1-based read positions). */
+int pa_map_hits(pa_ctx *ctx, int32_t nhits, const char *model, const char *aligned, const int64_t *ali_off,
+                const char *reads, const int64_t *read_off, const int32_t *hmm_from, const int32_t *hmm_to,
+                const int32_t *ali_from, const int32_t *ali_to, const int32_t *frame, const int32_t *strand,
+                const int32_t *comp, const int64_t *comp_off, const int32_t *ncols_ref, int trim_pos,
+                double pos_freq, pa_maprec *rec, char *base_pool, char *codon_pool, int32_t *unmap_pool,
+                int64_t pool_cols_cap, int64_t unmap_cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

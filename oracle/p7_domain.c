@@ -134,7 +134,7 @@ int p7d_rescore_envelope(const ORC_PROFILE *p, const uint8_t *dsq, int L, int ie
   float *oE = (float *)malloc(sizeof(float) * (Ld + 1)), *oN = (float *)malloc(sizeof(float) * (Ld + 1));
   float *oJ = (float *)malloc(sizeof(float) * (Ld + 1)), *oB = (float *)malloc(sizeof(float) * (Ld + 1));
   float *oC = (float *)malloc(sizeof(float) * (Ld + 1));
-  for (size_t z = 0; z < W; z++) fx.M[z] = fx.I[z] = fx.D[z] = 0.0f;
+  for (size_t z = 0; z < W; z++) fx.M[z] = fx.I[z] = fx.D[z] = -INFINITY; /* row 0: no residue yet */
   oN[0] = 0.0f;
   oB[0] = 0.0f;
   oE[0] = oJ[0] = oC[0] = -INFINITY;

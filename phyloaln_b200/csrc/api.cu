@@ -1,0 +1,612 @@
+// api.cu -- C ABI of libphyloaln_b200.so (see include/phyloaln_b200.h) and the host-side
+// orchestration of the kernels in kernels.cuh / domain.cuh / mapping.cuh.
+//
+// Flow of pa_search for one resident chunk of targets and ALL committed profiles (the reference
+// instead runs one hmmsearch process per profile over all targets, lib/aln.py:664-667):
+//   msv_kernel<Q> (every pair)  -> Pass1 list  -> bias_kernel -> Pass2 list -> vit_kernel ->
+//   Pass2 list -> fwd_kernel -> Pass4 list -> domain_kernel -> domain records -> host scoring.
+// Lists are compacted with atomics between stages; capacity overflow is reported as an error
+// (-3) so the caller can shrink the chunk -- there is no CPU fallback anywhere.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/phyloaln_b200.h"
+#include "kernels.cuh"
+#include "domain.cuh"
+#include "mapping.cuh"
+#include "profile.hpp"
+
+using namespace pa;
+
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) {                                                                       \
+      char b_[512];                                                                                \
+      snprintf(b_, sizeof(b_), "%s:%d: %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+      ctx->err = b_;                                                                               \
+      return -1;                                                                                   \
+    }                                                                                              \
+  } while (0)
+
+template <class T>
+struct DevBuf {
+  T *p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = n + n / 8 + 64;
+    cudaError_t e = cudaMalloc((void **)&p, want * sizeof(T));
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+struct pa_ctx {
+  int device = 0;
+  std::string err;
+  pa_opts opts{0.02, 1e-3, 1e-5, 1, 1, 0, 0};
+  cudaStream_t stream = nullptr;
+  int num_sms = 148;
+  size_t smem_optin = 0;
+
+  std::vector<HostProfile> hmms;
+  bool committed = false;
+  std::vector<DevHmm> h_dev;
+  DevBuf<DevHmm> d_hmms;
+  DevBuf<uint32_t> d_msv;
+  DevBuf<int> d_vit;
+  DevBuf<float> d_fwd;
+  DevBuf<int> d_hmm_lists;
+  std::map<int, std::pair<int, int>> q_groups;  // Q -> (offset, count) in d_hmm_lists
+  int maxB = 1, maxM = 1;
+
+  // targets
+  DevBuf<char> d_nt;
+  DevBuf<unsigned long long> d_ntoff;
+  DevBuf<uint8_t> d_dsq;
+  DevBuf<uint32_t> d_toff, d_tlen;
+  DevBuf<uint16_t> d_lidx;
+  DevBuf<uint8_t> d_codon;
+  DevBuf<int> d_flag;
+  std::vector<uint32_t> h_tlen;
+  uint32_t ntargets = 0;
+  int nframes = 1;
+  int target_abc = 0;
+  int maxL = 0;
+  unsigned long long total_res = 0;
+
+  // per-length tables
+  std::vector<int> h_L;
+  DevBuf<int> d_L;
+  DevBuf<float> d_nullsc, d_biasA, d_biasB;
+  DevBuf<uint8_t> d_tjb;
+  DevBuf<int16_t> d_xwmove, d_thrJ;
+  DevBuf<uint16_t> d_L2li;
+  int nL = 0;
+
+  // stage lists
+  DevBuf<Pass1> d_p1;
+  DevBuf<Pass2> d_p2a, d_p2b;
+  DevBuf<Pass4> d_p4;
+  DevBuf<unsigned long long> d_counters;  // [0]=p1 [1]=p2a [2]=p2b [3]=p4 [4]=ssv cand [5..] domain
+  DomainBufs dom;
+
+  std::vector<pa_hit> hits;
+  std::string model_pool, target_pool;
+  pa_stats stats{};
+};
+
+static Targets make_targets(pa_ctx *ctx) {
+  Targets t;
+  t.dsq = ctx->d_dsq.p;
+  t.off = ctx->d_toff.p;
+  t.len = ctx->d_tlen.p;
+  t.lidx = ctx->d_lidx.p;
+  t.n = ctx->ntargets;
+  return t;
+}
+static LenTabs make_lentabs(pa_ctx *ctx) {
+  LenTabs l;
+  l.L = ctx->d_L.p;
+  l.nullsc = ctx->d_nullsc.p;
+  l.tjb = ctx->d_tjb.p;
+  l.xw_move = ctx->d_xwmove.p;
+  l.biasA = ctx->d_biasA.p;
+  l.biasB = ctx->d_biasB.p;
+  l.n = ctx->nL;
+  return l;
+}
+
+extern "C" int pa_abi_version(void) { return PA_ABI_VERSION; }
+
+extern "C" pa_ctx *pa_create(int device, char *err, int errlen) {
+  auto fail = [&](const char *what, cudaError_t e) -> pa_ctx * {
+    if (err && errlen > 0) snprintf(err, errlen, "%s: %s", what, cudaGetErrorString(e));
+    return nullptr;
+  };
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) return fail("no CUDA device (this library has no CPU fallback)", e);
+  if (device < 0 || device >= ndev) return fail("bad device index", cudaErrorInvalidDevice);
+  if ((e = cudaSetDevice(device)) != cudaSuccess) return fail("cudaSetDevice", e);
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return fail("cudaGetDeviceProperties", e);
+  if (prop.major < 9) {
+    if (err && errlen > 0) snprintf(err, errlen, "device %d is sm_%d%d; DPX kernels need sm_100a (B200)", device, prop.major, prop.minor);
+    return nullptr;
+  }
+  pa_ctx *ctx = new pa_ctx();
+  ctx->device = device;
+  ctx->num_sms = prop.multiProcessorCount;
+  ctx->smem_optin = prop.sharedMemPerBlockOptin;
+  if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+    delete ctx;
+    return fail("cudaStreamCreate", e);
+  }
+  return ctx;
+}
+
+extern "C" void pa_destroy(pa_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  ctx->d_hmms.release(); ctx->d_msv.release(); ctx->d_vit.release(); ctx->d_fwd.release(); ctx->d_hmm_lists.release();
+  ctx->d_nt.release(); ctx->d_ntoff.release(); ctx->d_dsq.release(); ctx->d_toff.release(); ctx->d_tlen.release();
+  ctx->d_lidx.release(); ctx->d_codon.release(); ctx->d_flag.release();
+  ctx->d_L.release(); ctx->d_nullsc.release(); ctx->d_biasA.release(); ctx->d_biasB.release(); ctx->d_tjb.release();
+  ctx->d_xwmove.release(); ctx->d_thrJ.release(); ctx->d_L2li.release();
+  ctx->d_p1.release(); ctx->d_p2a.release(); ctx->d_p2b.release(); ctx->d_p4.release(); ctx->d_counters.release();
+  ctx->dom.release();
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+extern "C" const char *pa_last_error(pa_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+extern "C" int pa_set_opts(pa_ctx *ctx, const pa_opts *o) {
+  if (!ctx || !o) return -1;
+  ctx->opts = *o;
+  if (ctx->committed) {  // thresholds live in DevHmm: refresh
+    ctx->committed = false;
+    return pa_commit_hmms(ctx);
+  }
+  return 0;
+}
+
+extern "C" int pa_add_hmm(pa_ctx *ctx, const char *name, int abc, int M, const double *mat, const double *ins,
+                          const double *t, const double *compo, const char *cons, const float *evparam) {
+  if (!ctx) return -1;
+  if (M < 1 || M > 2048) { ctx->err = "profile length must be 1..2048"; return -2; }
+  if (abc != PA_AMINO && abc != PA_DNA) { ctx->err = "unknown alphabet"; return -2; }
+  if (!ctx->hmms.empty() && ctx->hmms[0].abc != abc) { ctx->err = "all profiles of a context must share one alphabet"; return -2; }
+  if (ctx->hmms.size() >= 65535) { ctx->err = "too many profiles (max 65535)"; return -2; }
+  HostProfile hp;
+  hp.from_file_numbers(name, abc, M, mat, ins, t, compo, cons, evparam);
+  hp.configure();
+  ctx->hmms.push_back(std::move(hp));
+  ctx->committed = false;
+  return (int)ctx->hmms.size() - 1;
+}
+
+extern "C" int pa_set_evparam(pa_ctx *ctx, int h, const float *ev) {
+  if (!ctx || h < 0 || h >= (int)ctx->hmms.size()) return -1;
+  memcpy(ctx->hmms[h].ev, ev, sizeof(float) * 6);
+  ctx->hmms[h].has_stats = true;
+  ctx->committed = false;
+  return 0;
+}
+
+extern "C" int pa_num_hmms(pa_ctx *ctx) { return ctx ? (int)ctx->hmms.size() : -1; }
+
+// word position of (q, lane) inside one striped MSV row of Q*32 words (see msv_load_row)
+static inline int msv_word_pos(int Q, int q, int lane) {
+  const int N4 = Q / 4, R2 = (Q % 4) >= 2 ? 1 : 0;
+  if (q < 4 * N4) return (q / 4) * 128 + lane * 4 + (q % 4);
+  if (R2 && q < 4 * N4 + 2) return N4 * 128 + lane * 2 + (q - 4 * N4);
+  return N4 * 128 + R2 * 64 + lane;
+}
+
+extern "C" int pa_commit_hmms(pa_ctx *ctx) {
+  if (!ctx) return -1;
+  cudaSetDevice(ctx->device);
+  const int nh = (int)ctx->hmms.size();
+  if (nh == 0) { ctx->err = "no profiles"; return -2; }
+  std::vector<uint32_t> msv;
+  std::vector<int> vit;
+  std::vector<float> fwd;
+  ctx->h_dev.assign(nh, DevHmm{});
+  ctx->maxB = 1;
+  ctx->maxM = 1;
+  std::map<int, std::vector<int>> byQ;
+  const bool maxmode = ctx->opts.do_max != 0;
+  for (int h = 0; h < nh; h++) {
+    const HostProfile &hp = ctx->hmms[h];
+    if (!hp.has_stats) { ctx->err = "profile '" + hp.name + "' has no STATS LOCAL (uncalibrated)"; return -2; }
+    DevHmm &d = ctx->h_dev[h];
+    const int M = hp.M, Kp = hp.Kp;
+    d.M = M;
+    d.abc = hp.abc;
+    d.nrows = Kp;
+    d.Q = (M + 63) / 64;
+    d.B = (M + 31) / 32;
+    ctx->maxB = std::max(ctx->maxB, d.B);
+    ctx->maxM = std::max(ctx->maxM, M);
+    byQ[d.Q].push_back(h);
+    d.tbm = hp.tbm_b; d.tec = hp.tec_b; d.bias = hp.bias_b; d.base = hp.base_b;
+    d.base_w = hp.base_w; d.xw_E = hp.xw_E; d.scale_b = hp.scale_b; d.scale_w = hp.scale_w;
+    const double F1 = maxmode ? 1.0 : ctx->opts.F1, F2 = maxmode ? 1.0 : ctx->opts.F2, F3 = maxmode ? 1.0 : ctx->opts.F3;
+    d.thrF1 = gumbel_threshold(F1, hp.ev[0], hp.ev[1]);
+    d.thrF2m = gumbel_threshold(F2, hp.ev[0], hp.ev[1]);
+    d.thrF2v = gumbel_threshold(F2, hp.ev[2], hp.ev[3]);
+    d.thrF3 = exp_threshold(F3, hp.ev[4], hp.ev[5]);
+    const float L0 = 400.0f, L1 = (float)M / 8.0f;
+    d.t00 = L0 / (L0 + 1.0f); d.t01 = 1.0f / (L0 + 1.0f);
+    d.t10 = 1.0f / (L1 + 1.0f); d.t11 = L1 / (L1 + 1.0f);
+    memcpy(d.eo1, hp.eo1, sizeof(d.eo1));
+    memcpy(d.ev, hp.ev, sizeof(d.ev));
+
+    // ---- MSV striped s16x2 table: delta = bias - rbv, dead padding beyond M
+    const int Q = d.Q, roww = Q * 32;
+    while (msv.size() % 4) msv.push_back(0);
+    d.msv_off = msv.size();
+    msv.resize(msv.size() + (size_t)Kp * roww, 0);
+    for (int x = 0; x < Kp; x++)
+      for (int q = 0; q < Q; q++)
+        for (int lane = 0; lane < 32; lane++) {
+          int16_t half[2];
+          for (int hf = 0; hf < 2; hf++) {
+            const int cell = (2 * lane + hf) * Q + q, k = cell + 1;
+            half[hf] = k <= M ? (int16_t)((int)hp.bias_b - (int)hp.rbv[(size_t)x * (M + 1) + k]) : (int16_t)PA_MSV_DEAD;
+          }
+          msv[d.msv_off + (size_t)x * roww + msv_word_pos(Q, q, lane)] = (uint32_t)(uint16_t)half[0] | ((uint32_t)(uint16_t)half[1] << 16);
+        }
+
+    // ---- lane-blocked tables [j][lane], k = lane*B + j + 1
+    const int B = d.B, W = B * 32;
+    auto cellk = [&](int c) { return (c % 32) * B + (c / 32) + 1; };
+    while (vit.size() % 4) vit.push_back(0);
+    d.vit_off = vit.size();
+    vit.resize(vit.size() + (size_t)W * (4 + 4 + 1 + Kp), PA_NEG16);
+    int *vA = vit.data() + d.vit_off, *vB = vA + 4 * W, *vps = vB + 4 * W, *vem = vps + W;
+    for (int c = 0; c < W; c++) {
+      const int k = cellk(c);
+      if (k <= M) {
+        const int16_t *tp = &hp.twv[(size_t)(k - 1) * 8], *tk = &hp.twv[(size_t)k * 8];
+        vA[4 * c + 0] = tp[T_BM]; vA[4 * c + 1] = tp[T_MM]; vA[4 * c + 2] = tp[T_IM]; vA[4 * c + 3] = tp[T_DM];
+        vB[4 * c + 0] = tp[T_MD]; vB[4 * c + 1] = tp[T_DD]; vB[4 * c + 2] = tk[T_MI]; vB[4 * c + 3] = tk[T_II];
+        for (int x = 0; x < Kp; x++) vem[(size_t)x * W + c] = hp.rwv[(size_t)x * (M + 1) + k];
+      }
+    }
+    for (int lane = 0; lane < 32; lane++) {  // in-lane prefix sums of DD(k-1)
+      int s = 0;
+      for (int j = 0; j < B; j++) {
+        const int c = j * 32 + lane;
+        s += vB[4 * c + 1];
+        vps[c] = s;
+      }
+    }
+    while (fwd.size() % 4) fwd.push_back(0.f);
+    d.fwd_off = fwd.size();
+    fwd.resize(fwd.size() + (size_t)W * (16 + Kp), 0.0f);
+    float *fA = fwd.data() + d.fwd_off, *fB = fA + 4 * W, *bA = fB + 4 * W, *bB = bA + 4 * W, *fem = bB + 4 * W;
+    for (int c = 0; c < W; c++) {
+      const int k = cellk(c);
+      if (k <= M) {
+        const float *tp = &hp.tfv[(size_t)(k - 1) * 8], *tk = &hp.tfv[(size_t)k * 8];
+        fA[4 * c + 0] = tp[T_BM]; fA[4 * c + 1] = tp[T_MM]; fA[4 * c + 2] = tp[T_IM]; fA[4 * c + 3] = tp[T_DM];
+        fB[4 * c + 0] = tp[T_MD]; fB[4 * c + 1] = tp[T_DD]; fB[4 * c + 2] = tk[T_MI]; fB[4 * c + 3] = tk[T_II];
+        bA[4 * c + 0] = tk[T_MM]; bA[4 * c + 1] = tk[T_MI]; bA[4 * c + 2] = tk[T_MD]; bA[4 * c + 3] = tk[T_IM];
+        bB[4 * c + 0] = tk[T_II]; bB[4 * c + 1] = tk[T_DM]; bB[4 * c + 2] = tk[T_DD]; bB[4 * c + 3] = tp[T_BM];
+        for (int x = 0; x < Kp; x++) fem[(size_t)x * W + c] = hp.rfv[(size_t)x * (M + 1) + k];
+      }
+    }
+  }
+  CK(ctx->d_hmms.ensure(nh));
+  CK(cudaMemcpy(ctx->d_hmms.p, ctx->h_dev.data(), sizeof(DevHmm) * nh, cudaMemcpyHostToDevice));
+  CK(ctx->d_msv.ensure(msv.size()));
+  CK(cudaMemcpy(ctx->d_msv.p, msv.data(), msv.size() * 4, cudaMemcpyHostToDevice));
+  CK(ctx->d_vit.ensure(vit.size()));
+  CK(cudaMemcpy(ctx->d_vit.p, vit.data(), vit.size() * 4, cudaMemcpyHostToDevice));
+  CK(ctx->d_fwd.ensure(fwd.size()));
+  CK(cudaMemcpy(ctx->d_fwd.p, fwd.data(), fwd.size() * 4, cudaMemcpyHostToDevice));
+  std::vector<int> lists;
+  ctx->q_groups.clear();
+  for (auto &kv : byQ) {
+    ctx->q_groups[kv.first] = {(int)lists.size(), (int)kv.second.size()};
+    lists.insert(lists.end(), kv.second.begin(), kv.second.end());
+  }
+  CK(ctx->d_hmm_lists.ensure(lists.size()));
+  CK(cudaMemcpy(ctx->d_hmm_lists.p, lists.data(), lists.size() * 4, cudaMemcpyHostToDevice));
+  CK(ctx->d_counters.ensure(16));
+  ctx->committed = true;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// targets
+// ---------------------------------------------------------------------------------------------
+static const char *kGenCodes[][2] = {
+    {"1", "FFLLSSSSYY**CC*WLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG"},
+    {"2", "FFLLSSSSYY**CCWWLLLLPPPPHHQQRRRRIIMMTTTTNNKKSS**VVVVAAAADDEEGGGG"},
+    {"3", "FFLLSSSSYY**CCWWTTTTPPPPHHQQRRRRIIMMTTTTNNKKSSRRVVVVAAAADDEEGGGG"},
+    {"4", "FFLLSSSSYY**CCWWLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG"},
+    {"5", "FFLLSSSSYY**CCWWLLLLPPPPHHQQRRRRIIMMTTTTNNKKSSSSVVVVAAAADDEEGGGG"},
+    {"6", "FFLLSSSSYYQQCC*WLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG"},
+    {"9", "FFLLSSSSYY**CCWWLLLLPPPPHHQQRRRRIIIMTTTTNNNKSSSSVVVVAAAADDEEGGGG"},
+    {"10", "FFLLSSSSYY**CCCWLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG"},
+    {"11", "FFLLSSSSYY**CC*WLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG"},
+    {"12", "FFLLSSSSYY**CC*WLLLSPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG"},
+    {"13", "FFLLSSSSYY**CCWWLLLLPPPPHHQQRRRRIIMMTTTTNNKKSSGGVVVVAAAADDEEGGGG"},
+    {"14", "FFLLSSSSYYY*CCWWLLLLPPPPHHQQRRRRIIIMTTTTNNNKSSSSVVVVAAAADDEEGGGG"},
+    {"15", "FFLLSSSSYY*QCC*WLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG"},
+    {"16", "FFLLSSSSYY*LCC*WLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG"},
+    {"21", "FFLLSSSSYY**CCWWLLLLPPPPHHQQRRRRIIMMTTTTNNNKSSSSVVVVAAAADDEEGGGG"},
+    {"22", "FFLLSS*SYY*LCC*WLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG"},
+    {"23", "FF*LSSSSYY**CC*WLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG"},
+    {"24", "FFLLSSSSYY**CCWWLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSSKVVVVAAAADDEEGGGG"},
+    {"25", "FFLLSSSSYY**CCGWLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG"},
+    {"26", "FFLLSSSSYY**CC*WLLLAPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG"},
+};
+
+// distinct-length tables + lidx after d_tlen is known; h_tlen must be filled
+static int build_length_tables(pa_ctx *ctx) {
+  const uint32_t n = ctx->ntargets;
+  int maxL = 0;
+  for (uint32_t i = 0; i < n; i++) maxL = std::max(maxL, (int)ctx->h_tlen[i]);
+  ctx->maxL = maxL;
+  std::vector<uint8_t> present((size_t)maxL + 1, 0);
+  unsigned long long tot = 0;
+  for (uint32_t i = 0; i < n; i++) { present[ctx->h_tlen[i]] = 1; tot += ctx->h_tlen[i]; }
+  ctx->total_res = tot;
+  std::vector<uint16_t> L2li((size_t)maxL + 1, 0);
+  ctx->h_L.clear();
+  for (int L = 0; L <= maxL; L++)
+    if (present[L]) {
+      if (ctx->h_L.size() >= 65535) { ctx->err = "more than 65535 distinct target lengths in one chunk"; return -2; }
+      L2li[L] = (uint16_t)ctx->h_L.size();
+      ctx->h_L.push_back(L);
+    }
+  const int nL = ctx->nL = (int)ctx->h_L.size();
+  std::vector<float> nullsc(nL), bA(nL), bB(nL);
+  std::vector<uint8_t> tjb(nL);
+  std::vector<int16_t> xw(nL);
+  const float scale_b = (float)(3.0 / 0.69314718055994529), scale_w = (float)(500.0 / 0.69314718055994529);
+  for (int i = 0; i < nL; i++) {
+    const int L = ctx->h_L[i];
+    nullsc[i] = null1_score(L);
+    tjb[i] = unbiased_byteify(scale_b, logf(3.0f / (float)(L + 3)));
+    const float pmove = (2.0f + 1.0f) / ((float)L + 2.0f + 1.0f);
+    xw[i] = wordify(scale_w, logf(pmove));
+    const float p1 = (float)L / (float)(L + 1);
+    bA[i] = (float)L * logf(p1);
+    bB[i] = logf((float)(1.0 - (double)p1));
+  }
+  CK(ctx->d_L.ensure(nL)); CK(ctx->d_nullsc.ensure(nL)); CK(ctx->d_biasA.ensure(nL)); CK(ctx->d_biasB.ensure(nL));
+  CK(ctx->d_tjb.ensure(nL)); CK(ctx->d_xwmove.ensure(nL)); CK(ctx->d_L2li.ensure((size_t)maxL + 1));
+  CK(cudaMemcpyAsync(ctx->d_L.p, ctx->h_L.data(), nL * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->d_nullsc.p, nullsc.data(), nL * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->d_biasA.p, bA.data(), nL * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->d_biasB.p, bB.data(), nL * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->d_tjb.p, tjb.data(), nL, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->d_xwmove.p, xw.data(), nL * 2, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->d_L2li.p, L2li.data(), ((size_t)maxL + 1) * 2, cudaMemcpyHostToDevice, ctx->stream));
+  CK(ctx->d_lidx.ensure(n));
+  lidx_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_tlen.p, ctx->d_L2li.p, ctx->d_lidx.p, n);
+  ctx->stats.kernel_launches++;
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+extern "C" int64_t pa_load_reads(pa_ctx *ctx, const char *nt, const uint64_t *off, uint32_t nreads, int moltype,
+                                 int gencode, int no_reverse, int codon_only) {
+  if (!ctx) return -1;
+  cudaSetDevice(ctx->device);
+  const uint64_t total = off[nreads];
+  if (2 * total + 32ull * nreads + 64 >= (1ull << 32)) { ctx->err = "chunk too large (2*nt + 32*reads must stay below 4 GiB)"; return -2; }
+  int nfwd, nrev;
+  if (moltype == PA_TRANSLATE) {
+    nfwd = codon_only ? 1 : 3;
+    nrev = no_reverse ? 0 : 3;
+    ctx->target_abc = PA_AMINO;
+  } else {
+    nfwd = 1;
+    nrev = no_reverse ? 0 : 1;
+    ctx->target_abc = PA_DNA;
+  }
+  const int nframes = nfwd + nrev;
+  const uint64_t ntargets64 = (uint64_t)nreads * nframes;
+  if (ntargets64 >= (1ull << 32)) { ctx->err = "too many targets in one chunk"; return -2; }
+  uint8_t tab64[64];
+  memset(tab64, 26, 64);
+  if (moltype == PA_TRANSLATE) {
+    const char *aa = nullptr;
+    char key[16];
+    snprintf(key, sizeof(key), "%d", gencode);
+    for (auto &g : kGenCodes)
+      if (!strcmp(g[0], key)) aa = g[1];
+    if (!aa) { ctx->err = "unsupported genetic code table"; return -2; }
+    const char *syms = "ACDEFGHIKLMNPQRSTVWY-BJZOUX*";
+    for (int i = 0; i < 64; i++) tab64[i] = (uint8_t)(strchr(syms, aa[i]) - syms);
+  }
+  cudaEvent_t e0, e1, e2;
+  cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2);
+  cudaEventRecord(e0, ctx->stream);
+  CK(ctx->d_nt.ensure(total + 16));
+  CK(ctx->d_ntoff.ensure((size_t)nreads + 1));
+  CK(ctx->d_codon.ensure(64));
+  CK(ctx->d_flag.ensure(4));
+  CK(cudaMemcpyAsync(ctx->d_nt.p, nt, total, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->d_ntoff.p, off, ((size_t)nreads + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->d_codon.p, tab64, 64, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemsetAsync(ctx->d_flag.p, 0, 16, ctx->stream));
+  const size_t outbytes = ((2 * total + 3) & ~3ull) + 32ull * nreads + 64;
+  CK(ctx->d_dsq.ensure(outbytes));
+  CK(ctx->d_toff.ensure(ntargets64 + 1));
+  CK(ctx->d_tlen.ensure(ntargets64 + 1));
+  cudaEventRecord(e1, ctx->stream);
+  const int grid = std::min<uint64_t>((nreads + 7) / 8, (uint64_t)ctx->num_sms * 8);
+  if (nreads)
+    translate_kernel<<<std::max(grid, 1), 256, 0, ctx->stream>>>(ctx->d_nt.p, ctx->d_ntoff.p, nreads, moltype == PA_TRANSLATE ? 0 : 1,
+                                                               nfwd, nrev, ctx->d_codon.p, ctx->d_dsq.p, ctx->d_toff.p,
+                                                               ctx->d_tlen.p, ctx->d_flag.p);
+  ctx->stats.kernel_launches++;
+  cudaEventRecord(e2, ctx->stream);
+  int flag = 0;
+  CK(cudaMemcpyAsync(&flag, ctx->d_flag.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  // host-side target lengths (same arithmetic as the kernel) while the GPU works
+  ctx->h_tlen.resize(ntargets64);
+  for (uint32_t r = 0; r < nreads; r++) {
+    const int L = (int)(off[r + 1] - off[r]);
+    for (int f = 0; f < nframes; f++) {
+      int len;
+      if (moltype == PA_TRANSLATE) {
+        const int j = f >= nfwd ? f - nfwd : f;
+        len = (L - j) >= 3 ? (L - j) / 3 : 0;
+      } else
+        len = L;
+      ctx->h_tlen[(size_t)r * nframes + f] = (uint32_t)len;
+    }
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaGetLastError());
+  float ms;
+  cudaEventElapsedTime(&ms, e0, e1); ctx->stats.ms_h2d = ms;
+  cudaEventElapsedTime(&ms, e1, e2); ctx->stats.ms_translate = ms;
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+  if (flag) { ctx->err = "invalid nucleotide character in reads (Biopython would raise TranslationError)"; return -2; }
+  ctx->ntargets = (uint32_t)ntargets64;
+  ctx->nframes = nframes;
+  if (build_length_tables(ctx) != 0) return -1;
+  return (int64_t)ntargets64;
+}
+
+extern "C" int64_t pa_load_proteins(pa_ctx *ctx, const char *aa, const uint64_t *off, uint32_t nseq, int abc) {
+  if (!ctx) return -1;
+  cudaSetDevice(ctx->device);
+  const uint64_t total = off[nseq];
+  if (total + 4ull * nseq + 64 >= (1ull << 32)) { ctx->err = "chunk too large"; return -2; }
+  std::vector<uint32_t> toff((size_t)nseq + 1);
+  ctx->h_tlen.resize(nseq);
+  uint32_t pos = 0;
+  for (uint32_t i = 0; i < nseq; i++) {
+    toff[i] = pos;
+    const uint32_t L = (uint32_t)(off[i + 1] - off[i]);
+    ctx->h_tlen[i] = L;
+    pos += (L + 3) & ~3u;
+  }
+  toff[nseq] = pos;
+  CK(ctx->d_nt.ensure(total + 16));
+  CK(ctx->d_ntoff.ensure((size_t)nseq + 1));
+  CK(ctx->d_dsq.ensure((size_t)pos + 64));
+  CK(ctx->d_toff.ensure((size_t)nseq + 1));
+  CK(ctx->d_tlen.ensure((size_t)nseq + 1));
+  CK(cudaMemcpyAsync(ctx->d_nt.p, aa, total, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->d_ntoff.p, off, ((size_t)nseq + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->d_toff.p, toff.data(), ((size_t)nseq + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->d_tlen.p, ctx->h_tlen.data(), (size_t)nseq * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemsetAsync(ctx->d_dsq.p, 0, (size_t)pos + 64, ctx->stream));
+  if (nseq) {
+    const int grid = std::min<uint64_t>((nseq + 7) / 8, (uint64_t)ctx->num_sms * 8);
+    digitize_kernel<<<std::max(grid, 1), 256, 0, ctx->stream>>>(ctx->d_nt.p, ctx->d_ntoff.p, ctx->d_toff.p, nseq, abc, ctx->d_dsq.p);
+    ctx->stats.kernel_launches++;
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaGetLastError());
+  ctx->ntargets = nseq;
+  ctx->nframes = 1;
+  ctx->target_abc = abc;
+  if (build_length_tables(ctx) != 0) return -1;
+  return nseq;
+}
+
+extern "C" int pa_num_frames(pa_ctx *ctx) { return ctx ? ctx->nframes : -1; }
+
+extern "C" int64_t pa_get_targets(pa_ctx *ctx, char *out, uint64_t cap, uint64_t *out_off) {
+  if (!ctx) return -1;
+  cudaSetDevice(ctx->device);
+  const uint32_t n = ctx->ntargets;
+  std::vector<uint32_t> toff(n);
+  if (n) CK(cudaMemcpy(toff.data(), ctx->d_toff.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  size_t bytes = 0;
+  for (uint32_t i = 0; i < n; i++) bytes = std::max<size_t>(bytes, (size_t)toff[i] + ctx->h_tlen[i]);
+  std::vector<uint8_t> dsq(bytes + 1);
+  if (bytes) CK(cudaMemcpy(dsq.data(), ctx->d_dsq.p, bytes, cudaMemcpyDeviceToHost));
+  const char *syms = Alphabet::get(ctx->target_abc).syms;
+  uint64_t pos = 0;
+  for (uint32_t i = 0; i < n; i++) {
+    out_off[i] = pos;
+    if (pos + ctx->h_tlen[i] > cap) { ctx->err = "pa_get_targets: output buffer too small"; return -3; }
+    for (uint32_t j = 0; j < ctx->h_tlen[i]; j++) out[pos + j] = syms[dsq[toff[i] + j]];
+    pos += ctx->h_tlen[i];
+  }
+  out_off[n] = pos;
+  return (int64_t)n;
+}
+
+// ---------------------------------------------------------------------------------------------
+// search
+// ---------------------------------------------------------------------------------------------
+template <int Q>
+static cudaError_t launch_msv(pa_ctx *ctx, MsvArgs &a, int nrows_max) {
+  const size_t smem = (size_t)nrows_max * Q * 32 * 4;
+  cudaError_t e = cudaFuncSetAttribute(msv_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  int bps = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, msv_kernel<Q>, 256, smem);
+  bps = std::max(1, bps);
+  const uint32_t ntiles = (a.tg.n + a.tile - 1) / a.tile;
+  const unsigned long long nitems = (unsigned long long)a.nlist * ntiles;
+  const int grid = (int)std::min<unsigned long long>(nitems, (unsigned long long)ctx->num_sms * bps);
+  if (grid > 0) msv_kernel<Q><<<grid, 256, smem, ctx->stream>>>(a);
+  ctx->stats.kernel_launches++;
+  return cudaGetLastError();
+}
+
+static cudaError_t dispatch_msv(pa_ctx *ctx, int Q, MsvArgs &a, int nrows) {
+  switch (Q) {
+#define C_(q) case q: return launch_msv<q>(ctx, a, nrows);
+    C_(1) C_(2) C_(3) C_(4) C_(5) C_(6) C_(7) C_(8) C_(9) C_(10) C_(11) C_(12) C_(13) C_(14) C_(15) C_(16)
+    C_(17) C_(18) C_(19) C_(20) C_(21) C_(22) C_(23) C_(24) C_(25) C_(26) C_(27) C_(28) C_(29) C_(30) C_(31) C_(32)
+#undef C_
+  }
+  return cudaErrorInvalidValue;
+}
+
+static int launch_thresholds(pa_ctx *ctx, int all_pass) {
+  const int nh = (int)ctx->hmms.size();
+  CK(ctx->d_thrJ.ensure((size_t)nh * ctx->nL));
+  const int n = nh * ctx->nL;
+  msv_threshold_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_hmms.p, nh, make_lentabs(ctx), ctx->d_thrJ.p, all_pass);
+  ctx->stats.kernel_launches++;
+  return 0;
+}
+
+static size_t warps_for_smem(pa_ctx *ctx, size_t per_warp) {
+  size_t budget = std::min<size_t>(ctx->smem_optin, 200 * 1024);
+  size_t w = budget / std::max<size_t>(per_warp, 1);
+  return std::max<size_t>(1, std::min<size_t>(8, w));
+}
+
+static int check_targets_ready(pa_ctx *ctx) {
+  if (!ctx->committed) { ctx->err = "profiles not committed (call pa_commit_hmms)"; return -2; }
+  if (ctx->ntargets == 0) return 0;
+  if (ctx->target_abc != ctx->hmms[0].abc) { ctx->err = "target alphabet does not match the profiles"; return -2; }
+  return 0;
+}
+
+#include "search_impl.inc"

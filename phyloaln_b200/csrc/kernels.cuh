@@ -1,0 +1,745 @@
+// kernels.cuh -- sm_100a kernels of the PhyloAln search hot path (filters).
+//
+//  translate_kernel   six-frame / codon translation or reverse complement + digitisation
+//                     (reference lib/aln.py:233-259; HBM-bound)
+//  msv_kernel<Q>      SSV pass in DPX s16x2 lanes (VIADDMNMX.S16x2.RELU + VIMNMX3.S16x2) with the
+//                     striped emission table in shared memory; pairs that could use the J state
+//                     or reach the F1 threshold are re-run inline with the exact unsigned-byte
+//                     MSV recurrence
+//  bias_kernel        2-state composition-bias filter (A.6)
+//  vit_kernel         Viterbi filter in exact signed-16 saturating semantics evaluated in s32 DPX
+//                     (VIADDMNMX with the -32768 clamp fused), parallel max-plus scan for D->D (A.5)
+//  fwd_kernel         Forward filter in scaled probability space, canonical 32-lane blocked
+//                     evaluation order (DESIGN.md "Canonical float order")
+//
+// All DP kernels: one warp per (profile, target) pair.  Lane l owns the contiguous model block
+// k = l*B+1 .. (l+1)*B, B = ceil(M/32); per-profile tables are stored [j][lane] so that every
+// table access of a warp is one fully coalesced 128/512-byte request.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace pa {
+
+#define PA_FULL 0xffffffffu
+#define PA_LN2 0.69314718055994529
+#define PA_MSV_DEAD (-20000)
+#define PA_NEG16 (-32768)
+#define PA_NEGBIG (-(1 << 29))
+#define PA_RESCALE 8192.0f
+
+struct DevHmm {
+  int M, Q, B, abc;             // Q: MSV words per lane; B = ceil(M/32)
+  int nrows;                    // Kp
+  unsigned long long msv_off;   // uint32 words into msv pool
+  unsigned long long vit_off;   // ints into vit pool: trA(int4) | trB(int4) | ps | em[Kp]
+  unsigned long long fwd_off;   // floats into fwd pool: trA | trB | bwA | bwB | em[Kp]
+  int tbm, tec, bias, base;
+  int base_w, xw_E;
+  float scale_b, scale_w;
+  float thrF1, thrF2m, thrF2v, thrF3;  // bit-score thresholds equivalent to P <= F
+  float t00, t01, t10, t11;            // bias-filter transitions
+  float eo1[32];
+  float ev[6];
+};
+
+struct Pass1 { uint32_t t; uint16_t h; int16_t xJ; };
+struct Pass2 { uint32_t t; uint16_t h; uint16_t flags; float filtersc; };  // flags bit0: needs Viterbi
+struct Pass4 { uint32_t t; uint16_t h; uint16_t pad; float filtersc; int fexp; float fmant; };
+
+struct Targets {
+  const uint8_t *dsq;        // digital residues
+  const uint32_t *off;       // byte offset of each target (4-byte aligned)
+  const uint32_t *len;       // residues
+  const uint16_t *lidx;      // index into the distinct-length tables
+  uint32_t n;
+};
+
+struct LenTabs {             // per distinct target length
+  const int *L;
+  const float *nullsc;
+  const uint8_t *tjb;        // MSV J->B byte cost
+  const int16_t *xw_move;    // Viterbi N->B / J->B / C->T word
+  const float *biasA;        // (float)L*logf(p1)        (bias-filter length terms, host libm)
+  const float *biasB;        // logf(1-p1)
+  int n;
+};
+
+// ---------------------------------------------------------------------------------------------
+// translation
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int nt_mask(uint8_t c) {  // bit: T=1 C=2 A=4 G=8; 0 invalid
+  switch (c & 0xDF) {                                  // upper-case
+    case 'T': case 'U': return 1;
+    case 'C': return 2;
+    case 'A': return 4;
+    case 'G': return 8;
+    case 'R': return 12;
+    case 'Y': return 3;
+    case 'M': return 6;
+    case 'K': return 9;
+    case 'S': return 10;
+    case 'W': return 5;
+    case 'H': return 7;
+    case 'B': return 11;
+    case 'V': return 14;
+    case 'D': return 13;
+    case 'N': return 15;
+    default: return 0;
+  }
+}
+__device__ __forceinline__ int comp_mask(int m) { return ((m & 1) << 2) | ((m & 4) >> 2) | ((m & 2) << 2) | ((m & 8) >> 2); }
+
+// digital amino codes: A0 C1 D2 E3 F4 G5 H6 I7 K8 L9 M10 N11 P12 Q13 R14 S15 T16 V17 W18 Y19 -20 B21 J22 Z23 O24 U25 X26 *27 ~28
+__device__ __forceinline__ int codon_code(int m0, int m1, int m2, const uint8_t *tab64) {
+  if (__popc(m0) == 1 && __popc(m1) == 1 && __popc(m2) == 1)
+    return tab64[(__ffs(m0) - 1) * 16 + (__ffs(m1) - 1) * 4 + (__ffs(m2) - 1)];
+  // ambiguous codon (Biopython rules)
+  uint32_t seen = 0;
+  int nstop = 0, ntot = 0;
+  for (int a = 0; a < 4; a++)
+    if (m0 >> a & 1)
+      for (int b = 0; b < 4; b++)
+        if (m1 >> b & 1)
+          for (int c = 0; c < 4; c++)
+            if (m2 >> c & 1) {
+              int r = tab64[a * 16 + b * 4 + c];
+              ntot++;
+              if (r == 27) nstop++;
+              else seen |= 1u << r;
+            }
+  if (nstop == ntot) return 27;
+  if (nstop > 0) return 26;
+  if (__popc(seen) == 1) return __ffs(seen) - 1;
+  if ((seen & ~((1u << 2) | (1u << 11))) == 0) return 21;  // D,N -> B
+  if ((seen & ~((1u << 3) | (1u << 13))) == 0) return 23;  // E,Q -> Z
+  if ((seen & ~((1u << 7) | (1u << 9))) == 0) return 22;   // I,L -> J
+  return 26;
+}
+// DNA digital codes "ACGT-RYMKSWHBVDN*~" from a T1 C2 A4 G8 mask
+__device__ __forceinline__ int dna_code(int m) {
+  const uint8_t tab[16] = {15, 3, 1, 6, 0, 10, 7, 11, 2, 8, 9, 12, 5, 14, 13, 15};
+  return tab[m];
+}
+
+__device__ __forceinline__ uint32_t target_base(unsigned long long ntoff, uint32_t r) {
+  return (uint32_t)(((2ull * ntoff + 3ull) & ~3ull) + 32ull * r);
+}
+
+// one warp per read
+__global__ void __launch_bounds__(256) translate_kernel(const char *__restrict__ nt, const unsigned long long *__restrict__ off,
+                                                        uint32_t nreads, int moltype, int nfwd, int nrev,
+                                                        const uint8_t *__restrict__ tab64, uint8_t *__restrict__ out,
+                                                        uint32_t *__restrict__ tgt_off, uint32_t *__restrict__ tgt_len,
+                                                        int *__restrict__ err) {
+  __shared__ uint8_t s_tab[64];
+  if (threadIdx.x < 64) s_tab[threadIdx.x] = tab64[threadIdx.x];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const int nframes = nfwd + nrev;
+  for (uint32_t r = blockIdx.x * wpb + wib; r < nreads; r += gridDim.x * wpb) {
+    const unsigned long long o = off[r];
+    const int L = (int)(off[r + 1] - o);
+    uint32_t base = target_base(o, r);
+    uint32_t pos = base;
+    if (moltype == 1) {  // nucleotide targets: read, then reverse complement
+      for (int f = 0; f < nframes; f++) {
+        for (int i = lane; i < L; i += 32) {
+          int m = nt_mask((uint8_t)nt[o + (f == 0 ? i : L - 1 - i)]);
+          if (m == 0) { atomicExch(err, 1); m = 15; }
+          if (f == 1) m = comp_mask(m);
+          out[pos + i] = (uint8_t)dna_code(m);
+        }
+        if (lane == 0) { tgt_off[(size_t)r * nframes + f] = pos; tgt_len[(size_t)r * nframes + f] = L; }
+        pos += (L + 3) & ~3;
+      }
+      continue;
+    }
+    for (int f = 0; f < nframes; f++) {
+      const bool rev = f >= nfwd;
+      const int j = rev ? f - nfwd : f;  // frame offset 0..2
+      const int naa = (L - j) >= 3 ? (L - j) / 3 : 0;
+      for (int c = lane; c < naa; c += 32) {
+        int p = j + 3 * c;
+        int m0, m1, m2;
+        if (!rev) {
+          m0 = nt_mask((uint8_t)nt[o + p]); m1 = nt_mask((uint8_t)nt[o + p + 1]); m2 = nt_mask((uint8_t)nt[o + p + 2]);
+        } else {
+          m0 = nt_mask((uint8_t)nt[o + L - 1 - p]); m1 = nt_mask((uint8_t)nt[o + L - 2 - p]); m2 = nt_mask((uint8_t)nt[o + L - 3 - p]);
+        }
+        if (m0 == 0 || m1 == 0 || m2 == 0) { atomicExch(err, 1); m0 = m1 = m2 = 15; }
+        if (rev) { m0 = comp_mask(m0); m1 = comp_mask(m1); m2 = comp_mask(m2); }
+        out[pos + c] = (uint8_t)codon_code(m0, m1, m2, s_tab);
+      }
+      if (lane == 0) { tgt_off[(size_t)r * nframes + f] = pos; tgt_len[(size_t)r * nframes + f] = naa; }
+      pos += (naa + 3) & ~3;
+    }
+  }
+}
+
+__global__ void lidx_kernel(const uint32_t *__restrict__ len, const uint16_t *__restrict__ L2li, uint16_t *__restrict__ lidx, uint32_t n) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) lidx[i] = L2li[len[i]];
+}
+
+// protein / pre-digitised targets: ASCII -> digital codes
+__global__ void digitize_kernel(const char *__restrict__ in, const unsigned long long *__restrict__ in_off,
+                                const uint32_t *__restrict__ tgt_off, uint32_t n, int abc, uint8_t *__restrict__ out) {
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  for (uint32_t s = blockIdx.x * wpb + wib; s < n; s += gridDim.x * wpb) {
+    unsigned long long o = in_off[s];
+    int L = (int)(in_off[s + 1] - o);
+    for (int i = lane; i < L; i += 32) {
+      uint8_t c = (uint8_t)in[o + i] & 0xDF;
+      int code;
+      if (abc == 0) {
+        const char *syms = "ACDEFGHIKLMNPQRSTVWY-BJZOUX";
+        code = 26;
+        if ((uint8_t)in[o + i] == '*') code = 27;
+        else
+          for (int q = 0; q < 27; q++)
+            if (syms[q] == (char)c) { code = q; break; }
+      } else {
+        int m = nt_mask(c);
+        code = dna_code(m == 0 ? 15 : m);
+      }
+      out[tgt_off[s] + i] = (uint8_t)code;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// SSV / MSV filter
+// ---------------------------------------------------------------------------------------------
+template <int Q>
+__device__ __forceinline__ void msv_load_row(const uint32_t *row, int lane, uint32_t (&d)[Q]) {
+  constexpr int N4 = Q / 4, R2 = (Q % 4) >= 2 ? 1 : 0, R1 = Q % 2;
+#pragma unroll
+  for (int g = 0; g < N4; g++) {
+    uint4 v = *reinterpret_cast<const uint4 *>(row + g * 128 + lane * 4);
+    d[4 * g] = v.x; d[4 * g + 1] = v.y; d[4 * g + 2] = v.z; d[4 * g + 3] = v.w;
+  }
+  if (R2) {
+    uint2 v = *reinterpret_cast<const uint2 *>(row + N4 * 128 + lane * 2);
+    d[4 * N4] = v.x; d[4 * N4 + 1] = v.y;
+  }
+  if (R1) d[Q - 1] = row[N4 * 128 + R2 * 64 + lane];
+}
+
+__device__ __forceinline__ int warp_max16x2(uint32_t m) {
+  int v = max((int)(short)(m & 0xffff), (int)(short)(m >> 16));
+  return __reduce_max_sync(PA_FULL, v);
+}
+
+struct MsvArgs {
+  const DevHmm *hmms;
+  const int *hmm_list;     // profiles with this Q
+  int nlist;
+  const uint32_t *tab;     // msv table pool
+  Targets tg;
+  const uint8_t *tjb_li;   // per length index
+  const int16_t *thrJ;     // [hmm*nL + li] minimal passing xJ (0..256)
+  int nL;
+  uint32_t tile;           // targets per work item
+  Pass1 *out;
+  unsigned long long *out_count;
+  unsigned long long out_cap;
+  unsigned long long *n_ssv_cand;
+  int all_pairs;           // 1: emit every pair with its exact MSV result (score_all)
+};
+
+template <int Q>
+__global__ void __launch_bounds__(256, 2) msv_kernel(MsvArgs a) {
+  extern __shared__ __align__(16) uint32_t s_tab[];  // nrows * Q*32 words
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const uint32_t ntiles = (a.tg.n + a.tile - 1) / a.tile;
+  const unsigned long long nitems = (unsigned long long)a.nlist * ntiles;
+  int cur_h = -1;
+  unsigned long long ncand = 0;
+  constexpr int ROWW = Q * 32;
+  for (unsigned long long item = blockIdx.x; item < nitems; item += gridDim.x) {
+    const int h = a.hmm_list[item / ntiles];
+    const uint32_t tile = (uint32_t)(item % ntiles);
+    const DevHmm &hm = a.hmms[h];
+    if (h != cur_h) {
+      __syncthreads();
+      const uint4 *src = reinterpret_cast<const uint4 *>(a.tab + hm.msv_off);
+      uint4 *dst = reinterpret_cast<uint4 *>(s_tab);
+      const int n4 = hm.nrows * ROWW / 4;
+      for (int i = threadIdx.x; i < n4; i += blockDim.x) dst[i] = src[i];
+      __syncthreads();
+      cur_h = h;
+    }
+    const int bias = hm.bias, base = hm.base, tec = hm.tec, tbm = hm.tbm;
+    const uint32_t t1 = min(a.tg.n, (tile + 1) * a.tile);
+    for (uint32_t t = tile * a.tile + wib; t < t1; t += wpb) {
+      const int L = (int)a.tg.len[t];
+      if (L == 0) continue;
+      const uint8_t *p = a.tg.dsq + a.tg.off[t];
+      const int li = a.tg.lidx[t];
+      const int tjb = a.tjb_li[li];
+      const int T = a.thrJ[(size_t)h * a.nL + li];
+      const int tjbm = (tjb + tbm) & 0xff;
+      const int xB0 = max(base - tjbm, 0);
+      int C = min(255 - bias, min(base + 1 + tec, T + tec));
+      const int Cp = a.all_pairs ? 0 : C - xB0;
+      // ---- SSV pass: u(i,k) = relu(u(i-1,k-1) + (bias - rbv)), running max
+      uint32_t w[Q];
+#pragma unroll
+      for (int q = 0; q < Q; q++) w[q] = 0;
+      uint32_t m = 0;
+      if (Cp > 0) {
+        for (int i0 = 0; i0 < L; i0 += 4) {
+          const uint32_t r4 = *reinterpret_cast<const uint32_t *>(p + i0);
+          const int nr = min(4, L - i0);
+          for (int r = 0; r < nr; r++) {
+            const int x = (r4 >> (8 * r)) & 0xff;
+            uint32_t d[Q];
+            msv_load_row<Q>(s_tab + x * ROWW, lane, d);
+            uint32_t tt = __shfl_up_sync(PA_FULL, w[Q - 1], 1);
+            if (lane == 0) tt = 0;
+            const uint32_t carry = __byte_perm(tt, w[Q - 1], 0x5432);
+#pragma unroll
+            for (int q = Q - 1; q >= 1; q--) w[q] = __viaddmax_s16x2_relu(w[q - 1], d[q], 0u);
+            w[0] = __viaddmax_s16x2_relu(carry, d[0], 0u);
+#pragma unroll
+            for (int q = 0; q + 1 < Q; q += 2) m = __vimax3_s16x2(m, w[q], w[q + 1]);
+            if (Q & 1) m = __vmaxs2(m, w[Q - 1]);
+          }
+        }
+      }
+      const int U = (Cp > 0) ? warp_max16x2(m) : 0;
+      if (U < Cp) continue;
+      ncand++;
+      // ---- exact MSV recurrence (J state, overflow) for candidates
+      int xJ = 0, xB = xB0;
+      bool overflow = false;
+#pragma unroll
+      for (int q = 0; q < Q; q++) w[q] = 0;
+      for (int i = 0; i < L && !overflow; i++) {
+        const int x = p[i];
+        uint32_t d[Q];
+        msv_load_row<Q>(s_tab + x * ROWW, lane, d);
+        const uint32_t xBv = (uint32_t)xB * 0x10001u;
+        uint32_t tt = __shfl_up_sync(PA_FULL, w[Q - 1], 1);
+        if (lane == 0) tt = 0;
+        const uint32_t carry = __byte_perm(tt, w[Q - 1], 0x5432);
+        uint32_t rm = 0;
+#pragma unroll
+        for (int q = Q - 1; q >= 1; q--) {
+          w[q] = __viaddmax_s16x2_relu(__vmaxs2(w[q - 1], xBv), d[q], 0u);
+          rm = __vmaxs2(rm, w[q]);
+        }
+        w[0] = __viaddmax_s16x2_relu(__vmaxs2(carry, xBv), d[0], 0u);
+        rm = __vmaxs2(rm, w[0]);
+        int xE = warp_max16x2(rm);
+        if (xE >= 255 - bias) { overflow = true; break; }
+        xE = max(xE - tec, 0);
+        xJ = max(xJ, xE);
+        xB = max(max(base, xJ) - tjbm, 0);
+      }
+      if (overflow) xJ = -1;
+      if (a.all_pairs || overflow || xJ >= T) {
+        if (lane == 0) {
+          unsigned long long idx = atomicAdd(a.out_count, 1ull);
+          if (idx < a.out_cap) {
+            Pass1 r;
+            r.t = t; r.h = (uint16_t)h; r.xJ = (int16_t)xJ;
+            a.out[idx] = r;
+          }
+        }
+      }
+    }
+  }
+  if (lane == 0 && ncand) atomicAdd(a.n_ssv_cand, ncand);
+}
+
+// per (profile, length) minimal passing MSV xJ byte
+__global__ void msv_threshold_kernel(const DevHmm *hmms, int nh, LenTabs lt, int16_t *thrJ, int all_pass) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= nh * lt.n) return;
+  int h = idx / lt.n, li = idx % lt.n;
+  const DevHmm &hm = hmms[h];
+  int tjb = lt.tjb[li];
+  float nullsc = lt.nullsc[li];
+  int T = 256;
+  for (int xJ = 0; xJ < 256; xJ++) {
+    float usc = ((float)(xJ - tjb) - (float)hm.base);
+    usc /= hm.scale_b;
+    usc -= 3.0f;
+    float seq = (float)((double)(usc - nullsc) / PA_LN2);
+    if (seq >= hm.thrF1) { T = xJ; break; }
+  }
+  if (all_pass) T = 0;
+  thrJ[idx] = (int16_t)T;
+}
+
+__device__ __forceinline__ float msv_score_from_xJ(const DevHmm &hm, int xJ, int tjb) {
+  if (xJ < 0) return __int_as_float(0x7f800000);
+  float usc = ((float)(xJ - tjb) - (float)hm.base);
+  usc /= hm.scale_b;
+  usc -= 3.0f;
+  return usc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// bias filter: one thread per MSV survivor
+// ---------------------------------------------------------------------------------------------
+__device__ float bias_filtersc(const DevHmm &hm, const uint8_t *p, int L, float lenA, float lenB) {
+  float d0 = 0.999f, d1 = 0.001f * hm.eo1[p[0]];
+  int sexp = 0;
+  for (int i = 1;; i++) {
+    float mx = fmaxf(d0, d1);
+    int e = ilogbf(mx);
+    d0 = scalbnf(d0, -e);
+    d1 = scalbnf(d1, -e);
+    sexp += e;
+    if (i == L) break;
+    float n0 = __fadd_rn(__fmul_rn(d0, hm.t00), __fmul_rn(d1, hm.t10));
+    float n1 = __fmul_rn(__fadd_rn(__fmul_rn(d0, hm.t01), __fmul_rn(d1, hm.t11)), hm.eo1[p[i]]);
+    d0 = n0;
+    d1 = n1;
+  }
+  float tot = __fadd_rn(d0, d1);
+  float hmmsc = (float)(log((double)tot) + (double)sexp * PA_LN2);
+  return __fadd_rn(__fadd_rn(hmmsc, lenA), lenB);
+}
+
+struct BiasArgs {
+  const DevHmm *hmms;
+  Targets tg;
+  LenTabs lt;
+  const Pass1 *in;
+  unsigned long long n_in;
+  Pass2 *out;
+  unsigned long long *out_count;
+  unsigned long long out_cap;
+  int do_bias;
+  float *bias_out;  // optional (score_all): filtersc per input record
+};
+
+__global__ void bias_kernel(BiasArgs a) {
+  unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+  if (i >= a.n_in) return;
+  Pass1 r = a.in[i];
+  const DevHmm &hm = a.hmms[r.h];
+  const int L = (int)a.tg.len[r.t];
+  const int li = a.tg.lidx[r.t];
+  const float nullsc = a.lt.nullsc[li];
+  const float usc = msv_score_from_xJ(hm, r.xJ, a.lt.tjb[li]);
+  float filtersc = nullsc;
+  if (a.do_bias) filtersc = bias_filtersc(hm, a.tg.dsq + a.tg.off[r.t], L, a.lt.biasA[li], a.lt.biasB[li]);
+  if (a.bias_out) a.bias_out[i] = filtersc;
+  const float seq = (float)((double)(usc - filtersc) / PA_LN2);
+  if (!(seq >= hm.thrF1)) return;  // P > F1
+  Pass2 o;
+  o.t = r.t; o.h = r.h; o.flags = (seq >= hm.thrF2m) ? 0 : 1; o.filtersc = filtersc;
+  unsigned long long idx = atomicAdd(a.out_count, 1ull);
+  if (idx < a.out_cap) a.out[idx] = o;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Viterbi filter: one warp per pair, lane-blocked, state in shared memory
+// ---------------------------------------------------------------------------------------------
+struct VitArgs {
+  const DevHmm *hmms;
+  const int *tab;          // vit pool
+  Targets tg;
+  LenTabs lt;
+  const Pass2 *in;
+  unsigned long long n_in;
+  Pass2 *out;
+  unsigned long long *out_count;
+  unsigned long long out_cap;
+  int maxB;                // shared-memory sizing
+  int all_pairs;           // score_all: run Viterbi on every input, write raw xC
+  int *raw_out;
+};
+
+__device__ __forceinline__ int warp_max_s32(int v) { return __reduce_max_sync(PA_FULL, v); }
+
+// returns raw xC (32767 on overflow)
+__device__ int vit_pair(const DevHmm &hm, const int *tab, const uint8_t *p, int L, int xw_move, int *sm, int lane) {
+  const int B = hm.B, W = B * 32;
+  const int4 *trA = reinterpret_cast<const int4 *>(tab + hm.vit_off);
+  const int4 *trB = trA + W;
+  const int *ps = reinterpret_cast<const int *>(trB + W);
+  const int *em = ps + W;
+  int *Mx = sm, *Ix = sm + W, *Dx = sm + 2 * W;  // single buffer, updated in place (descending j)
+  for (int j = 0; j < B; j++) { Mx[j * 32 + lane] = PA_NEG16; Ix[j * 32 + lane] = PA_NEG16; Dx[j * 32 + lane] = PA_NEG16; }
+  __syncwarp();
+  const int xN = hm.base_w, xw_E = hm.xw_E;
+  int xB = max(xN + xw_move, PA_NEG16), xJ = PA_NEG16, xC = PA_NEG16;
+  const int ilast = (B - 1) * 32 + lane;
+  for (int i = 0; i < L; i++) {
+    const int *emx = em + (size_t)p[i] * W;
+    // previous-row values of the left neighbour's last cell
+    int mL = __shfl_up_sync(PA_FULL, Mx[ilast], 1), iL = __shfl_up_sync(PA_FULL, Ix[ilast], 1),
+        dL = __shfl_up_sync(PA_FULL, Dx[ilast], 1);
+    if (lane == 0) mL = iL = dL = PA_NEG16;
+    int rowmax = PA_NEG16;
+    for (int j = B - 1; j >= 0; j--) {
+      const int c = j * 32 + lane;
+      const int4 A = trA[c], Bq = trB[c];
+      const int pm = j ? Mx[c - 32] : mL, pi = j ? Ix[c - 32] : iL, pd = j ? Dx[c - 32] : dL;
+      int sv = __viaddmax_s32(xB, A.x, PA_NEG16);
+      sv = __viaddmax_s32(pm, A.y, sv);
+      sv = __viaddmax_s32(pi, A.z, sv);
+      sv = __viaddmax_s32(pd, A.w, sv);
+      sv = __viaddmax_s32(sv, emx[c], PA_NEG16);
+      int iv = __viaddmax_s32(Mx[c], Bq.z, PA_NEG16);
+      iv = __viaddmax_s32(Ix[c], Bq.w, iv);
+      Mx[c] = sv;
+      Ix[c] = iv;
+      rowmax = max(rowmax, sv);
+    }
+    const int xE = warp_max_s32(rowmax);
+    if (xE >= 32767) return 32767;
+    // D row: local chains, then max-plus scan across lanes
+    int mcL = __shfl_up_sync(PA_FULL, Mx[ilast], 1);
+    if (lane == 0) mcL = PA_NEGBIG;
+    int aloc = PA_NEGBIG;
+    for (int j = 0; j < B; j++) {
+      const int c = j * 32 + lane;
+      const int4 Bq = trB[c];
+      const int mleft = j ? Mx[c - 32] : mcL;
+      aloc = max(mleft + Bq.x, aloc + Bq.y);   // M(k-1)+MD(k-1), D(k-1)+DD(k-1); no clamp inside (addends <= 0)
+      aloc = max(aloc, PA_NEGBIG);
+      Dx[c] = aloc;
+    }
+    int LA = aloc, LS = ps[ilast];
+    for (int o = 1; o < 32; o <<= 1) {
+      int a2 = __shfl_up_sync(PA_FULL, LA, o), s2 = __shfl_up_sync(PA_FULL, LS, o);
+      if (lane >= o) {
+        LA = max(LA, max(a2 + LS, PA_NEGBIG));
+        LS = max(LS + s2, PA_NEGBIG);
+      }
+    }
+    int din = __shfl_up_sync(PA_FULL, LA, 1);
+    if (lane == 0) din = PA_NEGBIG;
+    for (int j = 0; j < B; j++) {
+      const int c = j * 32 + lane;
+      Dx[c] = max(max(Dx[c], din + ps[c]), PA_NEG16);
+    }
+    xC = max(xC, max(xE + xw_E, PA_NEG16));
+    xJ = max(xJ, max(xE + xw_E, PA_NEG16));
+    xB = max(max(xJ + xw_move, xN + xw_move), PA_NEG16);
+    __syncwarp();
+  }
+  return xC;
+}
+
+__device__ __forceinline__ float vit_score_from_xC(const DevHmm &hm, int xC, int xw_move) {
+  if (xC >= 32767) return __int_as_float(0x7f800000);
+  if (xC <= PA_NEG16) return __int_as_float(0xff800000);
+  float sc = (float)xC + (float)xw_move - (float)hm.base_w;
+  sc /= hm.scale_w;
+  sc -= 3.0f;
+  return sc;
+}
+
+__global__ void __launch_bounds__(256) vit_kernel(VitArgs a) {
+  extern __shared__ __align__(16) int s_vit[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  int *sm = s_vit + (size_t)wib * a.maxB * 32 * 3;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * wpb + wib; i < a.n_in; i += (unsigned long long)gridDim.x * wpb) {
+    Pass2 r = a.in[i];
+    const DevHmm &hm = a.hmms[r.h];
+    if (!(r.flags & 1) && !a.all_pairs) {  // P <= F2 already: Viterbi not needed
+      if (lane == 0) {
+        unsigned long long idx = atomicAdd(a.out_count, 1ull);
+        if (idx < a.out_cap) a.out[idx] = r;
+      }
+      continue;
+    }
+    const int L = (int)a.tg.len[r.t];
+    const int li = a.tg.lidx[r.t];
+    const int xw_move = a.lt.xw_move[li];
+    const int xC = vit_pair(hm, a.tab, a.tg.dsq + a.tg.off[r.t], L, xw_move, sm, lane);
+    if (a.raw_out && lane == 0) a.raw_out[i] = xC;
+    if (a.all_pairs) continue;
+    const float vfsc = vit_score_from_xC(hm, xC, xw_move);
+    const float seq = (float)((double)(vfsc - r.filtersc) / PA_LN2);
+    if (seq >= hm.thrF2v && lane == 0) {
+      unsigned long long idx = atomicAdd(a.out_count, 1ull);
+      if (idx < a.out_cap) a.out[idx] = r;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Forward / Backward rows in scaled probability space (canonical order)
+// ---------------------------------------------------------------------------------------------
+struct XF { float tNN, tNB, tJJ, tJB, tCC, tCT, tEJ, tEC; };
+struct Specials { float xE, xN, xJ, xB, xC; };
+
+__device__ __forceinline__ XF xf_config(int Lcfg, int multihit) {
+  XF x;
+  float nj = multihit ? 1.0f : 0.0f;
+  float pmove = __fdiv_rn(2.0f + nj, __fadd_rn(__fadd_rn((float)Lcfg, 2.0f), nj));
+  float ploop = __fsub_rn(1.0f, pmove);
+  x.tNN = x.tJJ = x.tCC = ploop;
+  x.tNB = x.tJB = x.tCT = pmove;
+  x.tEJ = multihit ? 0.5f : 0.0f;
+  x.tEC = multihit ? 0.5f : 1.0f;
+  return x;
+}
+
+__device__ __forceinline__ float lane_sum(float s) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) s = __fadd_rn(s, __shfl_xor_sync(PA_FULL, s, o));
+  return s;
+}
+
+struct FwdTabs {
+  const float4 *trA;  // {BM[k-1], MM[k-1], IM[k-1], DM[k-1]}
+  const float4 *trB;  // {MD[k-1], DD[k-1], MI[k], II[k]}
+  const float4 *bwA;  // {MM[k], MI[k], MD[k], IM[k]}
+  const float4 *bwB;  // {II[k], DM[k], DD[k], BM[k-1]}
+  const float *em;    // [x][W]
+  int B, W, M;
+};
+__device__ __forceinline__ FwdTabs fwd_tabs(const DevHmm &hm, const float *pool) {
+  FwdTabs t;
+  t.B = hm.B; t.W = hm.B * 32; t.M = hm.M;
+  t.trA = reinterpret_cast<const float4 *>(pool + hm.fwd_off);
+  t.trB = t.trA + t.W;
+  t.bwA = t.trB + t.W;
+  t.bwB = t.bwA + t.W;
+  t.em = reinterpret_cast<const float *>(t.bwB + t.W);
+  return t;
+}
+
+// One forward row. Arrays are [j*32+lane]; cells beyond M stay 0. wP: scratch row. Returns xE.
+__device__ float fwd_row(const FwdTabs &T, int x, const float *Mp, const float *Ip, const float *Dp, float xBp,
+                         float *Mc, float *Ic, float *Dc, float *wP, int lane) {
+  const int B = T.B;
+  const float *em = T.em + (size_t)x * T.W;
+  const int nv = min(B, max(0, T.M - lane * B));  // valid cells of this lane
+  const int ilast = (B - 1) * 32 + lane;
+  float mL = __shfl_up_sync(PA_FULL, Mp[ilast], 1), iL = __shfl_up_sync(PA_FULL, Ip[ilast], 1),
+        dL = __shfl_up_sync(PA_FULL, Dp[ilast], 1);
+  if (lane == 0) mL = iL = dL = 0.0f;
+  for (int j = 0; j < nv; j++) {
+    const int c = j * 32 + lane;
+    const float4 A = T.trA[c], Bq = T.trB[c];
+    const float pm = j ? Mp[c - 32] : mL, pi = j ? Ip[c - 32] : iL, pd = j ? Dp[c - 32] : dL;
+    float t = __fmul_rn(xBp, A.x);
+    t = __fadd_rn(t, __fmul_rn(pm, A.y));
+    t = __fadd_rn(t, __fmul_rn(pi, A.z));
+    t = __fadd_rn(t, __fmul_rn(pd, A.w));
+    Mc[c] = __fmul_rn(t, em[c]);
+    Ic[c] = __fadd_rn(__fmul_rn(Mp[c], Bq.z), __fmul_rn(Ip[c], Bq.w));
+  }
+  __syncwarp();
+  float mcL = __shfl_up_sync(PA_FULL, Mc[ilast], 1);
+  if (lane == 0) mcL = 0.0f;
+  float LA = 0.0f, LP = 1.0f;
+  for (int j = 0; j < nv; j++) {
+    const int c = j * 32 + lane;
+    const float4 Bq = T.trB[c];
+    const float a = __fmul_rn(j ? Mc[c - 32] : mcL, Bq.x);
+    if (j == 0) { LA = a; LP = Bq.y; }
+    else { LA = __fadd_rn(a, __fmul_rn(LA, Bq.y)); LP = __fmul_rn(LP, Bq.y); }
+    Dc[c] = LA;
+    wP[c] = LP;
+  }
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    float a2 = __shfl_up_sync(PA_FULL, LA, o), p2 = __shfl_up_sync(PA_FULL, LP, o);
+    if (lane >= o) { LA = __fadd_rn(LA, __fmul_rn(LP, a2)); LP = __fmul_rn(LP, p2); }
+  }
+  float cin = __shfl_up_sync(PA_FULL, LA, 1);
+  if (lane == 0) cin = 0.0f;
+  float s = 0.0f;
+  for (int j = 0; j < nv; j++) {
+    const int c = j * 32 + lane;
+    const float d = __fadd_rn(Dc[c], __fmul_rn(wP[c], cin));
+    Dc[c] = d;
+    s = __fadd_rn(s, __fadd_rn(Mc[c], d));
+  }
+  __syncwarp();
+  return lane_sum(s);
+}
+
+__device__ __forceinline__ void scale_row(float *Mc, float *Ic, float *Dc, int B, int lane, int e) {
+  for (int j = 0; j < B; j++) {
+    const int c = j * 32 + lane;
+    Mc[c] = scalbnf(Mc[c], -e); Ic[c] = scalbnf(Ic[c], -e); Dc[c] = scalbnf(Dc[c], -e);
+  }
+}
+
+// Forward parser over p[0..L-1]; sm: 7 rows of W floats (zero-initialised here). Optionally stores
+// per-row specials/exponents (sp/sexp index 0..L). Returns exponent, *mant = xC*tCT.
+__device__ int fwd_parser(const FwdTabs &T, const uint8_t *p, int L, int Lcfg, int multihit, float *sm, int lane,
+                          float *mant, Specials *sp, int *sexp) {
+  const int W = T.W;
+  float *Mp = sm, *Ip = sm + W, *Dp = sm + 2 * W, *Mc = sm + 3 * W, *Ic = sm + 4 * W, *Dc = sm + 5 * W, *wP = sm + 6 * W;
+  for (int c = lane; c < 7 * W; c += 32) sm[c] = 0.0f;
+  __syncwarp();
+  const XF xf = xf_config(Lcfg, multihit);
+  float xN = 1.0f, xB = xf.tNB, xE = 0.0f, xJ = 0.0f, xC = 0.0f;
+  int etot = 0;
+  if (sp && lane == 0) { Specials s0; s0.xE = 0; s0.xN = xN; s0.xJ = 0; s0.xB = xB; s0.xC = 0; sp[0] = s0; sexp[0] = 0; }
+  for (int i = 0; i < L; i++) {
+    xE = fwd_row(T, p[i], Mp, Ip, Dp, xB, Mc, Ic, Dc, wP, lane);
+    xN = __fmul_rn(xN, xf.tNN);
+    xJ = __fadd_rn(__fmul_rn(xJ, xf.tJJ), __fmul_rn(xE, xf.tEJ));
+    xC = __fadd_rn(__fmul_rn(xC, xf.tCC), __fmul_rn(xE, xf.tEC));
+    xB = __fadd_rn(__fmul_rn(xJ, xf.tJB), __fmul_rn(xN, xf.tNB));
+    if (xE > PA_RESCALE) {
+      const int e = ilogbf(xE);
+      scale_row(Mc, Ic, Dc, T.B, lane, e);
+      xN = scalbnf(xN, -e); xJ = scalbnf(xJ, -e); xC = scalbnf(xC, -e); xB = scalbnf(xB, -e); xE = scalbnf(xE, -e);
+      etot += e;
+      __syncwarp();
+    }
+    if (sp && lane == 0) { Specials s; s.xE = xE; s.xN = xN; s.xJ = xJ; s.xB = xB; s.xC = xC; sp[i + 1] = s; sexp[i + 1] = etot; }
+    float *t;
+    t = Mp; Mp = Mc; Mc = t;
+    t = Ip; Ip = Ic; Ic = t;
+    t = Dp; Dp = Dc; Dc = t;
+  }
+  *mant = __fmul_rn(xC, xf.tCT);
+  return etot;
+}
+
+struct FwdArgs {
+  const DevHmm *hmms;
+  const float *tab;
+  Targets tg;
+  const Pass2 *in;
+  unsigned long long n_in;
+  Pass4 *out;
+  unsigned long long *out_count;
+  unsigned long long out_cap;
+  int maxB;
+  int all_pairs;       // score_all: emit every input with its forward result, in input order
+};
+
+__global__ void __launch_bounds__(256) fwd_kernel(FwdArgs a) {
+  extern __shared__ __align__(16) float s_fwd[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  float *sm = s_fwd + (size_t)wib * a.maxB * 32 * 7;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * wpb + wib; i < a.n_in; i += (unsigned long long)gridDim.x * wpb) {
+    Pass2 r = a.in[i];
+    const DevHmm &hm = a.hmms[r.h];
+    const FwdTabs T = fwd_tabs(hm, a.tab);
+    const int L = (int)a.tg.len[r.t];
+    float mant;
+    const int e = fwd_parser(T, a.tg.dsq + a.tg.off[r.t], L, L, 1, sm, lane, &mant, nullptr, nullptr);
+    const float fwdsc = (float)((double)e * PA_LN2 + log((double)mant));
+    const float seq = (float)((double)(fwdsc - r.filtersc) / PA_LN2);
+    if (lane == 0 && (a.all_pairs || seq >= hm.thrF3)) {
+      Pass4 o;
+      o.t = r.t; o.h = r.h; o.pad = 0; o.filtersc = r.filtersc; o.fexp = e; o.fmant = mant;
+      if (a.all_pairs) a.out[i] = o;
+      else {
+        unsigned long long idx = atomicAdd(a.out_count, 1ull);
+        if (idx < a.out_cap) a.out[idx] = o;
+      }
+    }
+  }
+}
+
+}  // namespace pa
