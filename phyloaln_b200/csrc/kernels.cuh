@@ -428,7 +428,7 @@ __global__ void bias_kernel(BiasArgs a) {
   const float nullsc = a.lt.nullsc[li];
   const float usc = msv_score_from_xJ(hm, r.xJ, a.lt.tjb[li]);
   float filtersc = nullsc;
-  if (a.do_bias) filtersc = bias_filtersc(hm, a.tg.dsq + a.tg.off[r.t], L, a.lt.biasA[li], a.lt.biasB[li]);
+  if (a.do_bias && L > 0) filtersc = bias_filtersc(hm, a.tg.dsq + a.tg.off[r.t], L, a.lt.biasA[li], a.lt.biasB[li]);
   if (a.bias_out) a.bias_out[i] = filtersc;
   const float seq = (float)((double)(usc - filtersc) / PA_LN2);
   if (!(seq >= hm.thrF1)) return;  // P > F1

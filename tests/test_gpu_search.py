@@ -1,0 +1,117 @@
+"""GPU parity: the whole search (filters + domain definition + alignment) against the oracle."""
+import numpy as np
+import pytest
+
+from tests import helpers
+
+pytestmark = pytest.mark.gpu
+
+INT_FIELDS = ["ndom_in_seq", "dom_idx", "ienv", "jenv", "iali", "jali", "hmmfrom", "hmmto", "multidomain_region"]
+FLOAT_FIELDS = ["envsc", "domcorrection", "oasc", "dombias", "dom_bits", "seq_bits", "pre_bits", "seqbias", "fwdsc", "nullsc"]
+
+
+def compare_hits(oracle, hmms, seqs, hits, model, aligned, opts=None):
+    """Every oracle hit must be reproduced exactly: set, coordinates, strings; scores within 0.01 bit."""
+    got = {}
+    for i in range(len(hits)):
+        got[(int(hits["hmm"][i]), int(hits["target"][i]), int(hits["dom_idx"][i]))] = i
+    nwant = 0
+    for hi, h in enumerate(hmms):
+        P = oracle.Profile.from_hmm(h)
+        ohits, _ = P.search(seqs, opts=opts, nthreads=8, want_trace=False)
+        for oh in ohits:
+            nwant += 1
+            key = (hi, oh["target"], oh["dom_idx"])
+            assert key in got, f"missing hit {key}"
+            g = got[key]
+            for f in INT_FIELDS:
+                assert int(hits[f][g]) == oh[f], (key, f, int(hits[f][g]), oh[f])
+            assert model[g] == oh["model"], key
+            assert aligned[g] == oh["aligned"], key
+            for f in FLOAT_FIELDS:
+                assert abs(float(hits[f][g]) - oh[f]) <= 0.01 * 0.6931 + 1e-5 * abs(oh[f]), (key, f, float(hits[f][g]), oh[f])
+            for f in ("dom_lnP", "seq_lnP"):
+                assert abs(float(hits[f][g]) - oh[f]) <= 1e-3 * max(1.0, abs(oh[f])), (key, f)
+    assert nwant == len(hits), (nwant, len(hits))
+    return nwant
+
+
+def test_search_matches_oracle_proteins(oracle, gpu_ctx_factory):
+    rng = np.random.default_rng(77)
+    hmms = [helpers.calibrated_hmm(f"h{i}", M, seed=10 + i) for i, M in enumerate([40, 90, 130, 200, 310])]
+    seqs = helpers.protein_targets(hmms, 3000, rng, Lmin=25, Lmax=60, plant_every=9)
+    ctx = gpu_ctx_factory()
+    for h in hmms:
+        ctx.add_hmm(h)
+    ctx.commit()
+    ctx.load_proteins(seqs)
+    hits, model, aligned = ctx.search()
+    n = compare_hits(oracle, hmms, seqs, hits, model, aligned)
+    assert n > 50
+    ctx.close()
+
+
+def test_search_matches_oracle_long_targets(oracle, gpu_ctx_factory):
+    """Transcript-like targets (config 4 shape): several domains per target, rescaling, M > 512."""
+    rng = np.random.default_rng(5)
+    hmms = [helpers.calibrated_hmm(f"L{i}", M, seed=40 + i, bg_mix=0.15) for i, M in enumerate([150, 330, 600])]
+    from phyloaln_b200 import hmmbuild_lite as hb, synth
+    seqs = []
+    for i in range(150):
+        L = int(rng.integers(200, 900))
+        s = hb.random_sequences("amino", 1, L, rng)[0]
+        for _ in range(int(rng.integers(0, 3))):
+            h = hmms[int(rng.integers(len(hmms)))]
+            a = int(rng.integers(1, h.M // 2))
+            b = int(rng.integers(a + 30, h.M + 1))
+            frag = synth.sample_protein(h, rng, a, b)
+            pos = int(rng.integers(0, max(1, L - len(frag))))
+            s = s[:pos] + frag + s[pos + len(frag):]
+        seqs.append(s)
+    ctx = gpu_ctx_factory()
+    for h in hmms:
+        ctx.add_hmm(h)
+    ctx.commit()
+    ctx.load_proteins(seqs)
+    hits, model, aligned = ctx.search()
+    n = compare_hits(oracle, hmms, seqs, hits, model, aligned)
+    assert n > 40
+    assert (hits["ndom_in_seq"] > 1).any()
+    ctx.close()
+
+
+def test_search_six_frame_reads(oracle, gpu_ctx_factory):
+    """Reads -> six-frame translation on the GPU -> search; oracle gets the frames from its own translator."""
+    from phyloaln_b200 import synth
+    rng = np.random.default_rng(9)
+    hmms = [helpers.calibrated_hmm(f"r{i}", M, seed=60 + i, bg_mix=0.1) for i, M in enumerate([80, 160, 260])]
+    reads = synth.random_reads(2000, 150, rng)
+    synth.plant_reads(reads, hmms, 0.1, rng, sub_rate=0.02)
+    rl = [r.tobytes().decode() for r in reads]
+    frames = []
+    for r in rl:
+        frames.extend(p for _, p in oracle.six_frames(r, 1))
+    ctx = gpu_ctx_factory()
+    for h in hmms:
+        ctx.add_hmm(h)
+    ctx.commit()
+    assert ctx.load_read_list(rl, moltype=0, gencode=1) == len(frames)
+    hits, model, aligned = ctx.search()
+    n = compare_hits(oracle, hmms, frames, hits, model, aligned)
+    assert n > 30
+    ctx.close()
+
+
+def test_max_mode_and_nobias(oracle, gpu_ctx_factory):
+    rng = np.random.default_rng(3)
+    hmms = [helpers.calibrated_hmm("m0", 70, seed=91)]
+    seqs = helpers.protein_targets(hmms, 200, rng, Lmin=30, Lmax=50, plant_every=4)
+    for kw, ok in (({"do_max": True}, {"do_max": 1}), ({"do_bias": False}, {"do_bias": 0}), ({"do_null2": False}, {"do_null2": 0})):
+        ctx = gpu_ctx_factory()
+        ctx.add_hmm(hmms[0])
+        ctx.set_opts(**kw)
+        ctx.commit()
+        ctx.load_proteins(seqs)
+        hits, model, aligned = ctx.search()
+        compare_hits(oracle, hmms, seqs, hits, model, aligned, opts=oracle.default_opts(**ok))
+        ctx.close()
