@@ -1,0 +1,310 @@
+#!/usr/bin/env python
+"""bench.py -- PhyloAln search hot path on B200: reads/s and GCUPS (BASELINE.json metric).
+
+Workload (BASELINE.json configs[1], "config2"): synthetic 150 bp Illumina-like reads, six-frame
+translated, searched against 1,000 BUSCO-size protein profile HMMs.  One *step* = one resident
+chunk of `--reads-per-step` reads against ALL profiles (the full 10 M-read config is 10e6 /
+reads-per-step identical steps; throughput is per read, so it extrapolates linearly).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+value      reads/s with the read chunk already resident in HBM (translate + all filters + domain
+           stage + host-side domain scoring), max over ranks, whole job.
+e2e        same metric through the public C ABI with HOST buffers: H2D of the reads, translation,
+           search, D2H of the hit records, every step.
+roofline   dominant kernel = msv_kernel (SSV/MSV filter): algorithmic 4 integer lane-ops per DP
+           cell x cells per launch / CUDA-event time, against the 16-bit lane-op peak
+           microbenchmarked in this run (VIADDMNMX.S16x2 issue rate x 2 lanes).
+cpu_baseline  the CPU oracle (scalar C restatement of the hmmsearch pipeline, OpenMP over all host
+           cores) on a bounded sample of the same workload; kind "port" (no hmmsearch binary exists
+           in this image).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "reads/s (six-frame 150bp reads vs 1000 protein HMMs, hmmsearch-equivalent pipeline)"
+UNIT = "reads/s"
+
+
+def build_profiles(n_hmm: int, seed: int):
+    from phyloaln_b200 import synth
+    rng = np.random.default_rng(seed)
+    Ms = synth.busco_lengths(n_hmm, rng)
+    return [synth.random_hmm(f"syn{i:04d}", int(Ms[i]), rng) for i in range(n_hmm)]
+
+
+def make_reads(n: int, hmms, seed: int, frac: float = 0.01):
+    from phyloaln_b200 import synth
+    rng = np.random.default_rng(seed)
+    reads = synth.random_reads(n, 150, rng)
+    synth.plant_reads(reads, hmms, frac, rng)
+    return reads
+
+
+def calibrate_on_gpu(ctx, hmms, seed=42, n=200):
+    """STATS LOCAL for synthetic profiles, scored by the GPU kernels themselves (hmmbuild's job)."""
+    import math
+    from phyloaln_b200 import hmmbuild_lite as hb
+    rng = np.random.default_rng(seed)
+    s200 = hb.random_sequences("amino", n, 200, rng)
+    s100 = hb.random_sequences("amino", n, 100, rng)
+    ntot = ctx.load_proteins(s200 + s100)
+    for i, h in enumerate(hmms):
+        r = ctx.score_all(i, ntot, want=("msv", "vit", "fwd"))
+        lam = math.log(2.0) + 1.44 / (h.M * hb.mean_match_relent_bits(h))
+
+        def loc(bits):
+            return -math.log(float(np.mean(np.exp(-lam * np.asarray(bits, dtype=np.float64))))) / lam
+        ln2 = math.log(2.0)
+        mmu = loc((r["msv"][:n].astype(np.float64) - hb.null1(200)) / ln2)
+        vmu = loc((r["vit"][:n].astype(np.float64) - hb.null1(200)) / ln2)
+        gmu = loc((r["fwd"][n:].astype(np.float64) - hb.null1(100)) / ln2)
+        tau = gmu - math.log(-math.log(1.0 - 0.04)) / lam
+        h.stats = {"MSV": (round(mmu, 4), round(lam, 5)), "VITERBI": (round(vmu, 4), round(lam, 5)),
+                   "FORWARD": (round(tau, 4), round(lam, 5))}
+        ctx.set_evparam(i, h.evparams())
+    ctx.commit()
+
+
+class ClockSampler:
+    def __init__(self, gpu_index: int):
+        self.p = None
+        self.path = f"/tmp/pa_clocks_{os.getpid()}.csv"
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.f = open(self.path, "w")
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                       "-lms", "200"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            tok = [t.strip() for t in line.split(",")]
+            if len(tok) < 7:
+                continue
+            try:
+                sm.append(float(tok[0]))
+                mx.append(float(tok[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, tok[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        os.remove(self.path)
+        if sm:
+            out["sm_mhz"] = float(np.median(sm))
+            out["sm_max_mhz"] = float(max(mx))
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+def cpu_reference_run(hmms, reads, threads: int, seconds_target: float = 15.0):
+    """Oracle on the host cores over a bounded sample; returns (reads/s vs ALL profiles, description, gcups)."""
+    from oracle import oracle as O
+    from phyloaln_b200 import hmmbuild_lite as hb
+    n_h = min(len(hmms), 16)
+    sub = hmms[:n_h]
+    profs = []
+    for h in sub:
+        P = O.Profile.from_hmm(h)
+        if not h.stats:
+            hb.calibrate(h, lambda hm, seqs, P=P: P.score_all(seqs), n=40)
+            P.set_stats(h.evparams())
+        profs.append(P)
+    # size the sample from a short probe
+    probe = [r.tobytes().decode() for r in reads[:200]]
+    frames = [p for r in probe for _, p in O.six_frames(r, 1)]
+    t0 = time.perf_counter()
+    profs[0].search(frames, nthreads=threads, want_trace=False)
+    dt = max(time.perf_counter() - t0, 1e-3)
+    cells_per_s = sum(map(len, frames)) * sub[0].M / dt
+    total_M = sum(h.M for h in sub)
+    n_reads = int(min(len(reads), max(200, seconds_target * cells_per_s / (296.0 * total_M))))
+    sample = [r.tobytes().decode() for r in reads[:n_reads]]
+    t0 = time.perf_counter()
+    frames = [p for r in sample for _, p in O.six_frames(r, 1)]
+    nres = sum(map(len, frames))
+    for P in profs:
+        P.search(frames, nthreads=threads, want_trace=False)
+    dt = time.perf_counter() - t0
+    cells = nres * total_M
+    gcups = cells / dt / 1e9
+    all_M = sum(h.M for h in hmms)
+    reads_per_s = n_reads / (dt * all_M / total_M)   # scale profile count linearly to the full config
+    desc = (f"{n_reads} reads x {n_h} profiles (of {len(hmms)}), translate+full pipeline, {dt:.1f}s, "
+            f"scaled linearly to {len(hmms)} profiles")
+    return reads_per_s, desc, gcups
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--hmms", type=int, default=1000)
+    ap.add_argument("--reads-per-step", type=int, default=32768)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    config = {"workload": "config2: 150bp synthetic reads (1% planted homologs, 0.1% N) x BUSCO-size protein HMMs, six-frame",
+              "n_hmm": args.hmms, "reads_per_step_per_gpu": args.reads_per_step, "read_len": 150,
+              "frames": 6, "full_config_reads": 10_000_000,
+              "l2": "inputs larger than L2: every step streams ~190 MB of per-profile score tables (1000 profiles) "
+                    "plus a fresh, different read chunk; no explicit flush"}
+    hmms = build_profiles(args.hmms, seed=2002)
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        threads = os.cpu_count() or 1
+        reads = make_reads(max(2000, args.reads_per_step // 8), hmms, seed=1002)
+        vals = []
+        desc = ""
+        for s in range(args.warmup + args.steps):
+            v, desc, gc = cpu_reference_run(hmms, reads, threads, seconds_target=max(4.0, 60.0 / max(1, args.warmup + args.steps)))
+            if s >= args.warmup:
+                vals.append(v)
+        v = float(np.mean(vals)) if vals else 0.0
+        line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "u8/s16/f32", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc},
+                "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    from phyloaln_b200 import capi
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl")
+    ctx = capi.Context(local_rank)
+    for h in hmms:
+        ctx.add_hmm(h, require_stats=False)
+    ctx.commit()
+    calibrate_on_gpu(ctx, hmms)
+
+    # measured integer-pipe peak (thread-instructions/s); lane-ops = 2 per packed instruction
+    dpx = {m: ctx.microbench_dpx(i) for i, m in enumerate(["viaddmnmx_s16x2_relu", "vimnmx3_s16x2", "ssv_mix", "viaddmnmx_s32"])}
+    peak_laneops = 2.0 * dpx["viaddmnmx_s16x2_relu"] * 1e9
+
+    nsteps = args.warmup + args.steps
+    chunks = [make_reads(args.reads_per_step, hmms, seed=1002 + 7919 * (rank * nsteps + s)) for s in range(nsteps)]
+    offs = np.arange(args.reads_per_step + 1, dtype=np.uint64) * 150
+    sumM = sum(h.M for h in hmms)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    # ---------------- device-resident pass: translate kernel time + search -------------
+    sampler = ClockSampler(local_rank)
+    times, stats_acc = [], []
+    launches_timed = 0
+    for s in range(nsteps):
+        l0 = ctx.stats()["kernel_launches"]
+        ctx.load_reads(chunks[s].reshape(-1), offs)            # reads resident after this call
+        tr_ms = ctx.stats()["ms_translate"]
+        barrier()
+        t0 = time.perf_counter()
+        hits, _, _ = ctx.search()
+        dt = time.perf_counter() - t0 + tr_ms * 1e-3            # search (synchronous) + translation kernel
+        barrier()
+        if s >= args.warmup:
+            times.append(dt)
+            stats_acc.append(ctx.stats())
+            launches_timed += stats_acc[-1]["kernel_launches"] - l0
+    # ---------------- end-to-end pass: host buffers in, hit records out ----------------
+    e2e_times, d2h = [], 0
+    for s in range(nsteps):
+        barrier()
+        t0 = time.perf_counter()
+        ctx.load_reads(chunks[s].reshape(-1), offs)
+        hits, model, aligned = ctx.search()
+        dt = time.perf_counter() - t0
+        barrier()
+        if s >= args.warmup:
+            e2e_times.append(dt)
+            d2h = int(hits.nbytes + sum(map(len, model)) + sum(map(len, aligned)))
+    clocks = sampler.stop()
+    launches_total = launches_timed
+
+    tot = float(np.sum(times))
+    tot_e2e = float(np.sum(e2e_times))
+    if dist is not None:
+        import torch
+        t = torch.tensor([tot, tot_e2e], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        tot, tot_e2e = float(t[0]), float(t[1])
+    reads_total = args.reads_per_step * args.steps * world
+    value = reads_total / tot
+    e2e_value = reads_total / tot_e2e
+    ms_msv = float(np.mean([s["ms_msv"] for s in stats_acc]))
+    ms_stage = {k: float(np.mean([s[k] for s in stats_acc])) for k in
+                ("ms_translate", "ms_msv", "ms_bias", "ms_vit", "ms_fwd", "ms_domain", "ms_total")}
+    cells_per_step = 296.0 * args.reads_per_step * sumM        # residues/read (50+49+49)*2 x sum of M
+    achieved_laneops = 4.0 * cells_per_step / (ms_msv * 1e-3)
+    gcups = cells_per_step * world / (tot / args.steps) / 1e9
+    last = stats_acc[-1]
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * tot / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8/s16 (DPX s16x2, s32), f32", "data": "synthetic", "config": config,
+            "gcups": gcups,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(chunks[0].nbytes + offs.nbytes),
+                    "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches_total),
+            "clocks": clocks,
+            "roofline": {"bound": "int_dpx", "kernel": "msv_kernel<Q> (SSV + inline MSV)", "achieved": achieved_laneops / 1e12,
+                         "peak": peak_laneops / 1e12, "unit": "T 16-bit lane-op/s (algorithmic 4/cell)",
+                         "frac": achieved_laneops / peak_laneops, "traffic": None,
+                         "msv_gcups": cells_per_step / (ms_msv * 1e-3) / 1e9,
+                         "peak_source": "measured in this run: VIADDMNMX.S16x2.RELU issue rate x 2 lanes (pa_microbench_dpx)",
+                         "dpx_ginstr_per_s": dpx},
+            "stage_ms": ms_stage,
+            "funnel": {k: int(last[k]) for k in ("n_pairs", "n_past_ssv", "n_past_msv", "n_past_bias", "n_past_vit", "n_past_fwd", "n_domains")}}
+    if rank == 0:
+        if not args.no_cpu_baseline and world == 1:
+            try:
+                v, desc, gc = cpu_reference_run(hmms, chunks[0], os.cpu_count() or 1, seconds_target=12.0)
+                line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port", "sample": desc,
+                                        "gcups": gc}
+            except Exception as e:  # the baseline is reported, never required
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {e}"}
+        print(json.dumps(line))
+    ctx.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

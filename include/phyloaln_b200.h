@@ -126,6 +126,11 @@ int pa_get_stats(pa_ctx *ctx, pa_stats *st);
 int pa_score_all(pa_ctx *ctx, int hmm, float *msv, int32_t *msv_raw, float *vit, int32_t *vit_raw,
                  float *fwd, float *bias);
 
+/* Measured issue rate of the DPX integer pipe (no reference equivalent; roofline denominator).
+ * mode 0 VIADDMNMX.S16x2.RELU, 1 VIMNMX3.S16x2, 2 SSV mix, 3 VIADDMNMX.S32. Result in giga
+ * thread-instructions per second over the whole GPU. */
+int pa_microbench_dpx(pa_ctx *ctx, int mode, double *ginstr_per_s);
+
 /* Hit -> reference-column mapping (extend_pos = 0). For hit h: model/aligned strings (PhyloAln
  * form: upper case, '-' for gaps) at ali_off[h]..ali_off[h+1]; raw read nucleotides at
  * read_off[h]..; hmm_from/to, ali_from/to 1-based; frame 0..2 or -1 (nucleotide mode);

@@ -49,7 +49,7 @@ MAPREC_DTYPE = np.dtype(PaMapRec)
 
 EXPORTS = ["pa_abi_version", "pa_create", "pa_destroy", "pa_last_error", "pa_set_opts", "pa_add_hmm", "pa_set_evparam",
            "pa_commit_hmms", "pa_num_hmms", "pa_load_reads", "pa_load_proteins", "pa_num_frames", "pa_get_targets",
-           "pa_search", "pa_get_hits", "pa_hit_pool_bytes", "pa_get_stats", "pa_score_all", "pa_map_hits"]
+           "pa_search", "pa_get_hits", "pa_hit_pool_bytes", "pa_get_stats", "pa_score_all", "pa_map_hits", "pa_microbench_dpx"]
 
 _lib = None
 
@@ -91,6 +91,7 @@ def load_library():
     L.pa_get_stats.argtypes = [vp, C.POINTER(PaStats)]
     L.pa_score_all.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp]
     L.pa_map_hits.argtypes = [vp, C.c_int32] + [vp] * 14 + [i32, C.c_double, vp, vp, vp, vp, i64, i64]
+    L.pa_microbench_dpx.argtypes = [vp, i32, C.POINTER(C.c_double)]
     _lib = L
     return L
 
@@ -209,6 +210,11 @@ class Context:
         st = PaStats()
         self._check(self.L.pa_get_stats(self.h, C.byref(st)), "pa_get_stats")
         return {f: getattr(st, f) for f, _ in PaStats._fields_}
+
+    def microbench_dpx(self, mode: int) -> float:
+        v = C.c_double()
+        self._check(self.L.pa_microbench_dpx(self.h, mode, C.byref(v)), "pa_microbench_dpx")
+        return v.value
 
     def score_all(self, hmm_idx: int, ntargets: int, want=("msv", "vit", "fwd", "bias")):
         out = {}

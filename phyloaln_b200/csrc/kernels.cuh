@@ -743,3 +743,30 @@ __global__ void __launch_bounds__(256) fwd_kernel(FwdArgs a) {
 }
 
 }  // namespace pa
+
+// ---------------------------------------------------------------------------------------------
+// integer-pipe microbenchmark: independent VIADDMNMX.S16x2(.RELU) / VIMNMX3.S16x2 chains.
+// Gives the measured 16-bit lane-op peak the filter rooflines are quoted against.
+// ---------------------------------------------------------------------------------------------
+namespace pa {
+template <int MODE>
+__global__ void __launch_bounds__(256) dpx_microbench_kernel(uint32_t *out, int iters, uint32_t seed) {
+  uint32_t v[8], d = seed ^ threadIdx.x, m = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) v[i] = (threadIdx.x * 2654435761u + i) & 0x00ff00ffu;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      if (MODE == 0) v[i] = __viaddmax_s16x2_relu(v[i], d, 0u);          // SSV cell op
+      if (MODE == 1) v[i] = __vimax3_s16x2(v[i], d, m);                  // 3-input max
+      if (MODE == 2) { v[i] = __viaddmax_s16x2_relu(v[i], d, 0u); if (i & 1) m = __vimax3_s16x2(m, v[i], v[i - 1]); }  // SSV mix
+      if (MODE == 3) v[i] = (uint32_t)__viaddmax_s32((int)v[i], (int)d, -32768);  // Viterbi op
+    }
+    d += 0x00010001u;
+  }
+  uint32_t r = m;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r ^= v[i];
+  if (r == 0x12345678u) out[0] = r;
+}
+}  // namespace pa
