@@ -73,6 +73,7 @@ def calibrate_on_gpu(ctx, hmms, seed=42, n=200):
         tau = gmu - math.log(-math.log(1.0 - 0.04)) / lam
         h.stats = {"MSV": (round(mmu, 4), round(lam, 5)), "VITERBI": (round(vmu, 4), round(lam, 5)),
                    "FORWARD": (round(tau, 4), round(lam, 5))}
+    for i, h in enumerate(hmms):
         ctx.set_evparam(i, h.evparams())
     ctx.commit()
 
