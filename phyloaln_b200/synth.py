@@ -52,6 +52,13 @@ def sample_protein(hmm: HMM, rng: np.random.Generator, start: int = 1, end: int 
     return "".join(alphabet[rng.choice(len(alphabet), p=row)] for row in p)
 
 
+def consensus_protein(hmm: HMM, start: int = 1, end: int | None = None) -> str:
+    """Most probable residue of match states start..end."""
+    end = end or hmm.M
+    alphabet = AMINO if hmm.abc == "amino" else DNA
+    return "".join(alphabet[i] for i in np.argmin(hmm.mat[start:end + 1], axis=1))
+
+
 def back_translate(prot: str) -> str:
     return "".join(_CODON[a] for a in prot)
 
@@ -66,7 +73,7 @@ def random_reads(n: int, length: int, rng: np.random.Generator, n_frac: float = 
 
 
 def plant_reads(reads: np.ndarray, hmms: list[HMM], frac: float, rng: np.random.Generator, sub_rate: float = 0.05):
-    """Overwrite a fraction of reads with back-translated profile fragments (random strand)."""
+    """Overwrite a fraction of reads with back-translated profile-consensus fragments."""
     n, length = reads.shape
     idx = rng.choice(n, size=int(n * frac), replace=False)
     comp = bytes.maketrans(b"ACGT", b"TGCA")
@@ -76,7 +83,7 @@ def plant_reads(reads: np.ndarray, hmms: list[HMM], frac: float, rng: np.random.
         if h.M < naa + 2:
             continue
         s = int(rng.integers(1, h.M - naa + 1))
-        nt = back_translate(sample_protein(h, rng, s, s + naa - 1))
+        nt = back_translate(consensus_protein(h, s, s + naa - 1))
         off = int(rng.integers(0, length - len(nt) + 1))
         b = bytearray(reads[r].tobytes())
         b[off:off + len(nt)] = nt.encode()
