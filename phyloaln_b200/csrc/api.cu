@@ -191,7 +191,7 @@ extern "C" int pa_set_opts(pa_ctx *ctx, const pa_opts *o) {
 extern "C" int pa_add_hmm(pa_ctx *ctx, const char *name, int abc, int M, const double *mat, const double *ins,
                           const double *t, const double *compo, const char *cons, const float *evparam) {
   if (!ctx) return -1;
-  if (M < 1 || M > 2048) { ctx->err = "profile length must be 1..2048"; return -2; }
+  if (M < 1 || M > 2047) { ctx->err = "profile length must be 1..2047"; return -2; }
   if (abc != PA_AMINO && abc != PA_DNA) { ctx->err = "unknown alphabet"; return -2; }
   if (!ctx->hmms.empty() && ctx->hmms[0].abc != abc) { ctx->err = "all profiles of a context must share one alphabet"; return -2; }
   if (ctx->hmms.size() >= 65535) { ctx->err = "too many profiles (max 65535)"; return -2; }
@@ -242,7 +242,7 @@ extern "C" int pa_commit_hmms(pa_ctx *ctx) {
     d.M = M;
     d.abc = hp.abc;
     d.nrows = Kp;
-    d.Q = (M + 63) / 64;
+    d.Q = M / 64 + 1;  // the last striped cell must be padding (see msv_kernel)
     d.B = (M + 31) / 32;
     ctx->maxB = std::max(ctx->maxB, d.B);
     ctx->maxM = std::max(ctx->maxM, M);

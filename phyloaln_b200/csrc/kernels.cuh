@@ -246,6 +246,7 @@ struct MsvArgs {
   unsigned long long out_cap;
   unsigned long long *n_ssv_cand;
   int all_pairs;           // 1: emit every pair with its exact MSV result (score_all)
+  uint32_t zero;           // always 0; a run-time value so ptxas cannot re-materialise {0,0} per use
 };
 
 template <int Q>
@@ -257,6 +258,10 @@ __global__ void __launch_bounds__(256, 2) msv_kernel(MsvArgs a) {
   int cur_h = -1;
   unsigned long long ncand = 0;
   constexpr int ROWW = Q * 32;
+  // Q = M/64 + 1, so the very last striped cell (lane 31, high half, word Q-1) is always padding and
+  // stays 0: the row carry can wrap around from lane 31 to lane 0 without a select.
+  const int lanem1 = (lane + 31) & 31;
+  const uint32_t zero = a.zero;
   for (unsigned long long item = blockIdx.x; item < nitems; item += gridDim.x) {
     const int h = a.hmm_list[item / ntiles];
     const uint32_t tile = (uint32_t)(item % ntiles);
@@ -289,23 +294,31 @@ __global__ void __launch_bounds__(256, 2) msv_kernel(MsvArgs a) {
       for (int q = 0; q < Q; q++) w[q] = 0;
       uint32_t m = 0;
       if (Cp > 0) {
-        for (int i0 = 0; i0 < L; i0 += 4) {
-          const uint32_t r4 = *reinterpret_cast<const uint32_t *>(p + i0);
-          const int nr = min(4, L - i0);
-          for (int r = 0; r < nr; r++) {
-            const int x = (r4 >> (8 * r)) & 0xff;
-            uint32_t d[Q];
-            msv_load_row<Q>(s_tab + x * ROWW, lane, d);
-            uint32_t tt = __shfl_up_sync(PA_FULL, w[Q - 1], 1);
-            if (lane == 0) tt = 0;
-            const uint32_t carry = __byte_perm(tt, w[Q - 1], 0x5432);
-#pragma unroll
-            for (int q = Q - 1; q >= 1; q--) w[q] = __viaddmax_s16x2_relu(w[q - 1], d[q], 0u);
-            w[0] = __viaddmax_s16x2_relu(carry, d[0], 0u);
-#pragma unroll
-            for (int q = 0; q + 1 < Q; q += 2) m = __vimax3_s16x2(m, w[q], w[q + 1]);
-            if (Q & 1) m = __vmaxs2(m, w[Q - 1]);
+        // each lane fetches one residue of a 32-row block and turns it into a table-row offset;
+        // rows then get their offset by shuffle: no ALU work for addressing in the row body
+        uint32_t myoff = (lane < L) ? (uint32_t)p[lane] * ROWW : 0u;
+        for (int i0 = 0; i0 < L; i0 += 32) {
+          const uint32_t curoff = myoff;
+          if (i0 + 32 < L) myoff = (i0 + 32 + lane < L) ? (uint32_t)p[i0 + 32 + lane] * ROWW : 0u;
+          const int nr = min(32, L - i0);
+#define PA_SSV_ROW(rr)                                                                     \
+  {                                                                                        \
+    const uint32_t ro = __shfl_sync(PA_FULL, curoff, (rr));                                \
+    uint32_t d[Q];                                                                         \
+    msv_load_row<Q>(s_tab + ro, lane, d);                                                  \
+    const uint32_t tt = __shfl_sync(PA_FULL, w[Q - 1], lanem1);                            \
+    const uint32_t carry = __byte_perm(tt, w[Q - 1], 0x5432);                              \
+    _Pragma("unroll") for (int q = Q - 1; q >= 1; q--) w[q] = __viaddmax_s16x2(w[q - 1], d[q], zero); \
+    w[0] = __viaddmax_s16x2(carry, d[0], zero);                                            \
+    _Pragma("unroll") for (int q = 0; q + 1 < Q; q += 2) m = __vimax3_s16x2(m, w[q], w[q + 1]); \
+    if (Q & 1) m = __vmaxs2(m, w[Q - 1]);                                                  \
+  }
+          int r = 0;
+          for (; r + 4 <= nr; r += 4) {
+            PA_SSV_ROW(r) PA_SSV_ROW(r + 1) PA_SSV_ROW(r + 2) PA_SSV_ROW(r + 3)
           }
+          for (; r < nr; r++) PA_SSV_ROW(r)
+#undef PA_SSV_ROW
         }
       }
       const int U = (Cp > 0) ? warp_max16x2(m) : 0;
@@ -321,16 +334,15 @@ __global__ void __launch_bounds__(256, 2) msv_kernel(MsvArgs a) {
         uint32_t d[Q];
         msv_load_row<Q>(s_tab + x * ROWW, lane, d);
         const uint32_t xBv = (uint32_t)xB * 0x10001u;
-        uint32_t tt = __shfl_up_sync(PA_FULL, w[Q - 1], 1);
-        if (lane == 0) tt = 0;
+        const uint32_t tt = __shfl_sync(PA_FULL, w[Q - 1], lanem1);
         const uint32_t carry = __byte_perm(tt, w[Q - 1], 0x5432);
         uint32_t rm = 0;
 #pragma unroll
         for (int q = Q - 1; q >= 1; q--) {
-          w[q] = __viaddmax_s16x2_relu(__vmaxs2(w[q - 1], xBv), d[q], 0u);
+          w[q] = __viaddmax_s16x2(__vmaxs2(w[q - 1], xBv), d[q], zero);
           rm = __vmaxs2(rm, w[q]);
         }
-        w[0] = __viaddmax_s16x2_relu(__vmaxs2(carry, xBv), d[0], 0u);
+        w[0] = __viaddmax_s16x2(__vmaxs2(carry, xBv), d[0], zero);
         rm = __vmaxs2(rm, w[0]);
         int xE = warp_max16x2(rm);
         if (xE >= 255 - bias) { overflow = true; break; }
