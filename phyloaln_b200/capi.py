@@ -90,7 +90,7 @@ def load_library():
     L.pa_hit_pool_bytes.argtypes = [vp]
     L.pa_get_stats.argtypes = [vp, C.POINTER(PaStats)]
     L.pa_score_all.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp]
-    L.pa_map_hits.argtypes = [vp, C.c_int32] + [vp] * 14 + [i32, C.c_double, vp, vp, vp, vp, i64, i64]
+    L.pa_map_hits.argtypes = [vp, C.c_int32, C.c_char_p, C.c_char_p, vp, C.c_char_p] + [vp] * 10 + [i32, C.c_double, vp, vp, vp, vp, i64, i64]
     L.pa_microbench_dpx.argtypes = [vp, i32, C.POINTER(C.c_double)]
     _lib = L
     return L

@@ -1,0 +1,86 @@
+"""Drop-in for PhyloAln's per-alignment ``hmmsearch`` + ``extract_reads`` step.
+
+The reference runs, inside ``assemble(g)`` (/root/reference/lib/aln.py:650-674), one ``hmmsearch``
+child per alignment over the whole ``all.target.fasta`` and then parses its text report.  The
+B200 path inverts the loop nest (SURVEY.md section 8b "Batching reality"): ONE batched search
+streams the reads once against ALL profiles, then writes for every alignment g exactly the files
+``assemble(g)`` would have produced -- ``map/{g}.hit_info.tsv``, ``map/{g}.targets.fas``,
+``map/{g}.hmmsearch.log`` and the markers ``ok/hmmsearch_{g}.ok``, ``ok/extract_reads_{g}.ok`` -- so
+the unchanged ``assemble(g)`` finds its resume markers and continues at lib/aln.py:745.
+Call :func:`hmmsearch_step` between ``prepare_target`` (lib/main.py:237) and ``assemble_mp`` (:250).
+"""
+from __future__ import annotations
+
+import gzip
+import os
+
+import numpy as np
+
+from .hmmio import read_hmm
+from .search import B200Searcher, parse_hmmsearch_parameters, write_step_outputs, write_tblout
+
+
+def read_raw_fasta(path: str):
+    """all.raw.fasta (single-line FASTA written by prepare_target, lib/aln.py:443-456).
+
+    Dictionary semantics as in raw2target()/read_fastx (lib/library.py:186-198): a repeated id keeps
+    its first position but the LAST sequence wins.
+    Returns (ids, nt uint8 array, offsets uint64[n+1])."""
+    opener = gzip.open if path.endswith(".gz") else open
+    seqs: dict[str, bytes] = {}
+    name = None
+    with opener(path, "rb") as fh:
+        for line in fh:
+            line = line.rstrip(b"\r\n")
+            if line.startswith(b">"):
+                name = line[1:].split(b" ")[0].decode()
+                seqs[name] = b""
+            elif name is not None:
+                seqs[name] += line
+    ids = list(seqs)
+    off = np.zeros(len(ids) + 1, dtype=np.uint64)
+    off[1:] = np.cumsum([len(seqs[i]) for i in ids])
+    nt = np.frombuffer(b"".join(seqs[i] for i in ids), dtype=np.uint8)
+    return ids, nt, off
+
+
+def hmmsearch_step(outdir: str, groups, mol_type: str = "prot", gencode: int = 1, no_reverse: bool = False,
+                   codon: bool = False, hmmsearch_parameters=(), devices=(0,), raw_fasta: str | None = None,
+                   write_tbl: bool = True):
+    """Batched replacement of ``for g in groups: hmmsearch g.hmm all.target.fasta; extract_reads(g)``.
+
+    Returns {g: number of hit_info rows}.  Raises on any failure (the reference returns (1, g) per
+    failed group, lib/aln.py:669-672; here the whole batch fails loudly -- there is no CPU fallback)."""
+    groups = list(groups)
+    opts = parse_hmmsearch_parameters(hmmsearch_parameters)
+    todo = [g for g in groups if not (os.path.isfile(os.path.join(outdir, "ok", f"hmmsearch_{g}.ok")) and
+                                      os.path.isfile(os.path.join(outdir, "ok", f"extract_reads_{g}.ok")))]
+    counts = {}
+    if not todo:
+        return counts
+    hmms = [read_hmm(os.path.join(outdir, "ref_hmm", g + ".hmm")) for g in todo]
+    raw_fasta = raw_fasta or os.path.join(outdir, "all.raw.fasta")
+    ids, nt, off = read_raw_fasta(raw_fasta)
+    # '--codon' forces no_reverse in the reference (lib/main.py:196-198)
+    if codon:
+        no_reverse = True
+    searcher = B200Searcher(hmms, devices=devices, options=opts)
+    try:
+        rep, nframes, translated = searcher.search_and_report(nt, off, ids, mol_type=mol_type, gencode=gencode,
+                                                              no_reverse=no_reverse, codon=codon)
+        stats = [c.stats() for c in searcher.ctxs]
+    finally:
+        searcher.close()
+    raw = nt.tobytes()
+
+    def raw_seq(read):
+        return raw[int(off[read]):int(off[read + 1])].decode()
+    for hi, g in enumerate(todo):
+        rows = rep[hi]
+        log = [f"phyloaln_b200 batched search: {len(ids)} reads x {len(todo)} profiles on GPU(s) {list(devices)}",
+               f"Z = {len(ids) * nframes} targets; reported domains for {g}: {len(rows)}", f"stats: {stats}"]
+        write_step_outputs(outdir, g, rows, ids, raw_seq, nframes, translated, log)
+        if write_tbl:
+            write_tblout(os.path.join(outdir, "map", g + ".hmmsearch.tbl"), g, rows)
+        counts[g] = len(rows)
+    return counts

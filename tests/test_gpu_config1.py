@@ -1,0 +1,96 @@
+"""GPU parity at full config-1 size (BASELINE.json configs[0]): the reference's own test reads
+(prepare_target output, committed as a golden fixture) against the five tests/ref profiles, and the
+hit -> reference-column mapping against vectors produced by the reference's Python."""
+import gzip
+import json
+import os
+import shutil
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+C1 = os.path.join(GOLD, "config1")
+GROUPS = ["OG0003531", "OG0003709", "OG0003820", "OG0003977", "OG0004212"]
+
+
+def test_config1_dropin_outputs_identical_to_golden(tmp_path):
+    from phyloaln_b200 import dropin
+    out = tmp_path / "run"
+    (out / "ref_hmm").mkdir(parents=True)
+    for g in GROUPS:
+        shutil.copy(os.path.join(C1, "ref_hmm", g + ".hmm"), out / "ref_hmm" / (g + ".hmm"))
+    with gzip.open(os.path.join(C1, "all.raw.fasta.gz"), "rb") as f, open(out / "all.raw.fasta", "wb") as g:
+        shutil.copyfileobj(f, g)
+    counts = dropin.hmmsearch_step(str(out), GROUPS, mol_type="codon", gencode=1)
+    total = 0
+    for g in GROUPS:
+        got = open(out / "map" / (g + ".hit_info.tsv")).read()
+        want = open(os.path.join(C1, "hit_info", g + ".hit_info.tsv")).read()
+        assert got == want, g
+        assert os.path.isfile(out / "ok" / f"hmmsearch_{g}.ok") and os.path.isfile(out / "ok" / f"extract_reads_{g}.ok")
+        # targets.fas: one record per distinct read, first-seen order, raw nucleotides
+        ids = []
+        for line in want.splitlines():
+            rid = line.split("\t")[1]
+            if rid not in ids:
+                ids.append(rid)
+        fas = open(out / "map" / (g + ".targets.fas")).read().splitlines()
+        assert fas[0::2] == [">" + i for i in ids]
+        total += counts[g]
+    assert total == 777
+    # second call: resume markers present -> nothing to do (lib/aln.py:653-654, 484-488)
+    assert dropin.hmmsearch_step(str(out), GROUPS, mol_type="codon") == {}
+
+
+def test_config1_scores_within_tolerance(gpu_ctx_factory):
+    from phyloaln_b200 import dropin, hmmio, search
+    ids, nt, off = dropin.read_raw_fasta(os.path.join(C1, "all.raw.fasta.gz"))
+    hmms = [hmmio.read_hmm(os.path.join(C1, "ref_hmm", g + ".hmm")) for g in GROUPS]
+    s = search.B200Searcher(hmms)
+    rep, nframes, translated = s.search_and_report(nt, off, ids, mol_type="codon")
+    s.close()
+    for hi, g in enumerate(GROUPS):
+        want = [l.split("\t") for l in open(os.path.join(C1, "hit_info", g + ".scores.tsv")).read().splitlines()]
+        assert len(want) == len(rep[hi])
+        for w, r in zip(want, rep[hi]):
+            assert w[0] == r["name"] and int(w[1]) == r["dom_idx"]
+            assert abs(float(w[2]) - r["seq_bits"]) < 0.01 and abs(float(w[4]) - r["dom_bits"]) < 0.01
+            # E-values within 1e-3 relative <=> lnP within 1e-3 absolute
+            assert abs(float(w[3]) - np.log(r["seq_evalue"] / (len(ids) * nframes))) < 1e-3
+
+
+def test_mapping_kernel_matches_reference_python(gpu_ctx_factory):
+    from phyloaln_b200 import mapping
+    cases = json.load(open(os.path.join(GOLD, "mapping_golden.json")))
+    comps = {c["group"]: mapping.composition_table({int(k): v for k, v in c["site_composition"].items()})
+             for c in cases if "site_composition" in c}
+    kat = [c for c in cases if c["group"] == "KAT5"][0]
+    comps["g"] = mapping.composition_table({int(k): v for k, v in kat["site_composition_inline"].items()})
+    todo = [c for c in cases if "row" in c]
+    rows, reads = [], {}
+    for i, c in enumerate(todo):
+        r = list(c["row"])
+        r[1] = f"{r[1]}#{i}"           # unique key per case (several cases share a read id)
+        reads[r[1]] = c["read"]
+        rows.append(r)
+    ctx = gpu_ctx_factory()
+    got = mapping.map_hits(ctx, rows, reads, comps, trim_pos=5, pos_freq=0.2)
+    ctx.close()
+    n_trim = n_unmap = 0
+    for c, g in zip(todo, got):
+        if not c["keep"]:
+            assert g is None
+            continue
+        assert g is not None, c["row"]
+        assert (g["qstart"], g["qend"], g["start_trim"], g["end_trim"]) == (c["qstart"], c["qend"], c["start_trim"], c["end_trim"]), c["row"]
+        assert [g["qstart"], g["qend"], g["ali_from"], g["ali_to"]] == [int(x) for x in c["trimmed"]]
+        assert g["base"] == c["base"], c["row"]
+        if c["codon"] is not None:
+            assert g["codon"] == c["codon"], c["row"]
+        assert [g["interval"]] == c["seqids"], c["row"]
+        assert g["unmap"] == c["unmap"], c["row"]
+        n_trim += bool(c["start_trim"] or c["end_trim"])
+        n_unmap += bool(c["unmap"])
+    assert n_trim > 20 and n_unmap > 20
