@@ -87,6 +87,13 @@ def lib():
         for f in (L.orc_gumbel_surv, L.orc_exp_surv, L.orc_exp_logsurv):
             f.restype = C.c_double
             f.argtypes = [C.c_double, C.c_double, C.c_double]
+        L.orc_profile_tsc.restype = C.c_float
+        L.orc_profile_tsc.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.orc_profile_msc.restype = C.c_float
+        L.orc_profile_msc.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        for f in (L.orc_profile_rbv, L.orc_profile_rwv):
+            f.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.orc_profile_bytes.argtypes = [C.c_void_p, C.c_int]
         _LIB = L
     return _LIB
 

@@ -452,3 +452,12 @@ float orc_null1(int L) {
   float p1 = (float)L / (float)(L + 1);
   return (float)((double)L * log((double)p1) + log(1.0 - (double)p1));
 }
+
+/* accessors for tests (brute-force path enumeration against the configured profile) */
+float orc_profile_tsc(const ORC_PROFILE *p, int k, int t) { return p->tsc[k * 8 + t]; }
+float orc_profile_msc(const ORC_PROFILE *p, int x, int k) { return p->msc[x * (p->M + 1) + k]; }
+int orc_profile_rbv(const ORC_PROFILE *p, int x, int k) { return p->rbv[x * (p->M + 1) + k]; }
+int orc_profile_rwv(const ORC_PROFILE *p, int x, int k) { return p->rwv[x * (p->M + 1) + k]; }
+int orc_profile_bytes(const ORC_PROFILE *p, int which) {
+  switch (which) { case 0: return p->tbm_b; case 1: return p->tec_b; case 2: return p->bias_b; default: return p->base_b; }
+}

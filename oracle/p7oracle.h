@@ -117,6 +117,12 @@ const char *orc_hmm_name(const ORC_HMM *h);
 ORC_PROFILE *orc_profile_create(const ORC_HMM *h);
 void orc_profile_free(ORC_PROFILE *p);
 
+float orc_profile_tsc(const ORC_PROFILE *p, int k, int t);
+float orc_profile_msc(const ORC_PROFILE *p, int x, int k);
+int orc_profile_rbv(const ORC_PROFILE *p, int x, int k);
+int orc_profile_rwv(const ORC_PROFILE *p, int x, int k);
+int orc_profile_bytes(const ORC_PROFILE *p, int which);
+
 int orc_digitize(int abc, const char *seq, int n, uint8_t *out);  /* returns #invalid */
 char orc_sym(int abc, int code);
 

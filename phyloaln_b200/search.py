@@ -206,6 +206,29 @@ def write_tblout(path: str, query: str, rows):
                      f"{r['ndom']:3d} {r['ndom']:3d} {len(doms):3d} {len(doms):3d} -\n")
 
 
+def shard_bounds(nreads: int, world: int, rank: int):
+    """Contiguous read range of one rank (reads shard by chunk; profiles are replicated)."""
+    per = (nreads + world - 1) // world
+    return min(nreads, rank * per), min(nreads, (rank + 1) * per)
+
+
+def gather_hits_distributed(hits: np.ndarray, model, aligned, dst: int = 0):
+    """Host-side gather of per-rank hit lists (the only cross-rank step; no collective on the DP path).
+
+    Uses torch.distributed object gather so it works with the nccl and gloo backends alike.
+    Returns (hits, model, aligned) on rank dst, (None, None, None) elsewhere."""
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(), dist.get_rank()
+    payload = (hits.tobytes(), list(model), list(aligned))
+    bucket = [None] * world if rank == dst else None
+    dist.gather_object(payload, bucket, dst=dst)
+    if rank != dst:
+        return None, None, None
+    parts = [np.frombuffer(b[0], dtype=capi.HIT_DTYPE) for b in bucket]
+    allhits = np.concatenate(parts) if parts else np.zeros(0, dtype=capi.HIT_DTYPE)
+    return allhits, [m for b in bucket for m in b[1]], [m for b in bucket for m in b[2]]
+
+
 class B200Searcher:
     """All profiles x one read set on one or more B200s (one context per GPU, reads sharded by chunk)."""
 

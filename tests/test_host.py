@@ -1,0 +1,164 @@
+"""CPU tests of the host logic and of the C-ABI surface (no GPU compute)."""
+import math
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_cabi_library_loads_and_exports_every_declared_symbol():
+    from phyloaln_b200 import capi
+    L = capi.load_library()
+    header = open(os.path.join(ROOT, "include", "phyloaln_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = sorted(set(re.findall(r"\b(pa_[a-z_0-9]+)\s*\(", header)))
+    assert len(declared) >= 19
+    for sym in declared:
+        assert hasattr(L, sym), f"{sym} declared in include/phyloaln_b200.h but not exported"
+    assert set(capi.EXPORTS) <= set(declared)
+    assert L.pa_abi_version() == 1
+
+
+def test_no_gpu_is_a_loud_error():
+    from phyloaln_b200 import capi
+    try:
+        ctx = capi.Context(0)
+    except capi.PaError as e:       # build container: no device -> must refuse, never fall back
+        assert "CUDA" in str(e) or "device" in str(e)
+        return
+    ctx.close()                     # on a GPU box the context simply works
+
+
+def test_struct_layouts_match_header():
+    from phyloaln_b200 import capi
+    import ctypes
+    assert ctypes.sizeof(capi.PaHit) == 120 and ctypes.sizeof(capi.PaMapRec) == 56 and ctypes.sizeof(capi.PaOpts) == 40
+    assert capi.HIT_DTYPE.itemsize == 120
+
+
+def test_parse_hmmsearch_parameters():
+    from phyloaln_b200.search import SearchParameterError, parse_hmmsearch_parameters as p
+    o = p([" -E", "1e-5", " --domE", "0.1", " --nobias", " --cpu", "4"])
+    assert (o.E, o.domE, o.nobias, o.max, o.T) == (1e-5, 0.1, True, False, None) and o.ignored == ["--cpu"]
+    o = p(["-T 25 --domT 20 -Z 1000 --domZ 10 --F1 0.1 --F2 0.01 --F3 1e-4 --max --nonull2"])
+    assert (o.T, o.domT, o.Z, o.domZ, o.F1, o.F2, o.F3, o.max, o.nonull2) == (25, 20, 1000, 10, 0.1, 0.01, 1e-4, True, True)
+    assert p([]).E == 10.0 and p(None).domE == 10.0
+    for bad in (["--cut_ga"], ["-E"], ["-E", "abc"], ["--bogus"]):
+        with pytest.raises(SearchParameterError):
+            p(bad)
+
+
+def test_frame_naming_and_rows():
+    from phyloaln_b200 import search
+    assert [search.frame_suffix(f, 6, True) for f in range(6)] == [("_pos1", "+", 0), ("_pos2", "+", 1), ("_pos3", "+", 2),
+                                                                    ("_rev_pos1", "rev", 0), ("_rev_pos2", "rev", 1), ("_rev_pos3", "rev", 2)]
+    assert search.frame_suffix(0, 1, True) == ("_pos1", "+", 0)                     # --codon
+    assert [search.frame_suffix(f, 3, True) for f in range(3)] == [("_pos1", "+", 0), ("_pos2", "+", 1), ("_pos3", "+", 2)]
+    assert [search.frame_suffix(f, 2, False) for f in range(2)] == [("", "+", None), ("_rev", "rev", None)]
+    rows = [{"target": 9, "hmmfrom": 2, "hmmto": 9, "alifrom": 1, "alito": 9, "model": "ktayi.akq", "aligned": "KTAYIwAKQ"}]
+    assert search.hit_rows("g", rows, ["r0", "r1"], 6, True) == [("g", "r1", 2, 9, 1, 9, "rev", 0, "KTAYI-AKQ", "KTAYIWAKQ")]
+    assert search.hit_rows("g", [dict(rows[0], target=1)], ["r0"], 2, False)[0][6:8] == ("rev", None)
+    assert search.shard_bounds(10, 4, 0) == (0, 3) and search.shard_bounds(10, 4, 3) == (9, 10) and search.shard_bounds(2, 4, 3) == (2, 2)
+
+
+def _fake_hits(oracle):
+    """Oracle hits of two profiles recast into the product's hit record layout."""
+    from phyloaln_b200 import capi
+    from tests import helpers
+    rng = np.random.default_rng(21)
+    hmms = [helpers.calibrated_hmm(f"rp{i}", M, seed=70 + i, bg_mix=0.1) for i, M in enumerate([60, 110])]
+    seqs = helpers.protein_targets(hmms, 600, rng, Lmin=30, Lmax=60, plant_every=4)
+    names = [f"read{i // 6}_pos{i % 6}" for i in range(len(seqs))]
+    recs, model, aligned, per = [], [], [], []
+    for hi, h in enumerate(hmms):
+        oh, _ = oracle.Profile.from_hmm(h).search(seqs, nthreads=4, want_trace=False)
+        per.append(oh)
+        for d in oh:
+            r = np.zeros(1, dtype=capi.HIT_DTYPE)[0]
+            r["hmm"] = hi
+            for f in ("target", "ndom_in_seq", "dom_idx", "ienv", "jenv", "iali", "jali", "hmmfrom", "hmmto", "dom_bits", "dom_lnP",
+                      "seq_bits", "seq_lnP", "seqbias", "dombias"):
+                r[f] = d[f]
+            recs.append(r)
+            model.append(d["model"])
+            aligned.append(d["aligned"])
+    return hmms, seqs, names, np.array(recs, dtype=capi.HIT_DTYPE), model, aligned, per
+
+
+def test_report_matches_oracle_report(oracle):
+    from oracle import report as orep
+    from phyloaln_b200 import search
+    hmms, seqs, names, hits, model, aligned, per = _fake_hits(oracle)
+    Z = 5.0e6   # large Z so that the E-value thresholds actually cut
+    perm = np.random.default_rng(1).permutation(len(hits))
+    rep = search.report(hits[perm], [model[i] for i in perm], [aligned[i] for i in perm], lambda t: names[t], Z,
+                        search.SearchOptions(), len(hmms))
+    kept = 0
+    for hi in range(len(hmms)):
+        want = orep.apply_report(per[hi], names, Z)
+        got = rep[hi]
+        assert [(w["target"], w["dom_idx"]) for w in want] == [(g["target"], g["dom_idx"]) for g in got]
+        assert [w["model"] for w in want] == [g["model"] for g in got]
+        kept += len(got)
+        assert len(got) < len(per[hi])          # thresholds removed something
+    assert kept > 20
+    # explicit score thresholds
+    o = search.SearchOptions(T=30.0, domT=25.0)
+    rep = search.report(hits, model, aligned, lambda t: names[t], Z, o, len(hmms))
+    for hi in range(len(hmms)):
+        assert all(r["seq_bits"] >= 30.0 and r["dom_bits"] >= 25.0 for r in rep[hi])
+
+
+def test_write_step_outputs_and_resume_markers(tmp_path, oracle):
+    from phyloaln_b200 import search
+    rows = [{"target": 7, "hmmfrom": 2, "hmmto": 9, "alifrom": 1, "alito": 9, "model": "KTAYI.AKQ", "aligned": "KTAYIwAKQ",
+             "name": "r1_pos2", "seq_evalue": 1e-9, "seq_bits": 40.0, "seq_bias": 0.1, "dom_ievalue": 1e-9, "dom_bits": 39.0,
+             "dom_bias": 0.1, "ndom": 1},
+            {"target": 7, "hmmfrom": 20, "hmmto": 22, "alifrom": 12, "alito": 14, "model": "AAA", "aligned": "AAA",
+             "name": "r1_pos2", "seq_evalue": 1e-9, "seq_bits": 40.0, "seq_bias": 0.1, "dom_ievalue": 1e-3, "dom_bits": 9.0,
+             "dom_bias": 0.0, "ndom": 1}]
+    search.write_step_outputs(str(tmp_path), "g", rows, ["r0", "r1"], lambda i: ["ACGT", "GGCC"][i], 6, True, ["log line"])
+    assert open(tmp_path / "map" / "g.hit_info.tsv").read() == "g\tr1\t2\t9\t1\t9\t+\t1\tKTAYI-AKQ\tKTAYIWAKQ\ng\tr1\t20\t22\t12\t14\t+\t1\tAAA\tAAA\n"
+    assert open(tmp_path / "map" / "g.targets.fas").read() == ">r1\nGGCC\n"
+    assert os.path.isfile(tmp_path / "ok" / "hmmsearch_g.ok") and os.path.isfile(tmp_path / "ok" / "extract_reads_g.ok")
+    search.write_tblout(str(tmp_path / "g.tbl"), "g", rows)
+    assert "r1_pos2" in open(tmp_path / "g.tbl").read()
+
+
+def test_read_raw_fasta_dictionary_semantics(tmp_path):
+    from phyloaln_b200 import dropin
+    p = tmp_path / "all.raw.fasta"
+    p.write_text(">a_PhAlTag_S_fastx1\nACGT\n>b_PhAlTag_S_fastx1\nGG\n>a_PhAlTag_S_fastx1\nTTTTT\n")
+    ids, nt, off = dropin.read_raw_fasta(str(p))
+    assert ids == ["a_PhAlTag_S_fastx1", "b_PhAlTag_S_fastx1"] and nt.tobytes() == b"TTTTTGG" and list(off) == [0, 5, 7]
+
+
+def test_hmmbuild_lite_and_file_roundtrip(tmp_path):
+    from phyloaln_b200 import hmmbuild_lite as hb, hmmio
+    aln = {"A.1": "MKTAYIAKQRQI--SF", "B.1": "MKTAYIAKQRQIGGSF", "C.1": "MKSAYIGKQRQL--SF", "OUT.1": "MRSAF-GKNRQL--AF"}
+    hmm, mcols = hb.build_from_alignment("t", aln, "amino")
+    assert hmm.M == 14 and mcols == [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 14, 15]
+    p = np.exp(-hmm.mat[1:])
+    assert np.allclose(p.sum(1), 1, atol=1e-6) and np.allclose(np.exp(-hmm.t[:, 0:3]).sum(1), 1, atol=1e-6)
+    assert hmm.consensus().upper().startswith("MK") and math.isinf(hmm.t[0][6]) and hmm.t[hmm.M][5] < 1e-9
+    with pytest.raises(hmmio.HMMFormatError):
+        hmm.evparams()
+    hmm.stats = {"MSV": (-9.5, 0.71), "VITERBI": (-10.2, 0.71), "FORWARD": (-4.1, 0.71)}
+    hmmio.write_hmm(hmm, str(tmp_path / "t.hmm"))
+    h2 = hmmio.read_hmm(str(tmp_path / "t.hmm"))
+    assert h2.M == hmm.M and h2.cons == hmm.cons and h2.map == hmm.map and list(h2.evparams()) == list(hmm.evparams())
+    assert np.allclose(h2.mat[1:], hmm.mat[1:], atol=6e-6) and np.array_equal(np.isinf(h2.t), np.isinf(hmm.t))
+    with pytest.raises(hmmio.HMMFormatError):
+        (tmp_path / "bad.hmm").write_text("not an hmm\n")
+        hmmio.read_hmm(str(tmp_path / "bad.hmm"))
+    dna, _ = hb.build_from_alignment("d", {"a": "ACGTACGTNN", "b": "ACGTACGTAC"}, "dna")
+    assert dna.K == 4 and dna.M == 10
+
+
+def test_composition_table():
+    from phyloaln_b200 import mapping
+    tab = mapping.composition_table({1: {"M": 3}, 2: {"K": 2, "-": 1}, 3: {"*": 1, "X": 2}})
+    assert tab.shape == (3, 32) and tab[0, 12] == 3 and tab[1, 26] == 1 and tab[2, 27] == 1 and tab[2, 23] == 2
