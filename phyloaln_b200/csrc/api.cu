@@ -75,6 +75,8 @@ struct pa_ctx {
   DevBuf<int> d_hmm_lists;
   std::map<int, std::pair<int, int>> q_groups;  // Q -> (offset, count) in d_hmm_lists
   int maxB = 1, maxM = 1;
+  std::vector<std::pair<int, std::pair<int, int>>> vit_classes;  // (Bv, (first rank, last rank + 1))
+  DevBuf<unsigned int> d_sort;  // cnt | start | cursor, each nh + 1
 
   // targets
   DevBuf<char> d_nt;
@@ -165,7 +167,7 @@ extern "C" pa_ctx *pa_create(int device, char *err, int errlen) {
 extern "C" void pa_destroy(pa_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
-  ctx->d_hmms.release(); ctx->d_msv.release(); ctx->d_vit.release(); ctx->d_fwd.release(); ctx->d_hmm_lists.release();
+  ctx->d_hmms.release(); ctx->d_msv.release(); ctx->d_vit.release(); ctx->d_fwd.release(); ctx->d_hmm_lists.release(); ctx->d_sort.release();
   ctx->d_nt.release(); ctx->d_ntoff.release(); ctx->d_dsq.release(); ctx->d_toff.release(); ctx->d_tlen.release();
   ctx->d_lidx.release(); ctx->d_codon.release(); ctx->d_flag.release();
   ctx->d_L.release(); ctx->d_nullsc.release(); ctx->d_biasA.release(); ctx->d_biasB.release(); ctx->d_tjb.release();
@@ -212,6 +214,13 @@ extern "C" int pa_set_evparam(pa_ctx *ctx, int h, const float *ev) {
 }
 
 extern "C" int pa_num_hmms(pa_ctx *ctx) { return ctx ? (int)ctx->hmms.size() : -1; }
+
+static int vit_class(int B) {
+  static const int cls[] = {1, 2, 3, 4, 6, 8, 10, 12, 14, 16, 20, 24, 28, 32, 40, 48, 56, 64};
+  for (int c : cls)
+    if (B <= c) return c;
+  return 64;
+}
 
 // word position of (q, lane) inside one striped MSV row of Q*32 words (see msv_load_row)
 static inline int msv_word_pos(int Q, int q, int lane) {
@@ -276,30 +285,36 @@ extern "C" int pa_commit_hmms(pa_ctx *ctx) {
           msv[d.msv_off + (size_t)x * roww + msv_word_pos(Q, q, lane)] = (uint32_t)(uint16_t)half[0] | ((uint32_t)(uint16_t)half[1] << 16);
         }
 
-    // ---- lane-blocked tables [j][lane], k = lane*B + j + 1
+    // ---- Viterbi tables, lane-blocked [j][lane] with the class-rounded block size Bv: k = lane*Bv + j + 1
+    d.Bv = vit_class(d.B);
+    {
+      const int Bv = d.Bv, Wv = Bv * 32;
+      while (vit.size() % 4) vit.push_back(0);
+      d.vit_off = vit.size();
+      vit.resize(vit.size() + (size_t)Wv * (9 + Kp), PA_NEG16);
+      int *vA = vit.data() + d.vit_off, *vI = vA + 4 * Wv, *vD = vI + 2 * Wv, *vps = vD + 2 * Wv, *vem = vps + Wv;
+      for (int c = 0; c < Wv; c++) {
+        const int k = (c % 32) * Bv + (c / 32) + 1;
+        if (k <= M) {
+          const int16_t *tp = &hp.twv[(size_t)(k - 1) * 8], *tk = &hp.twv[(size_t)k * 8];
+          vA[4 * c + 0] = tp[T_BM]; vA[4 * c + 1] = tp[T_MM]; vA[4 * c + 2] = tp[T_IM]; vA[4 * c + 3] = tp[T_DM];
+          vI[2 * c + 0] = tk[T_MI]; vI[2 * c + 1] = tk[T_II];
+          vD[2 * c + 0] = tp[T_MD]; vD[2 * c + 1] = tp[T_DD];
+          for (int x = 0; x < Kp; x++) vem[(size_t)x * Wv + c] = hp.rwv[(size_t)x * (M + 1) + k];
+        }
+      }
+      for (int lane = 0; lane < 32; lane++) {  // in-lane prefix sums of DD(k-1)
+        int sum = 0;
+        for (int j = 0; j < Bv; j++) {
+          const int c = j * 32 + lane;
+          sum += vD[2 * c + 1];
+          vps[c] = sum;
+        }
+      }
+    }
+    // ---- float tables, lane-blocked [j][lane] with the canonical B = ceil(M/32): k = lane*B + j + 1
     const int B = d.B, W = B * 32;
     auto cellk = [&](int c) { return (c % 32) * B + (c / 32) + 1; };
-    while (vit.size() % 4) vit.push_back(0);
-    d.vit_off = vit.size();
-    vit.resize(vit.size() + (size_t)W * (4 + 4 + 1 + Kp), PA_NEG16);
-    int *vA = vit.data() + d.vit_off, *vB = vA + 4 * W, *vps = vB + 4 * W, *vem = vps + W;
-    for (int c = 0; c < W; c++) {
-      const int k = cellk(c);
-      if (k <= M) {
-        const int16_t *tp = &hp.twv[(size_t)(k - 1) * 8], *tk = &hp.twv[(size_t)k * 8];
-        vA[4 * c + 0] = tp[T_BM]; vA[4 * c + 1] = tp[T_MM]; vA[4 * c + 2] = tp[T_IM]; vA[4 * c + 3] = tp[T_DM];
-        vB[4 * c + 0] = tp[T_MD]; vB[4 * c + 1] = tp[T_DD]; vB[4 * c + 2] = tk[T_MI]; vB[4 * c + 3] = tk[T_II];
-        for (int x = 0; x < Kp; x++) vem[(size_t)x * W + c] = hp.rwv[(size_t)x * (M + 1) + k];
-      }
-    }
-    for (int lane = 0; lane < 32; lane++) {  // in-lane prefix sums of DD(k-1)
-      int s = 0;
-      for (int j = 0; j < B; j++) {
-        const int c = j * 32 + lane;
-        s += vB[4 * c + 1];
-        vps[c] = s;
-      }
-    }
     while (fwd.size() % 4) fwd.push_back(0.f);
     d.fwd_off = fwd.size();
     fwd.resize(fwd.size() + (size_t)W * (16 + Kp), 0.0f);
@@ -316,6 +331,19 @@ extern "C" int pa_commit_hmms(pa_ctx *ctx) {
       }
     }
   }
+  {  // profile rank in (Bv, index) order: the sorted survivor list is then contiguous per Viterbi class
+    std::vector<int> ord(nh);
+    for (int h = 0; h < nh; h++) ord[h] = h;
+    std::stable_sort(ord.begin(), ord.end(), [&](int x, int y) { return ctx->h_dev[x].Bv < ctx->h_dev[y].Bv; });
+    ctx->vit_classes.clear();
+    for (int r = 0; r < nh; r++) {
+      ctx->h_dev[ord[r]].rank = r;
+      const int bv = ctx->h_dev[ord[r]].Bv;
+      if (ctx->vit_classes.empty() || ctx->vit_classes.back().first != bv) ctx->vit_classes.push_back({bv, {r, r + 1}});
+      else ctx->vit_classes.back().second.second = r + 1;
+    }
+  }
+  CK(ctx->d_sort.ensure(3 * ((size_t)nh + 1)));
   CK(ctx->d_hmms.ensure(nh));
   CK(cudaMemcpy(ctx->d_hmms.p, ctx->h_dev.data(), sizeof(DevHmm) * nh, cudaMemcpyHostToDevice));
   CK(ctx->d_msv.ensure(msv.size()));
@@ -585,6 +613,39 @@ static cudaError_t dispatch_msv(pa_ctx *ctx, int Q, MsvArgs &a, int nrows) {
 #undef C_
   }
   return cudaErrorInvalidValue;
+}
+
+template <int BT>
+static cudaError_t launch_vit(pa_ctx *ctx, VitArgs &v) {
+  const unsigned long long n = v.end - v.begin;
+  if (n == 0) return cudaSuccess;
+  const int grid = (int)std::min<unsigned long long>((n + 3) / 4, (unsigned long long)ctx->num_sms * 16);
+  vit_kernel<BT><<<grid, 128, 0, ctx->stream>>>(v);
+  ctx->stats.kernel_launches++;
+  return cudaGetLastError();
+}
+static cudaError_t dispatch_vit(pa_ctx *ctx, int Bv, VitArgs &v) {
+  switch (Bv) {
+#define C_(b) case b: return launch_vit<b>(ctx, v);
+    C_(1) C_(2) C_(3) C_(4) C_(6) C_(8) C_(10) C_(12) C_(14) C_(16) C_(20) C_(24) C_(28) C_(32) C_(40) C_(48) C_(56) C_(64)
+#undef C_
+  }
+  return cudaErrorInvalidValue;
+}
+
+// counting sort of n Pass2 records by profile rank: in -> out; start[] (host copy) gets nh + 1 offsets
+static int sort_by_profile(pa_ctx *ctx, const Pass2 *in, Pass2 *out, unsigned long long n, std::vector<unsigned int> &start) {
+  const int nh = (int)ctx->hmms.size();
+  unsigned int *cnt = ctx->d_sort.p, *st = cnt + (nh + 1), *cur = st + (nh + 1);
+  CK(cudaMemsetAsync(cnt, 0, sizeof(unsigned int) * (nh + 1), ctx->stream));
+  hist_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(in, n, ctx->d_hmms.p, cnt);
+  scan_kernel<<<1, 1024, 0, ctx->stream>>>(cnt, nh, st, cur);
+  scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(in, n, ctx->d_hmms.p, cur, out);
+  ctx->stats.kernel_launches += 3;
+  start.resize((size_t)nh + 1);
+  CK(cudaMemcpyAsync(start.data(), st, sizeof(unsigned int) * (nh + 1), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
 }
 
 static int launch_thresholds(pa_ctx *ctx, int all_pass) {

@@ -30,6 +30,7 @@ namespace pa {
 
 struct DevHmm {
   int M, Q, B, abc;             // Q: MSV words per lane; B = ceil(M/32)
+  int Bv, rank;                 // Viterbi lane-block size (class-rounded); position in (Bv, index) order
   int nrows;                    // Kp
   unsigned long long msv_off;   // uint32 words into msv pool
   unsigned long long vit_off;   // ints into vit pool: trA(int4) | trB(int4) | ps | em[Kp]
@@ -451,95 +452,9 @@ __global__ void bias_kernel(BiasArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Viterbi filter: one warp per pair, lane-blocked, state in shared memory
+// Viterbi filter
 // ---------------------------------------------------------------------------------------------
-struct VitArgs {
-  const DevHmm *hmms;
-  const int *tab;          // vit pool
-  Targets tg;
-  LenTabs lt;
-  const Pass2 *in;
-  unsigned long long n_in;
-  Pass2 *out;
-  unsigned long long *out_count;
-  unsigned long long out_cap;
-  int maxB;                // shared-memory sizing
-  int all_pairs;           // score_all: run Viterbi on every input, write raw xC
-  int *raw_out;
-};
-
 __device__ __forceinline__ int warp_max_s32(int v) { return __reduce_max_sync(PA_FULL, v); }
-
-// returns raw xC (32767 on overflow)
-__device__ int vit_pair(const DevHmm &hm, const int *tab, const uint8_t *p, int L, int xw_move, int *sm, int lane) {
-  const int B = hm.B, W = B * 32;
-  const int4 *trA = reinterpret_cast<const int4 *>(tab + hm.vit_off);
-  const int4 *trB = trA + W;
-  const int *ps = reinterpret_cast<const int *>(trB + W);
-  const int *em = ps + W;
-  int *Mx = sm, *Ix = sm + W, *Dx = sm + 2 * W;  // single buffer, updated in place (descending j)
-  for (int j = 0; j < B; j++) { Mx[j * 32 + lane] = PA_NEG16; Ix[j * 32 + lane] = PA_NEG16; Dx[j * 32 + lane] = PA_NEG16; }
-  __syncwarp();
-  const int xN = hm.base_w, xw_E = hm.xw_E;
-  int xB = max(xN + xw_move, PA_NEG16), xJ = PA_NEG16, xC = PA_NEG16;
-  const int ilast = (B - 1) * 32 + lane;
-  for (int i = 0; i < L; i++) {
-    const int *emx = em + (size_t)p[i] * W;
-    // previous-row values of the left neighbour's last cell
-    int mL = __shfl_up_sync(PA_FULL, Mx[ilast], 1), iL = __shfl_up_sync(PA_FULL, Ix[ilast], 1),
-        dL = __shfl_up_sync(PA_FULL, Dx[ilast], 1);
-    if (lane == 0) mL = iL = dL = PA_NEG16;
-    int rowmax = PA_NEG16;
-    for (int j = B - 1; j >= 0; j--) {
-      const int c = j * 32 + lane;
-      const int4 A = trA[c], Bq = trB[c];
-      const int pm = j ? Mx[c - 32] : mL, pi = j ? Ix[c - 32] : iL, pd = j ? Dx[c - 32] : dL;
-      int sv = __viaddmax_s32(xB, A.x, PA_NEG16);
-      sv = __viaddmax_s32(pm, A.y, sv);
-      sv = __viaddmax_s32(pi, A.z, sv);
-      sv = __viaddmax_s32(pd, A.w, sv);
-      sv = __viaddmax_s32(sv, emx[c], PA_NEG16);
-      int iv = __viaddmax_s32(Mx[c], Bq.z, PA_NEG16);
-      iv = __viaddmax_s32(Ix[c], Bq.w, iv);
-      Mx[c] = sv;
-      Ix[c] = iv;
-      rowmax = max(rowmax, sv);
-    }
-    const int xE = warp_max_s32(rowmax);
-    if (xE >= 32767) return 32767;
-    // D row: local chains, then max-plus scan across lanes
-    int mcL = __shfl_up_sync(PA_FULL, Mx[ilast], 1);
-    if (lane == 0) mcL = PA_NEGBIG;
-    int aloc = PA_NEGBIG;
-    for (int j = 0; j < B; j++) {
-      const int c = j * 32 + lane;
-      const int4 Bq = trB[c];
-      const int mleft = j ? Mx[c - 32] : mcL;
-      aloc = max(mleft + Bq.x, aloc + Bq.y);   // M(k-1)+MD(k-1), D(k-1)+DD(k-1); no clamp inside (addends <= 0)
-      aloc = max(aloc, PA_NEGBIG);
-      Dx[c] = aloc;
-    }
-    int LA = aloc, LS = ps[ilast];
-    for (int o = 1; o < 32; o <<= 1) {
-      int a2 = __shfl_up_sync(PA_FULL, LA, o), s2 = __shfl_up_sync(PA_FULL, LS, o);
-      if (lane >= o) {
-        LA = max(LA, max(a2 + LS, PA_NEGBIG));
-        LS = max(LS + s2, PA_NEGBIG);
-      }
-    }
-    int din = __shfl_up_sync(PA_FULL, LA, 1);
-    if (lane == 0) din = PA_NEGBIG;
-    for (int j = 0; j < B; j++) {
-      const int c = j * 32 + lane;
-      Dx[c] = max(max(Dx[c], din + ps[c]), PA_NEG16);
-    }
-    xC = max(xC, max(xE + xw_E, PA_NEG16));
-    xJ = max(xJ, max(xE + xw_E, PA_NEG16));
-    xB = max(max(xJ + xw_move, xN + xw_move), PA_NEG16);
-    __syncwarp();
-  }
-  return xC;
-}
 
 __device__ __forceinline__ float vit_score_from_xC(const DevHmm &hm, int xC, int xw_move) {
   if (xC >= 32767) return __int_as_float(0x7f800000);
@@ -550,12 +465,102 @@ __device__ __forceinline__ float vit_score_from_xC(const DevHmm &hm, int xC, int
   return sc;
 }
 
-__global__ void __launch_bounds__(256) vit_kernel(VitArgs a) {
-  extern __shared__ __align__(16) int s_vit[];
+// One (profile, target) pair per warp; DP state in registers. Lane l owns cells k = l*BT+1..(l+1)*BT
+// (BT = the profile's class-rounded block size; padded cells carry -32768 scores). Tables [j][lane]:
+// trA int4 {BM,MM,IM,DM}(k-1) | trI int2 {MI,II}(k) | trD int2 {MD,DD}(k-1) | ps int | em[x] int.
+// Saturating signed-16 semantics are evaluated exactly in s32: VIADDMNMX fuses add + max with the
+// -32768 floor; the upper saturation can only be reached in the row maximum, which ends the pass.
+template <int BT>
+__device__ __forceinline__ int vit_pair_reg(const DevHmm &hm, const int *tab, const uint8_t *p, int L, int xw_move, int lane) {
+  constexpr int W = BT * 32;
+  const int4 *trA = reinterpret_cast<const int4 *>(tab + hm.vit_off);
+  const int2 *trI = reinterpret_cast<const int2 *>(trA + W);
+  const int2 *trD = trI + W;
+  const int *ps = reinterpret_cast<const int *>(trD + W);
+  const int *em = ps + W;
+  int Mx[BT], Ix[BT], Dx[BT];
+#pragma unroll
+  for (int j = 0; j < BT; j++) { Mx[j] = PA_NEG16; Ix[j] = PA_NEG16; Dx[j] = PA_NEG16; }
+  const int xN = hm.base_w, xw_E = hm.xw_E;
+  int xB = max(xN + xw_move, PA_NEG16), xJ = PA_NEG16, xC = PA_NEG16;
+  const int pslast = ps[(BT - 1) * 32 + lane];
+  for (int i = 0; i < L; i++) {
+    const int *emx = em + (size_t)p[i] * W;
+    int mL = __shfl_up_sync(PA_FULL, Mx[BT - 1], 1), iL = __shfl_up_sync(PA_FULL, Ix[BT - 1], 1),
+        dL = __shfl_up_sync(PA_FULL, Dx[BT - 1], 1);
+    if (lane == 0) mL = iL = dL = PA_NEG16;
+    int rowmax = PA_NEG16;
+#pragma unroll
+    for (int j = BT - 1; j >= 0; j--) {
+      const int c = j * 32 + lane;
+      const int4 A = __ldg(trA + c);
+      const int2 Iq = __ldg(trI + c);
+      const int e = __ldg(emx + c);
+      const int pm = j ? Mx[j > 0 ? j - 1 : 0] : mL, pi = j ? Ix[j > 0 ? j - 1 : 0] : iL, pd = j ? Dx[j > 0 ? j - 1 : 0] : dL;
+      int sv = __viaddmax_s32(xB, A.x, PA_NEG16);
+      sv = __viaddmax_s32(pm, A.y, sv);
+      sv = __viaddmax_s32(pi, A.z, sv);
+      sv = __viaddmax_s32(pd, A.w, sv);
+      sv = __viaddmax_s32(sv, e, PA_NEG16);
+      int iv = __viaddmax_s32(Mx[j], Iq.x, PA_NEG16);
+      iv = __viaddmax_s32(Ix[j], Iq.y, iv);
+      Mx[j] = sv;
+      Ix[j] = iv;
+      rowmax = max(rowmax, sv);
+      if ((j & 3) == 0) asm volatile("" ::: "memory");  // bound load hoisting (register pressure)
+    }
+    const int xE = __reduce_max_sync(PA_FULL, rowmax);
+    if (xE >= 32767) return 32767;
+    int mcL = __shfl_up_sync(PA_FULL, Mx[BT - 1], 1);
+    if (lane == 0) mcL = PA_NEGBIG;
+    int aloc = PA_NEGBIG;
+#pragma unroll
+    for (int j = 0; j < BT; j++) {
+      const int2 Dq = __ldg(trD + j * 32 + lane);
+      const int mleft = j ? Mx[j > 0 ? j - 1 : 0] : mcL;
+      aloc = max(max(mleft + Dq.x, aloc + Dq.y), PA_NEGBIG);
+      Dx[j] = aloc;
+    }
+    int LA = aloc, LS = pslast;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int a2 = __shfl_up_sync(PA_FULL, LA, o), s2 = __shfl_up_sync(PA_FULL, LS, o);
+      if (lane >= o) {
+        LA = max(LA, max(a2 + LS, PA_NEGBIG));
+        LS = max(LS + s2, PA_NEGBIG);
+      }
+    }
+    int din = __shfl_up_sync(PA_FULL, LA, 1);
+    if (lane == 0) din = PA_NEGBIG;
+#pragma unroll
+    for (int j = 0; j < BT; j++) Dx[j] = __vimax3_s32(Dx[j], din + __ldg(ps + j * 32 + lane), PA_NEG16);
+    xC = max(xC, max(xE + xw_E, PA_NEG16));
+    xJ = max(xJ, max(xE + xw_E, PA_NEG16));
+    xB = max(max(xJ + xw_move, xN + xw_move), PA_NEG16);
+  }
+  return xC;
+}
+
+struct VitArgs {
+  const DevHmm *hmms;
+  const int *tab;          // vit pool
+  Targets tg;
+  LenTabs lt;
+  const Pass2 *in;         // sorted by profile rank; this launch handles [begin, end)
+  unsigned long long begin, end;
+  Pass2 *out;
+  unsigned long long *out_count;
+  unsigned long long out_cap;
+  int all_pairs;           // score_all: run Viterbi on every input, write raw xC at the input index
+  int *raw_out;
+};
+
+// register budget per class: keep several warps per scheduler for the common (M <= 512) profiles
+template <int BT>
+__global__ void __launch_bounds__(128, (BT <= 8 ? 5 : BT <= 16 ? 4 : BT <= 24 ? 3 : BT <= 32 ? 2 : 1)) vit_kernel(VitArgs a) {
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-  int *sm = s_vit + (size_t)wib * a.maxB * 32 * 3;
-  for (unsigned long long i = (unsigned long long)blockIdx.x * wpb + wib; i < a.n_in; i += (unsigned long long)gridDim.x * wpb) {
-    Pass2 r = a.in[i];
+  for (unsigned long long i = a.begin + (unsigned long long)blockIdx.x * wpb + wib; i < a.end; i += (unsigned long long)gridDim.x * wpb) {
+    const Pass2 r = a.in[i];
     const DevHmm &hm = a.hmms[r.h];
     if (!(r.flags & 1) && !a.all_pairs) {  // P <= F2 already: Viterbi not needed
       if (lane == 0) {
@@ -565,9 +570,8 @@ __global__ void __launch_bounds__(256) vit_kernel(VitArgs a) {
       continue;
     }
     const int L = (int)a.tg.len[r.t];
-    const int li = a.tg.lidx[r.t];
-    const int xw_move = a.lt.xw_move[li];
-    const int xC = vit_pair(hm, a.tab, a.tg.dsq + a.tg.off[r.t], L, xw_move, sm, lane);
+    const int xw_move = a.lt.xw_move[a.tg.lidx[r.t]];
+    const int xC = vit_pair_reg<BT>(hm, a.tab, a.tg.dsq + a.tg.off[r.t], L, xw_move, lane);
     if (a.raw_out && lane == 0) a.raw_out[i] = xC;
     if (a.all_pairs) continue;
     const float vfsc = vit_score_from_xC(hm, xC, xw_move);
@@ -576,6 +580,43 @@ __global__ void __launch_bounds__(256) vit_kernel(VitArgs a) {
       unsigned long long idx = atomicAdd(a.out_count, 1ull);
       if (idx < a.out_cap) a.out[idx] = r;
     }
+  }
+}
+
+// ---- counting sort of a Pass2 list by profile rank (groups pairs of one profile together) ----
+__global__ void hist_kernel(const Pass2 *in, unsigned long long n, const DevHmm *hmms, unsigned int *cnt) {
+  unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+  if (i < n) atomicAdd(&cnt[hmms[in[i].h].rank], 1u);
+}
+// single block: exclusive scan of cnt[0..nh) into start[] (also copied to cursor[]); start[nh] = total
+__global__ void scan_kernel(const unsigned int *cnt, int nh, unsigned int *start, unsigned int *cursor) {
+  __shared__ unsigned int carry;
+  __shared__ unsigned int buf[1024];
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < nh; base += 1024) {
+    const int i = base + threadIdx.x;
+    unsigned int v = i < nh ? cnt[i] : 0;
+    buf[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+      unsigned int t = threadIdx.x >= o ? buf[threadIdx.x - o] : 0;
+      __syncthreads();
+      buf[threadIdx.x] += t;
+      __syncthreads();
+    }
+    if (i < nh) { start[i] = carry + buf[threadIdx.x] - v; cursor[i] = start[i]; }
+    __syncthreads();
+    if (threadIdx.x == 1023) carry += buf[1023];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) start[nh] = carry;
+}
+__global__ void scatter_kernel(const Pass2 *in, unsigned long long n, const DevHmm *hmms, unsigned int *cursor, Pass2 *out) {
+  unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+  if (i < n) {
+    const Pass2 r = in[i];
+    out[atomicAdd(&cursor[hmms[r.h].rank], 1u)] = r;
   }
 }
 
