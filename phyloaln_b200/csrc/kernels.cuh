@@ -248,7 +248,6 @@ struct MsvArgs {
   unsigned long long *n_ssv_cand;
   int all_pairs;           // 1: emit every pair with its exact MSV result (score_all)
   uint32_t zero;           // always 0; a run-time value so ptxas cannot re-materialise {0,0} per use
-  int abc;                 // target alphabet (selects the register-resident table rows)
 };
 
 template <int Q>
@@ -264,11 +263,6 @@ __global__ void __launch_bounds__(256, 2) msv_kernel(MsvArgs a) {
   // stays 0: the row carry can wrap around from lane 31 to lane 0 without a select.
   const int lanem1 = (lane + 31) & 31;
   const uint32_t zero = a.zero;
-  // hot residues: amino L S R A (22 of 64 codons); nucleotide A C G T (everything)
-  const uint32_t hot_off0 = (a.abc == 0 ? 9u : 0u) * ROWW, hot_off1 = (a.abc == 0 ? 15u : 1u) * ROWW,
-                 hot_off2 = (a.abc == 0 ? 14u : 2u) * ROWW, hot_off3 = (a.abc == 0 ? 0u : 3u) * ROWW;
-  constexpr int NH = Q <= 8 ? 4 : (Q <= 12 ? 2 : 0);   // register budget: 4Q / 2Q / 0 words of hot rows
-  uint32_t hot0[Q], hot1[Q], hot2[Q], hot3[Q];
   for (unsigned long long item = blockIdx.x; item < nitems; item += gridDim.x) {
     const int h = a.hmm_list[item / ntiles];
     const uint32_t tile = (uint32_t)(item % ntiles);
@@ -281,10 +275,6 @@ __global__ void __launch_bounds__(256, 2) msv_kernel(MsvArgs a) {
       for (int i = threadIdx.x; i < n4; i += blockDim.x) dst[i] = src[i];
       __syncthreads();
       cur_h = h;
-      if (NH > 0) msv_load_row<Q>(s_tab + hot_off0, lane, hot0);
-      if (NH > 1) msv_load_row<Q>(s_tab + hot_off1, lane, hot1);
-      if (NH > 2) msv_load_row<Q>(s_tab + hot_off2, lane, hot2);
-      if (NH > 3) msv_load_row<Q>(s_tab + hot_off3, lane, hot3);
     }
     const int bias = hm.bias, base = hm.base, tec = hm.tec, tbm = hm.tbm;
     const uint32_t t1 = min(a.tg.n, (tile + 1) * a.tile);
@@ -306,35 +296,23 @@ __global__ void __launch_bounds__(256, 2) msv_kernel(MsvArgs a) {
       uint32_t m = 0;
       if (Cp > 0) {
         // each lane fetches one residue of a 32-row block and turns it into a table-row offset;
-        // rows then get their offset by shuffle: no ALU work for addressing in the row body.
-        // The table rows of the four most frequent residues live in registers (hot[]): their rows
-        // cost no shared-memory bandwidth, which is what bounds this kernel.
+        // rows then get their offset by shuffle: no ALU work for addressing in the row body
         uint32_t myoff = (lane < L) ? (uint32_t)p[lane] * ROWW : 0u;
         for (int i0 = 0; i0 < L; i0 += 32) {
           const uint32_t curoff = myoff;
           if (i0 + 32 < L) myoff = (i0 + 32 + lane < L) ? (uint32_t)p[i0 + 32 + lane] * ROWW : 0u;
           const int nr = min(32, L - i0);
-#define PA_SSV_BODY(D)                                                                     \
-  {                                                                                        \
-    const uint32_t tt = __shfl_sync(PA_FULL, w[Q - 1], lanem1);                            \
-    const uint32_t carry = __byte_perm(tt, w[Q - 1], 0x5432);                              \
-    _Pragma("unroll") for (int q = Q - 1; q >= 1; q--) w[q] = __viaddmax_s16x2(w[q - 1], D[q], zero); \
-    w[0] = __viaddmax_s16x2(carry, D[0], zero);                                            \
-    _Pragma("unroll") for (int q = 0; q + 1 < Q; q += 2) m = __vimax3_s16x2(m, w[q], w[q + 1]); \
-    if (Q & 1) m = __vmaxs2(m, w[Q - 1]);                                                  \
-  }
 #define PA_SSV_ROW(rr)                                                                     \
   {                                                                                        \
     const uint32_t ro = __shfl_sync(PA_FULL, curoff, (rr));                                \
-    if (NH > 0 && ro == hot_off0) PA_SSV_BODY(hot0)                                        \
-    else if (NH > 1 && ro == hot_off1) PA_SSV_BODY(hot1)                                   \
-    else if (NH > 2 && ro == hot_off2) PA_SSV_BODY(hot2)                                   \
-    else if (NH > 3 && ro == hot_off3) PA_SSV_BODY(hot3)                                   \
-    else {                                                                                 \
-      uint32_t d[Q];                                                                       \
-      msv_load_row<Q>(s_tab + ro, lane, d);                                                \
-      PA_SSV_BODY(d)                                                                       \
-    }                                                                                      \
+    uint32_t d[Q];                                                                         \
+    msv_load_row<Q>(s_tab + ro, lane, d);                                                  \
+    const uint32_t tt = __shfl_sync(PA_FULL, w[Q - 1], lanem1);                            \
+    const uint32_t carry = __byte_perm(tt, w[Q - 1], 0x5432);                              \
+    _Pragma("unroll") for (int q = Q - 1; q >= 1; q--) w[q] = __viaddmax_s16x2(w[q - 1], d[q], zero); \
+    w[0] = __viaddmax_s16x2(carry, d[0], zero);                                            \
+    _Pragma("unroll") for (int q = 0; q + 1 < Q; q += 2) m = __vimax3_s16x2(m, w[q], w[q + 1]); \
+    if (Q & 1) m = __vmaxs2(m, w[Q - 1]);                                                  \
   }
           int r = 0;
           for (; r + 4 <= nr; r += 4) {
@@ -342,7 +320,6 @@ __global__ void __launch_bounds__(256, 2) msv_kernel(MsvArgs a) {
           }
           for (; r < nr; r++) PA_SSV_ROW(r)
 #undef PA_SSV_ROW
-#undef PA_SSV_BODY
         }
       }
       const int U = (Cp > 0) ? warp_max16x2(m) : 0;
