@@ -208,7 +208,7 @@ def main():
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ctx = capi.Context(local_rank)
     for h in hmms:
         ctx.add_hmm(h, require_stats=False)
@@ -258,6 +258,28 @@ def main():
             e2e_times.append(dt)
             d2h = int(hits.nbytes + sum(map(len, model)) + sum(map(len, aligned)))
     clocks = sampler.stop()
+    # ---------------- HBM-bound kernel: translation of a large resident chunk ----------------
+    tr_roof = None
+    if rank == 0:
+        nbig = 1 << 20
+        big = np.ascontiguousarray(np.tile(chunks[0], (nbig // args.reads_per_step + 1, 1))[:nbig])
+        boffs = np.arange(nbig + 1, dtype=np.uint64) * 150
+        best = 1e9
+        for _ in range(3):
+            ctx.load_reads(big.reshape(-1), boffs)
+            best = min(best, ctx.stats()["ms_translate"])
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        ach = 446.0 * nbig / (best * 1e-3) / 1e9
+        tr_roof = {"bound": "hbm", "kernel": "translate_kernel", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                   "frac": ach / hbm_peak, "traffic": None, "reads": nbig, "ms": best,
+                   "algorithmic_bytes_per_read": 446,
+                   "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s"}
+        del big
     launches_total = launches_timed
 
     tot = float(np.sum(times))
@@ -274,6 +296,7 @@ def main():
     ms_stage = {k: float(np.mean([s[k] for s in stats_acc])) for k in
                 ("ms_translate", "ms_msv", "ms_bias", "ms_vit", "ms_fwd", "ms_domain", "ms_total")}
     cells_per_step = 296.0 * args.reads_per_step * sumM        # residues/read (50+49+49)*2 x sum of M
+    padded_cells_per_step = 296.0 * args.reads_per_step * sum(64 * (h.M // 64 + 1) for h in hmms)
     achieved_laneops = 4.0 * cells_per_step / (ms_msv * 1e-3)
     gcups = cells_per_step * world / (tot / args.steps) / 1e9
     last = stats_acc[-1]
@@ -289,8 +312,14 @@ def main():
                          "peak": peak_laneops / 1e12, "unit": "T 16-bit lane-op/s (algorithmic 4/cell)",
                          "frac": achieved_laneops / peak_laneops, "traffic": None,
                          "msv_gcups": cells_per_step / (ms_msv * 1e-3) / 1e9,
+                         "binding_resource": "shared-memory bandwidth: 2 B of emission deltas per (padded) cell must reach the "
+                                             "register file; ncu (profiles/r1_ncu_full_kernels.md): smem wavefronts 82-86 % of peak, "
+                                             "ALU pipe 66 %",
+                         "smem_tb_s": {"achieved": 2.0 * padded_cells_per_step / (ms_msv * 1e-3) / 1e12,
+                                       "peak": 128.0 * 148 * (clocks["sm_mhz"] or 1965.0) * 1e6 / 1e12},
                          "peak_source": "measured in this run: VIADDMNMX.S16x2.RELU issue rate x 2 lanes (pa_microbench_dpx)",
                          "dpx_ginstr_per_s": dpx},
+            "roofline_translate": tr_roof,
             "stage_ms": ms_stage,
             "funnel": {k: int(last[k]) for k in ("n_pairs", "n_past_ssv", "n_past_msv", "n_past_bias", "n_past_vit", "n_past_fwd", "n_domains")}}
     if rank == 0:

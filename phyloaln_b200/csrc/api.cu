@@ -487,7 +487,7 @@ extern "C" int64_t pa_load_reads(pa_ctx *ctx, const char *nt, const uint64_t *of
   CK(ctx->d_toff.ensure(ntargets64 + 1));
   CK(ctx->d_tlen.ensure(ntargets64 + 1));
   cudaEventRecord(e1, ctx->stream);
-  const int grid = std::min<uint64_t>((nreads + 7) / 8, (uint64_t)ctx->num_sms * 8);
+  const int grid = std::min<uint64_t>((nreads + 7) / 8, (uint64_t)ctx->num_sms * 16);
   if (nreads)
     translate_kernel<<<std::max(grid, 1), 256, 0, ctx->stream>>>(ctx->d_nt.p, ctx->d_ntoff.p, nreads, moltype == PA_TRANSLATE ? 0 : 1,
                                                                nfwd, nrev, ctx->d_codon.p, ctx->d_dsq.p, ctx->d_toff.p,

@@ -127,53 +127,75 @@ __device__ __forceinline__ uint32_t target_base(unsigned long long ntoff, uint32
   return (uint32_t)(((2ull * ntoff + 3ull) & ~3ull) + 32ull * r);
 }
 
-// one warp per read
+// One warp per read. The read's nucleotides are staged once in shared memory as 4-bit IUPAC masks
+// (coalesced byte loads, one nt_mask() per base instead of one per codon use); each lane then emits
+// 4 consecutive residues of one frame as a single 32-bit store. HBM traffic = L bytes in,
+// ~2L bytes out per read (446 B for 150 bp).
+#define PA_TR_MAXL 1024
 __global__ void __launch_bounds__(256) translate_kernel(const char *__restrict__ nt, const unsigned long long *__restrict__ off,
                                                         uint32_t nreads, int moltype, int nfwd, int nrev,
                                                         const uint8_t *__restrict__ tab64, uint8_t *__restrict__ out,
                                                         uint32_t *__restrict__ tgt_off, uint32_t *__restrict__ tgt_len,
                                                         int *__restrict__ err) {
   __shared__ uint8_t s_tab[64];
+  __shared__ uint8_t s_mask[8][PA_TR_MAXL];
   if (threadIdx.x < 64) s_tab[threadIdx.x] = tab64[threadIdx.x];
   __syncthreads();
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   const int nframes = nfwd + nrev;
+  uint8_t *mk = s_mask[wib];
   for (uint32_t r = blockIdx.x * wpb + wib; r < nreads; r += gridDim.x * wpb) {
     const unsigned long long o = off[r];
     const int L = (int)(off[r + 1] - o);
-    uint32_t base = target_base(o, r);
-    uint32_t pos = base;
-    if (moltype == 1) {  // nucleotide targets: read, then reverse complement
-      for (int f = 0; f < nframes; f++) {
-        for (int i = lane; i < L; i += 32) {
-          int m = nt_mask((uint8_t)nt[o + (f == 0 ? i : L - 1 - i)]);
-          if (m == 0) { atomicExch(err, 1); m = 15; }
-          if (f == 1) m = comp_mask(m);
-          out[pos + i] = (uint8_t)dna_code(m);
-        }
-        if (lane == 0) { tgt_off[(size_t)r * nframes + f] = pos; tgt_len[(size_t)r * nframes + f] = L; }
-        pos += (L + 3) & ~3;
+    const bool staged = L <= PA_TR_MAXL;
+    __syncwarp();
+    if (staged) {
+      bool bad = false;
+      for (int i = lane; i < L; i += 32) {
+        int m = nt_mask((uint8_t)nt[o + i]);
+        if (m == 0) { bad = true; m = 15; }
+        mk[i] = (uint8_t)m;
       }
-      continue;
+      if (bad) atomicExch(err, 1);
+      __syncwarp();
     }
+    auto mask_at = [&](int i) -> int {
+      if (staged) return mk[i];
+      int m = nt_mask((uint8_t)nt[o + i]);
+      if (m == 0) { atomicExch(err, 1); m = 15; }
+      return m;
+    };
+    uint32_t pos = target_base(o, r);
     for (int f = 0; f < nframes; f++) {
-      const bool rev = f >= nfwd;
-      const int j = rev ? f - nfwd : f;  // frame offset 0..2
-      const int naa = (L - j) >= 3 ? (L - j) / 3 : 0;
-      for (int c = lane; c < naa; c += 32) {
-        int p = j + 3 * c;
-        int m0, m1, m2;
-        if (!rev) {
-          m0 = nt_mask((uint8_t)nt[o + p]); m1 = nt_mask((uint8_t)nt[o + p + 1]); m2 = nt_mask((uint8_t)nt[o + p + 2]);
-        } else {
-          m0 = nt_mask((uint8_t)nt[o + L - 1 - p]); m1 = nt_mask((uint8_t)nt[o + L - 2 - p]); m2 = nt_mask((uint8_t)nt[o + L - 3 - p]);
+      const bool rev = (moltype == 1) ? (f == 1) : (f >= nfwd);
+      const int j = (moltype == 1) ? 0 : (rev ? f - nfwd : f);  // frame offset 0..2
+      const int step = moltype == 1 ? 1 : 3;
+      const int nres = moltype == 1 ? L : ((L - j) >= 3 ? (L - j) / 3 : 0);
+      const int nwords = (nres + 3) >> 2;
+      for (int w = lane; w < nwords; w += 32) {
+        uint32_t word = 0;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const int c = 4 * w + q;
+          int code = 0;
+          if (c < nres) {
+            const int p0 = j + step * c;
+            if (moltype == 1) {
+              int m = rev ? comp_mask(mask_at(L - 1 - p0)) : mask_at(p0);
+              code = dna_code(m);
+            } else {
+              int m0, m1, m2;
+              if (!rev) { m0 = mask_at(p0); m1 = mask_at(p0 + 1); m2 = mask_at(p0 + 2); }
+              else { m0 = comp_mask(mask_at(L - 1 - p0)); m1 = comp_mask(mask_at(L - 2 - p0)); m2 = comp_mask(mask_at(L - 3 - p0)); }
+              code = codon_code(m0, m1, m2, s_tab);
+            }
+          }
+          word |= (uint32_t)code << (8 * q);
         }
-        if (m0 == 0 || m1 == 0 || m2 == 0) { atomicExch(err, 1); m0 = m1 = m2 = 15; }
-        if (rev) { m0 = comp_mask(m0); m1 = comp_mask(m1); m2 = comp_mask(m2); }
-        out[pos + c] = (uint8_t)codon_code(m0, m1, m2, s_tab);
+        *reinterpret_cast<uint32_t *>(out + pos + 4 * w) = word;
       }
-      if (lane == 0) { tgt_off[(size_t)r * nframes + f] = pos; tgt_len[(size_t)r * nframes + f] = naa; }
-      pos += (naa + 3) & ~3;
+      if (lane == 0) { tgt_off[(size_t)r * nframes + f] = pos; tgt_len[(size_t)r * nframes + f] = nres; }
+      pos += (nres + 3) & ~3;
     }
   }
 }

@@ -264,22 +264,36 @@ class B200Searcher:
         nframes_box = [1]
         errors = []
 
+        def search_range(ctx, a, b, out):
+            """Search reads [a, b); on a capacity error (-3) split the range (the library has no fallback)."""
+            sub_off = (off[a:b + 1] - off[a]).astype(np.uint64)
+            sub_nt = nt[int(off[a]):int(off[b])]
+            if len(sub_nt) == 0:
+                sub_nt = np.zeros(1, dtype=np.uint8)
+            ctx.load_reads(sub_nt, sub_off, moltype=0 if translated else 1, gencode=gencode, no_reverse=no_reverse,
+                           codon_only=codon)
+            nf = ctx.num_frames()
+            nframes_box[0] = nf
+            try:
+                hits, model, aligned = ctx.search()
+            except capi.PaError as e:
+                if "(-3)" in str(e) and b - a > 1:
+                    mid = (a + b) // 2
+                    search_range(ctx, a, mid, out)
+                    search_range(ctx, mid, b, out)
+                    return
+                raise
+            hits = hits.copy()
+            hits["target"] += a * nf
+            out.append((hits, model, aligned))
+
         def work(ci, ctx):
             try:
                 for c in range(ci, len(bounds) - 1, len(self.ctxs)):
-                    a, b = bounds[c], bounds[c + 1]
-                    sub_off = (off[a:b + 1] - off[a]).astype(np.uint64)
-                    sub_nt = nt[int(off[a]):int(off[b])]
-                    if len(sub_nt) == 0:
-                        sub_nt = np.zeros(1, dtype=np.uint8)
-                    ctx.load_reads(sub_nt, sub_off, moltype=0 if translated else 1, gencode=gencode, no_reverse=no_reverse,
-                                   codon_only=codon)
-                    nf = ctx.num_frames()
-                    nframes_box[0] = nf
-                    hits, model, aligned = ctx.search()
-                    hits = hits.copy()
-                    hits["target"] += a * nf
-                    results[c] = (hits, model, aligned)
+                    parts = []
+                    search_range(ctx, bounds[c], bounds[c + 1], parts)
+                    results[c] = (np.concatenate([p[0] for p in parts]), [m for p in parts for m in p[1]],
+                                  [m for p in parts for m in p[2]])
             except Exception as e:  # surfaced after join
                 errors.append(e)
 
