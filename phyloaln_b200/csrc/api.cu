@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -19,6 +20,7 @@
 
 #include "../../include/phyloaln_b200.h"
 #include "kernels.cuh"
+#include "msv_tmem.cuh"
 #include "domain.cuh"
 #include "mapping.cuh"
 #include "profile.hpp"
@@ -69,7 +71,8 @@ struct pa_ctx {
   bool committed = false;
   std::vector<DevHmm> h_dev;
   DevBuf<DevHmm> d_hmms;
-  DevBuf<uint32_t> d_msv;
+  DevBuf<uint32_t> d_msv, d_msvh;
+  int msv_impl = 0;  // 0: TMEM kernel where the table fits (default), 1: shared-memory kernel everywhere (PA_MSV_IMPL=smem)
   DevBuf<int> d_vit;
   DevBuf<float> d_fwd;
   DevBuf<int> d_hmm_lists;
@@ -157,6 +160,7 @@ extern "C" pa_ctx *pa_create(int device, char *err, int errlen) {
   ctx->device = device;
   ctx->num_sms = prop.multiProcessorCount;
   ctx->smem_optin = prop.sharedMemPerBlockOptin;
+  if (const char *impl = getenv("PA_MSV_IMPL")) ctx->msv_impl = !strcmp(impl, "smem") ? 1 : 0;
   if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
     delete ctx;
     return fail("cudaStreamCreate", e);
@@ -167,7 +171,7 @@ extern "C" pa_ctx *pa_create(int device, char *err, int errlen) {
 extern "C" void pa_destroy(pa_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
-  ctx->d_hmms.release(); ctx->d_msv.release(); ctx->d_vit.release(); ctx->d_fwd.release(); ctx->d_hmm_lists.release(); ctx->d_sort.release();
+  ctx->d_hmms.release(); ctx->d_msv.release(); ctx->d_msvh.release(); ctx->d_vit.release(); ctx->d_fwd.release(); ctx->d_hmm_lists.release(); ctx->d_sort.release();
   ctx->d_nt.release(); ctx->d_ntoff.release(); ctx->d_dsq.release(); ctx->d_toff.release(); ctx->d_tlen.release();
   ctx->d_lidx.release(); ctx->d_codon.release(); ctx->d_flag.release();
   ctx->d_L.release(); ctx->d_nullsc.release(); ctx->d_biasA.release(); ctx->d_biasB.release(); ctx->d_tjb.release();
@@ -230,12 +234,26 @@ static inline int msv_word_pos(int Q, int q, int lane) {
   return N4 * 128 + R2 * 64 + lane;
 }
 
+// exact fp16 bit pattern of an integer that fp16 represents exactly (|v| <= 2048, or a multiple of 16 up to 32768)
+static inline uint16_t h16_exact(int v) {
+  if (v == 0) return 0;
+  const float f = (float)v;
+  uint32_t b;
+  memcpy(&b, &f, 4);
+  const uint32_t sign = b >> 31, e = ((b >> 23) & 0xff) - 127 + 15, mant = (b >> 13) & 0x3ff;
+  return (uint16_t)((sign << 15) | (e << 10) | mant);
+}
+
+static inline bool msv_use_tmem(const pa_ctx *ctx, int Q, int nrows) {
+  return ctx->msv_impl == 0 && Q <= PA_TMEM_MAXQ && msv_tmem_cols_needed(Q, nrows) <= 512;
+}
+
 extern "C" int pa_commit_hmms(pa_ctx *ctx) {
   if (!ctx) return -1;
   cudaSetDevice(ctx->device);
   const int nh = (int)ctx->hmms.size();
   if (nh == 0) { ctx->err = "no profiles"; return -2; }
-  std::vector<uint32_t> msv;
+  std::vector<uint32_t> msv, msvh;
   std::vector<int> vit;
   std::vector<float> fwd;
   ctx->h_dev.assign(nh, DevHmm{});
@@ -284,6 +302,22 @@ extern "C" int pa_commit_hmms(pa_ctx *ctx) {
           }
           msv[d.msv_off + (size_t)x * roww + msv_word_pos(Q, q, lane)] = (uint32_t)(uint16_t)half[0] | ((uint32_t)(uint16_t)half[1] << 16);
         }
+
+    // ---- the same deltas as fp16x2, [x][q][lane], for the tensor-memory kernel (msv_tmem.cuh)
+    d.msvh_off = msvh.size();
+    if (msv_use_tmem(ctx, Q, Kp)) {
+      msvh.resize(msvh.size() + (size_t)Kp * roww, 0);
+      for (int x = 0; x < Kp; x++)
+        for (int q = 0; q < Q; q++)
+          for (int lane = 0; lane < 32; lane++) {
+            uint16_t half[2];
+            for (int hf = 0; hf < 2; hf++) {
+              const int cell = (2 * lane + hf) * Q + q, k = cell + 1;
+              half[hf] = h16_exact(k <= M ? (int)hp.bias_b - (int)hp.rbv[(size_t)x * (M + 1) + k] : PA_MSV_DEAD);
+            }
+            msvh[d.msvh_off + ((size_t)x * Q + q) * 32 + lane] = (uint32_t)half[0] | ((uint32_t)half[1] << 16);
+          }
+    }
 
     // ---- Viterbi tables, lane-blocked [j][lane] with the class-rounded block size Bv: k = lane*Bv + j + 1
     d.Bv = vit_class(d.B);
@@ -348,6 +382,8 @@ extern "C" int pa_commit_hmms(pa_ctx *ctx) {
   CK(cudaMemcpy(ctx->d_hmms.p, ctx->h_dev.data(), sizeof(DevHmm) * nh, cudaMemcpyHostToDevice));
   CK(ctx->d_msv.ensure(msv.size()));
   CK(cudaMemcpy(ctx->d_msv.p, msv.data(), msv.size() * 4, cudaMemcpyHostToDevice));
+  CK(ctx->d_msvh.ensure(msvh.size() + 1));
+  if (!msvh.empty()) CK(cudaMemcpy(ctx->d_msvh.p, msvh.data(), msvh.size() * 4, cudaMemcpyHostToDevice));
   CK(ctx->d_vit.ensure(vit.size()));
   CK(cudaMemcpy(ctx->d_vit.p, vit.data(), vit.size() * 4, cudaMemcpyHostToDevice));
   CK(ctx->d_fwd.ensure(fwd.size()));
@@ -605,7 +641,32 @@ static cudaError_t launch_msv(pa_ctx *ctx, MsvArgs &a, int nrows_max) {
   return cudaGetLastError();
 }
 
+template <int Q>
+static cudaError_t launch_msv_tmem(pa_ctx *ctx, MsvArgs &a, int nrows) {
+  constexpr int G = 2;
+  const int need = msv_tmem_cols_needed(Q, nrows);
+  int ncols = 32;
+  while (ncols < need) ncols *= 2;
+  // resident CTAs per SM: fixed by the kernel's __launch_bounds__ (register cap) and by TMEM -- every
+  // resident CTA must own its columns, or it would spin in tcgen05.alloc until a neighbour exits
+  const int bps = std::max(1, std::min(Q <= 8 ? 2 : 1, 512 / ncols));
+  const uint32_t ntiles = (a.tg.n + a.tile - 1) / a.tile;
+  const unsigned long long nitems = (unsigned long long)a.nlist * ntiles;
+  const int grid = (int)std::min<unsigned long long>(nitems, (unsigned long long)ctx->num_sms * bps);
+  a.tab = ctx->d_msvh.p;
+  if (grid > 0) msv_tmem_kernel<Q, G><<<grid, msv_tmem_threads(Q), 0, ctx->stream>>>(a, ncols);
+  ctx->stats.kernel_launches++;
+  return cudaGetLastError();
+}
+
 static cudaError_t dispatch_msv(pa_ctx *ctx, int Q, MsvArgs &a, int nrows) {
+  if (msv_use_tmem(ctx, Q, nrows)) {
+    switch (Q) {
+#define C_(q) case q: return launch_msv_tmem<q>(ctx, a, nrows);
+      C_(1) C_(2) C_(3) C_(4) C_(5) C_(6) C_(7) C_(8) C_(9) C_(10) C_(11) C_(12) C_(13) C_(14) C_(15) C_(16)
+#undef C_
+    }
+  }
   switch (Q) {
 #define C_(q) case q: return launch_msv<q>(ctx, a, nrows);
     C_(1) C_(2) C_(3) C_(4) C_(5) C_(6) C_(7) C_(8) C_(9) C_(10) C_(11) C_(12) C_(13) C_(14) C_(15) C_(16)

@@ -33,6 +33,7 @@ struct DevHmm {
   int Bv, rank;                 // Viterbi lane-block size (class-rounded); position in (Bv, index) order
   int nrows;                    // Kp
   unsigned long long msv_off;   // uint32 words into msv pool
+  unsigned long long msvh_off;  // uint32 words into the fp16x2 pool of the TMEM kernel ([x][q][lane])
   unsigned long long vit_off;   // ints into vit pool: trA(int4) | trB(int4) | ps | em[Kp]
   unsigned long long fwd_off;   // floats into fwd pool: trA | trB | bwA | bwB | em[Kp]
   int tbm, tec, bias, base;
@@ -258,7 +259,7 @@ struct MsvArgs {
   const DevHmm *hmms;
   const int *hmm_list;     // profiles with this Q
   int nlist;
-  const uint32_t *tab;     // msv table pool
+  const uint32_t *tab;     // msv table pool (s16x2 striped for msv_kernel, fp16x2 [x][q][lane] for msv_tmem_kernel)
   Targets tg;
   const uint8_t *tjb_li;   // per length index
   const int16_t *thrJ;     // [hmm*nL + li] minimal passing xJ (0..256)

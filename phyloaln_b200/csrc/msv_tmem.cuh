@@ -1,0 +1,266 @@
+// msv_tmem.cuh -- SSV/MSV filter with the emission table resident in Blackwell tensor memory.
+//
+// Why: the shared-memory SSV kernel (kernels.cuh, msv_kernel<Q>) is bound by the 128 B/clk/SM
+// shared-memory crossbar (2 B of emission delta per DP cell) and, behind it, by the half-rate
+// VIADDMNMX.S16x2 on the ALU pipe (ncu: smem wavefronts 82-86 %, ALU 63 %; profiles/).  On sm_100a
+// two more resources are idle in that kernel and this one uses both:
+//   * TMEM (256 KB/SM, 512 columns x 128 lanes x 32 bit) read with tcgen05.ld (SASS LDTM): measured
+//     270 B/clk/SM (tools/probe_sm100.cu), twice the shared-memory crossbar, scoreboarded per
+//     destination register like any load.  The striped table of one profile, (Kp+1) rows x Q
+//     words per lane, is replicated into the four 32-lane quarters; a row fetch is ONE LDTM with a
+//     warp-uniform column address (the residue), no bank conflicts possible.
+//   * the FMA pipe: SSV values are small non-negative integers, exactly representable in fp16, so
+//     u(i,k) = relu(u(i-1,k-1) + delta) is one HFMA2.RELU per two cells (a*1+c, relu fused);
+//     non-negative fp16 bit patterns order like integers, so the running maximum stays a
+//     VIMNMX3.S16x2 on the ALU pipe.  Both pipes issue concurrently (probe: 117 cells/clk/SM for the
+//     8 HFMA2 + 4 VIMNMX3 mix against 63 for VIADDMNMX + VIMNMX3).
+// Exactness: all values below 2048 are exact in fp16; a pair whose true SSV value reaches the
+// candidate threshold Cp (<= 255) is re-run with the exact unsigned-byte MSV recurrence (also in
+// fp16 lanes, values < 256), so rounding above 2048 can only happen to pairs that are already
+// candidates.  Results are bit-identical to msv_kernel<Q> (tests/test_gpu_filters.py).
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "kernels.cuh"
+
+namespace pa {
+
+// ---- tcgen05 wrappers -------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t tmem_alloc(uint32_t *slot, uint32_t ncols) {  // ncols: power of two >= 32
+  if (threadIdx.x < 32) {
+    const uint32_t sa = (uint32_t)__cvta_generic_to_shared(slot);
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sa), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  return *slot;
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t base, uint32_t ncols) {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_cta_sync() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_st1(uint32_t taddr, uint32_t v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// tcgen05.ld 32x32b.xN: lane l of the warp receives N consecutive 32-bit columns of TMEM lane l
+template <int N>
+__device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t (&r)[N]);
+template <>
+__device__ __forceinline__ void tmem_ld<1>(uint32_t taddr, uint32_t (&r)[1]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r[0]) : "r"(taddr) : "memory");
+}
+template <>
+__device__ __forceinline__ void tmem_ld<2>(uint32_t taddr, uint32_t (&r)[2]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(taddr) : "memory");
+}
+template <>
+__device__ __forceinline__ void tmem_ld<4>(uint32_t taddr, uint32_t (&r)[4]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(taddr)
+               : "memory");
+}
+template <>
+__device__ __forceinline__ void tmem_ld<8>(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+template <>
+__device__ __forceinline__ void tmem_ld<16>(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                 "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+               : "r"(taddr)
+               : "memory");
+}
+// tcgen05.wait::ld: the PTX model leaves the destination registers undefined until this point; the
+// "+r" operands make every later use of the row depend on it.  ptxas turns it into scoreboard
+// waits on exactly those registers, so younger loads stay in flight.
+template <int N>
+__device__ __forceinline__ void tmem_wait_ld(uint32_t (&r)[N]) {
+  if constexpr (N == 1) asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(r[0])::"memory");
+  else if constexpr (N == 2) asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(r[0]), "+r"(r[1])::"memory");
+  else if constexpr (N == 4) asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3])::"memory");
+  else {
+#pragma unroll
+    for (int o = 0; o < N; o += 8)
+      asm volatile("tcgen05.wait::ld.sync.aligned;"
+                   : "+r"(r[o]), "+r"(r[o + 1]), "+r"(r[o + 2]), "+r"(r[o + 3]), "+r"(r[o + 4]), "+r"(r[o + 5]), "+r"(r[o + 6]), "+r"(r[o + 7])::"memory");
+  }
+}
+
+// relu(a + c) on two fp16 lanes: HFMA2.RELU a, 1, c
+__device__ __forceinline__ uint32_t h2_add_relu(uint32_t a, uint32_t c) {
+  uint32_t d;
+  asm("fma.rn.relu.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(0x3c003c00u), "r"(c));
+  return d;
+}
+__device__ __forceinline__ int h16_bits_to_int(int bits) { return __half2int_rn(__ushort_as_half((unsigned short)bits)); }
+__device__ __forceinline__ uint32_t int_to_h16x2(int v) { return (uint32_t)__half_as_ushort(__int2half_rn(v)) * 0x10001u; }
+
+__host__ __device__ constexpr int msv_tmem_lw(int Q) { return Q <= 1 ? 1 : Q <= 2 ? 2 : Q <= 4 ? 4 : Q <= 8 ? 8 : 16; }
+// columns needed: (nrows + 1 dead row) * Q, plus the over-read of the last row's LDTM
+__host__ __device__ constexpr int msv_tmem_cols_needed(int Q, int nrows) { return (nrows + 1) * Q + (msv_tmem_lw(Q) - Q); }
+#define PA_TMEM_MAXQ 16
+
+// One SSV row for the whole warp: lane l owns cells (2l+hf)*Q + q (hf = half of word q).
+template <int Q, int LW>
+__device__ __forceinline__ void ssv_row_h2(uint32_t (&w)[Q], uint32_t &m0, uint32_t &m1, const uint32_t (&d)[LW], int lanem1) {
+  const uint32_t tt = __shfl_sync(PA_FULL, w[Q - 1], lanem1);
+  const uint32_t carry = __byte_perm(tt, w[Q - 1], 0x5432);
+#pragma unroll
+  for (int q = Q - 1; q >= 1; q--) w[q] = h2_add_relu(w[q - 1], d[q]);
+  w[0] = h2_add_relu(carry, d[0]);
+#pragma unroll
+  for (int q = 0; q + 1 < Q; q += 2) {
+    if (q & 2) m1 = __vimax3_s16x2(m1, w[q], w[q + 1]);
+    else m0 = __vimax3_s16x2(m0, w[q], w[q + 1]);
+  }
+  if (Q & 1) m1 = __vmaxs2(m1, w[Q - 1]);
+}
+
+// G rows per prefetch group (double-buffered): the LDTMs of group g+1 are in flight while group g
+// is computed.  a.tab: fp16x2 delta pool, per profile [x][q][lane] words, x = 0..nrows-1.
+// CTA shape: Q <= 8 needs <= 256 TMEM columns, so two 512-thread CTAs share an SM (64 registers each);
+// Q 9..16 owns all 512 columns, one 1024-thread CTA per SM (64 registers).
+__host__ __device__ constexpr int msv_tmem_threads(int Q) { return Q <= 8 ? 512 : 1024; }
+template <int Q, int G>
+__global__ void __launch_bounds__(msv_tmem_threads(Q), (Q <= 8 ? 2 : 1)) msv_tmem_kernel(MsvArgs a, int ncols) {
+  constexpr int LW = msv_tmem_lw(Q);
+  __shared__ uint32_t s_slot;
+  // the shuffle tells the compiler that the warp index (and everything derived from it: target index,
+  // length, loop bounds) is warp-uniform, so shuffles inside those loops need no divergence guards
+  const int lane = threadIdx.x & 31, wib = __shfl_sync(PA_FULL, (int)(threadIdx.x >> 5), 0), wpb = blockDim.x >> 5;
+  const uint32_t tbase = tmem_alloc(&s_slot, (uint32_t)ncols);
+  const uint32_t lanebase = tbase + ((uint32_t)((wib & 3) * 32) << 16);
+  const uint32_t ntiles = (a.tg.n + a.tile - 1) / a.tile;
+  const unsigned long long nitems = (unsigned long long)a.nlist * ntiles;
+  int cur_h = -1;
+  unsigned long long ncand = 0;
+  const int lanem1 = (lane + 31) & 31;
+  for (unsigned long long item = blockIdx.x; item < nitems; item += gridDim.x) {
+    const int h = a.hmm_list[item / ntiles];
+    const uint32_t tile = (uint32_t)(item % ntiles);
+    const DevHmm &hm = a.hmms[h];
+    const int nrows = hm.nrows;
+    if (h != cur_h) {
+      tmem_cta_sync();  // every warp is done with the previous table
+      if (wib < 4) {
+        const uint32_t *src = a.tab + hm.msvh_off;
+        for (int x = 0; x < nrows; x++)
+#pragma unroll
+          for (int q = 0; q < Q; q++) tmem_st1(lanebase + x * Q + q, __ldg(src + (x * Q + q) * 32 + lane));
+        const uint32_t dead = int_to_h16x2(PA_MSV_DEAD);
+#pragma unroll
+        for (int q = 0; q < LW; q++) tmem_st1(lanebase + nrows * Q + q, dead);
+        tmem_wait_st();
+      }
+      tmem_cta_sync();
+      cur_h = h;
+    }
+    const int bias = hm.bias, base = hm.base, tec = hm.tec, tbm = hm.tbm;
+    const uint32_t t1 = min(a.tg.n, (tile + 1) * a.tile);
+    for (uint32_t t = tile * a.tile + wib; t < t1; t += wpb) {
+      const int L = (int)a.tg.len[t];
+      if (L == 0) continue;
+      const uint8_t *p = a.tg.dsq + a.tg.off[t];
+      const int li = a.tg.lidx[t];
+      const int tjb = a.tjb_li[li];
+      const int T = a.thrJ[(size_t)h * a.nL + li];
+      const int tjbm = (tjb + tbm) & 0xff;
+      const int xB0 = max(base - tjbm, 0);
+      const int C = min(255 - bias, min(base + 1 + tec, T + tec));
+      const int Cp = a.all_pairs ? 0 : C - xB0;
+      uint32_t w[Q];
+      if (Cp > 0) {
+        // ---- SSV pass: u(i,k) = relu(u(i-1,k-1) + delta(x_i,k)), running max over all cells
+#pragma unroll
+        for (int q = 0; q < Q; q++) w[q] = 0;
+        uint32_t m0 = 0, m1 = 0;
+        for (int i0 = 0; i0 < L; i0 += 32) {
+          const int nr = min(32, L - i0);
+          // lane r holds the TMEM address of row i0+r; rows past the end point at the dead row
+          const uint32_t myaddr = lanebase + (uint32_t)((lane < nr ? (int)p[i0 + lane] : nrows) * Q);
+          uint32_t buf[2][G][LW];
+#pragma unroll
+          for (int g = 0; g < G; g++) tmem_ld<LW>(__shfl_sync(PA_FULL, myaddr, g), buf[0][g]);
+          // the 32-row block is fully unrolled (row indices are immediates, no register rotation copies);
+          // the prefetch of the next group is unconditional: past the end it fetches the dead row
+#pragma unroll
+          for (int r = 0; r < 32; r += G) {
+            if (r >= nr) break;
+            constexpr int dummy = 0;
+            (void)dummy;
+            if (r + G < 32) {
+#pragma unroll
+              for (int g = 0; g < G; g++) tmem_ld<LW>(__shfl_sync(PA_FULL, myaddr, r + G + g), buf[((r / G) & 1) ^ 1][g]);
+            }
+#pragma unroll
+            for (int g = 0; g < G; g++) {
+              tmem_wait_ld<LW>(buf[(r / G) & 1][g]);
+              ssv_row_h2<Q, LW>(w, m0, m1, buf[(r / G) & 1][g], lanem1);
+            }
+          }
+        }
+        const int U = h16_bits_to_int(warp_max16x2(__vmaxs2(m0, m1)));
+        if (U < Cp) continue;
+      }
+      ncand++;
+      // ---- exact MSV recurrence (J state, overflow) for candidates; values < 256, exact in fp16
+      int xJ = 0, xB = xB0;
+      bool overflow = false;
+#pragma unroll
+      for (int q = 0; q < Q; q++) w[q] = 0;
+      for (int i = 0; i < L; i++) {
+        uint32_t d[LW];
+        tmem_ld<LW>(lanebase + (uint32_t)((int)p[i] * Q), d);
+        const uint32_t xBv = int_to_h16x2(xB);
+        const uint32_t tt = __shfl_sync(PA_FULL, w[Q - 1], lanem1);
+        const uint32_t carry = __byte_perm(tt, w[Q - 1], 0x5432);
+        tmem_wait_ld<LW>(d);
+        uint32_t rm = 0;
+#pragma unroll
+        for (int q = Q - 1; q >= 1; q--) {
+          w[q] = h2_add_relu(__vmaxs2(w[q - 1], xBv), d[q]);
+          rm = __vmaxs2(rm, w[q]);
+        }
+        w[0] = h2_add_relu(__vmaxs2(carry, xBv), d[0]);
+        rm = __vmaxs2(rm, w[0]);
+        int xE = h16_bits_to_int(warp_max16x2(rm));
+        if (xE >= 255 - bias) { overflow = true; break; }
+        xE = max(xE - tec, 0);
+        xJ = max(xJ, xE);
+        xB = max(max(base, xJ) - tjbm, 0);
+      }
+      if (overflow) xJ = -1;
+      if (a.all_pairs || overflow || xJ >= T) {
+        if (lane == 0) {
+          unsigned long long idx = atomicAdd(a.out_count, 1ull);
+          if (idx < a.out_cap) {
+            Pass1 r;
+            r.t = t; r.h = (uint16_t)h; r.xJ = (int16_t)xJ;
+            a.out[idx] = r;
+          }
+        }
+      }
+    }
+  }
+  if (lane == 0 && ncand) atomicAdd(a.n_ssv_cand, ncand);
+  tmem_dealloc(tbase, (uint32_t)ncols);
+}
+
+}  // namespace pa
