@@ -303,10 +303,13 @@ extern "C" int pa_commit_hmms(pa_ctx *ctx) {
           msv[d.msv_off + (size_t)x * roww + msv_word_pos(Q, q, lane)] = (uint32_t)(uint16_t)half[0] | ((uint32_t)(uint16_t)half[1] << 16);
         }
 
-    // ---- the same deltas as fp16x2, [x][q][lane], for the tensor-memory kernel (msv_tmem.cuh)
+    // ---- the same deltas as fp16x2 for the tensor-memory kernel (msv_tmem.cuh): words q < QT as
+    // [x][q][lane] (TMEM part), words q >= QT striped like the s16 table (shared-memory part, Q > 16)
     d.msvh_off = msvh.size();
     if (msv_use_tmem(ctx, Q, Kp)) {
+      const int QT = msv_tmem_qt(Q), QS = Q - QT;
       msvh.resize(msvh.size() + (size_t)Kp * roww, 0);
+      uint32_t *tpart = msvh.data() + d.msvh_off, *spart = tpart + (size_t)Kp * QT * 32;
       for (int x = 0; x < Kp; x++)
         for (int q = 0; q < Q; q++)
           for (int lane = 0; lane < 32; lane++) {
@@ -315,7 +318,9 @@ extern "C" int pa_commit_hmms(pa_ctx *ctx) {
               const int cell = (2 * lane + hf) * Q + q, k = cell + 1;
               half[hf] = h16_exact(k <= M ? (int)hp.bias_b - (int)hp.rbv[(size_t)x * (M + 1) + k] : PA_MSV_DEAD);
             }
-            msvh[d.msvh_off + ((size_t)x * Q + q) * 32 + lane] = (uint32_t)half[0] | ((uint32_t)half[1] << 16);
+            const uint32_t word = (uint32_t)half[0] | ((uint32_t)half[1] << 16);
+            if (q < QT) tpart[((size_t)x * QT + q) * 32 + lane] = word;
+            else spart[(size_t)x * QS * 32 + msv_word_pos(QS, q - QT, lane)] = word;
           }
     }
 
@@ -649,12 +654,17 @@ static cudaError_t launch_msv_tmem(pa_ctx *ctx, MsvArgs &a, int nrows) {
   while (ncols < need) ncols *= 2;
   // resident CTAs per SM: fixed by the kernel's __launch_bounds__ (register cap) and by TMEM -- every
   // resident CTA must own its columns, or it would spin in tcgen05.alloc until a neighbour exits
-  const int bps = std::max(1, std::min(Q <= 8 ? 2 : 1, 512 / ncols));
+  const int bps = std::max(1, std::min(MsvTmemCfg<Q>::MINB, 512 / ncols));
+  const size_t smem = (size_t)(nrows + 1) * MsvTmemCfg<Q>::QS * 32 * 4;  // hybrid (Q > 16) only
+  if (smem) {
+    cudaError_t e = cudaFuncSetAttribute(msv_tmem_kernel<Q, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
   const uint32_t ntiles = (a.tg.n + a.tile - 1) / a.tile;
   const unsigned long long nitems = (unsigned long long)a.nlist * ntiles;
   const int grid = (int)std::min<unsigned long long>(nitems, (unsigned long long)ctx->num_sms * bps);
   a.tab = ctx->d_msvh.p;
-  if (grid > 0) msv_tmem_kernel<Q, G><<<grid, msv_tmem_threads(Q), 0, ctx->stream>>>(a, ncols);
+  if (grid > 0) msv_tmem_kernel<Q, G><<<grid, MsvTmemCfg<Q>::THREADS, smem, ctx->stream>>>(a, ncols);
   ctx->stats.kernel_launches++;
   return cudaGetLastError();
 }
@@ -664,6 +674,7 @@ static cudaError_t dispatch_msv(pa_ctx *ctx, int Q, MsvArgs &a, int nrows) {
     switch (Q) {
 #define C_(q) case q: return launch_msv_tmem<q>(ctx, a, nrows);
       C_(1) C_(2) C_(3) C_(4) C_(5) C_(6) C_(7) C_(8) C_(9) C_(10) C_(11) C_(12) C_(13) C_(14) C_(15) C_(16)
+      C_(17) C_(18) C_(19) C_(20) C_(21) C_(22) C_(23) C_(24) C_(25) C_(26) C_(27) C_(28) C_(29) C_(30) C_(31) C_(32)
 #undef C_
     }
   }

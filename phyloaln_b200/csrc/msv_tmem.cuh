@@ -113,18 +113,42 @@ __device__ __forceinline__ int h16_bits_to_int(int bits) { return __half2int_rn(
 __device__ __forceinline__ uint32_t int_to_h16x2(int v) { return (uint32_t)__half_as_ushort(__int2half_rn(v)) * 0x10001u; }
 
 __host__ __device__ constexpr int msv_tmem_lw(int Q) { return Q <= 1 ? 1 : Q <= 2 ? 2 : Q <= 4 ? 4 : Q <= 8 ? 8 : 16; }
-// columns needed: (nrows + 1 dead row) * Q, plus the over-read of the last row's LDTM
-__host__ __device__ constexpr int msv_tmem_cols_needed(int Q, int nrows) { return (nrows + 1) * Q + (msv_tmem_lw(Q) - Q); }
-#define PA_TMEM_MAXQ 16
+#define PA_TMEM_MAXQ 32
+
+// Geometry per Q (words per lane, Q = M/64 + 1):
+//   Q <= 8    table needs <= 256 TMEM columns: two 512-thread CTAs per SM, 64 registers each
+//   Q 9..16   all 512 columns: one 1024-thread CTA per SM, 64 registers
+//   Q 17..32  hybrid: the first 16 words of every row come from TMEM, the other Q-16 from shared
+//             memory (LDS.128, the striped layout of msv_kernel); one 512-thread CTA per SM
+template <int Q>
+struct MsvTmemCfg {
+  static constexpr int QT = Q <= 16 ? Q : 16;
+  static constexpr int QS = Q - QT;
+  static constexpr int LW = msv_tmem_lw(QT);
+  static constexpr int THREADS = Q <= 8 ? 512 : Q <= 16 ? 1024 : 512;
+  static constexpr int MINB = Q <= 8 ? 2 : 1;
+};
+__host__ __device__ constexpr int msv_tmem_qt(int Q) { return Q <= 16 ? Q : 16; }
+// TMEM columns: (nrows + 1 dead row) * QT, plus the over-read of the last row's LDTM
+__host__ __device__ constexpr int msv_tmem_cols_needed(int Q, int nrows) {
+  return (nrows + 1) * msv_tmem_qt(Q) + (msv_tmem_lw(msv_tmem_qt(Q)) - msv_tmem_qt(Q));
+}
+// words of the fp16x2 pool per profile: TMEM part [x][q < QT][lane], then the shared-memory part
+// [x][striped QS*32] (rows 0..nrows-1; the dead row is synthesised on the device)
+__host__ __device__ constexpr size_t msv_tmem_pool_words(int Q, int nrows) { return (size_t)nrows * Q * 32; }
 
 // One SSV row for the whole warp: lane l owns cells (2l+hf)*Q + q (hf = half of word q).
-template <int Q, int LW>
-__device__ __forceinline__ void ssv_row_h2(uint32_t (&w)[Q], uint32_t &m0, uint32_t &m1, const uint32_t (&d)[LW], int lanem1) {
+template <int Q, int QT, int LW>
+__device__ __forceinline__ void ssv_row_h2(uint32_t (&w)[Q], uint32_t &m0, uint32_t &m1, const uint32_t (&dt)[LW],
+                                           const uint32_t *srow, int lane, int lanem1) {
+  constexpr int QS = Q - QT;
+  uint32_t ds[QS > 0 ? QS : 1];
+  if constexpr (QS > 0) msv_load_row<QS>(srow, lane, ds);
   const uint32_t tt = __shfl_sync(PA_FULL, w[Q - 1], lanem1);
   const uint32_t carry = __byte_perm(tt, w[Q - 1], 0x5432);
 #pragma unroll
-  for (int q = Q - 1; q >= 1; q--) w[q] = h2_add_relu(w[q - 1], d[q]);
-  w[0] = h2_add_relu(carry, d[0]);
+  for (int q = Q - 1; q >= 1; q--) w[q] = h2_add_relu(w[q - 1], q < QT ? dt[q < QT ? q : 0] : ds[q >= QT ? q - QT : 0]);
+  w[0] = h2_add_relu(carry, dt[0]);
 #pragma unroll
   for (int q = 0; q + 1 < Q; q += 2) {
     if (q & 2) m1 = __vimax3_s16x2(m1, w[q], w[q + 1]);
@@ -134,13 +158,15 @@ __device__ __forceinline__ void ssv_row_h2(uint32_t (&w)[Q], uint32_t &m0, uint3
 }
 
 // G rows per prefetch group (double-buffered): the LDTMs of group g+1 are in flight while group g
-// is computed.  a.tab: fp16x2 delta pool, per profile [x][q][lane] words, x = 0..nrows-1.
-// CTA shape: Q <= 8 needs <= 256 TMEM columns, so two 512-thread CTAs share an SM (64 registers each);
-// Q 9..16 owns all 512 columns, one 1024-thread CTA per SM (64 registers).
-__host__ __device__ constexpr int msv_tmem_threads(int Q) { return Q <= 8 ? 512 : 1024; }
+// is computed.  The residues of the next 32-row block (of this target or of the warp's next target)
+// and the next target's metadata are fetched one block ahead, so no global-memory latency sits on
+// the per-target critical path.
 template <int Q, int G>
-__global__ void __launch_bounds__(msv_tmem_threads(Q), (Q <= 8 ? 2 : 1)) msv_tmem_kernel(MsvArgs a, int ncols) {
-  constexpr int LW = msv_tmem_lw(Q);
+__global__ void __launch_bounds__(MsvTmemCfg<Q>::THREADS, MsvTmemCfg<Q>::MINB) msv_tmem_kernel(MsvArgs a, int ncols) {
+  using Cfg = MsvTmemCfg<Q>;
+  constexpr int QT = Cfg::QT, QS = Cfg::QS, LW = Cfg::LW;
+  constexpr int SROW = QS * 32;                       // words per shared-memory row
+  extern __shared__ __align__(16) uint32_t s_tab[];  // (nrows + 1) * SROW words (hybrid only)
   __shared__ uint32_t s_slot;
   // the shuffle tells the compiler that the warp index (and everything derived from it: target index,
   // length, loop bounds) is warp-uniform, so shuffles inside those loops need no divergence guards
@@ -159,26 +185,38 @@ __global__ void __launch_bounds__(msv_tmem_threads(Q), (Q <= 8 ? 2 : 1)) msv_tme
     const int nrows = hm.nrows;
     if (h != cur_h) {
       tmem_cta_sync();  // every warp is done with the previous table
+      const uint32_t *src = a.tab + hm.msvh_off;
+      const uint32_t dead = int_to_h16x2(PA_MSV_DEAD);
       if (wib < 4) {
-        const uint32_t *src = a.tab + hm.msvh_off;
         for (int x = 0; x < nrows; x++)
 #pragma unroll
-          for (int q = 0; q < Q; q++) tmem_st1(lanebase + x * Q + q, __ldg(src + (x * Q + q) * 32 + lane));
-        const uint32_t dead = int_to_h16x2(PA_MSV_DEAD);
+          for (int q = 0; q < QT; q++) tmem_st1(lanebase + x * QT + q, __ldg(src + (x * QT + q) * 32 + lane));
 #pragma unroll
-        for (int q = 0; q < LW; q++) tmem_st1(lanebase + nrows * Q + q, dead);
+        for (int q = 0; q < LW; q++) tmem_st1(lanebase + nrows * QT + q, dead);
         tmem_wait_st();
+      }
+      if constexpr (QS > 0) {
+        const uint32_t *ssrc = src + (size_t)nrows * QT * 32;
+        for (int i = threadIdx.x; i < nrows * SROW; i += blockDim.x) s_tab[i] = __ldg(ssrc + i);
+        for (int i = threadIdx.x; i < SROW; i += blockDim.x) s_tab[nrows * SROW + i] = dead;
       }
       tmem_cta_sync();
       cur_h = h;
     }
     const int bias = hm.bias, base = hm.base, tec = hm.tec, tbm = hm.tbm;
     const uint32_t t1 = min(a.tg.n, (tile + 1) * a.tile);
-    for (uint32_t t = tile * a.tile + wib; t < t1; t += wpb) {
-      const int L = (int)a.tg.len[t];
-      if (L == 0) continue;
-      const uint8_t *p = a.tg.dsq + a.tg.off[t];
-      const int li = a.tg.lidx[t];
+    uint32_t t = tile * a.tile + wib;
+    int nxL = 0, nxli = 0;
+    uint32_t nxoff = 0;
+    if (t < t1) { nxL = (int)a.tg.len[t]; nxoff = a.tg.off[t]; nxli = a.tg.lidx[t]; }
+    int pre_x = 0;          // this lane's residue of the next block to be processed
+    bool have_pre = false;  // warp-uniform
+    for (; t < t1; t += wpb) {
+      const int L = nxL, li = nxli;
+      const uint8_t *p = a.tg.dsq + nxoff;
+      if (t + wpb < t1) { nxL = (int)a.tg.len[t + wpb]; nxoff = a.tg.off[t + wpb]; nxli = a.tg.lidx[t + wpb]; }
+      else nxL = 0;
+      if (L == 0) { have_pre = false; continue; }
       const int tjb = a.tjb_li[li];
       const int T = a.thrJ[(size_t)h * a.nL + li];
       const int tjbm = (tjb + tbm) & 0xff;
@@ -191,10 +229,14 @@ __global__ void __launch_bounds__(msv_tmem_threads(Q), (Q <= 8 ? 2 : 1)) msv_tme
 #pragma unroll
         for (int q = 0; q < Q; q++) w[q] = 0;
         uint32_t m0 = 0, m1 = 0;
+        if (!have_pre) pre_x = lane < L ? (int)p[lane] : nrows;
         for (int i0 = 0; i0 < L; i0 += 32) {
           const int nr = min(32, L - i0);
-          // lane r holds the TMEM address of row i0+r; rows past the end point at the dead row
-          const uint32_t myaddr = lanebase + (uint32_t)((lane < nr ? (int)p[i0 + lane] : nrows) * Q);
+          // lane r holds row i0+r: its residue (rows past the end: the dead row)
+          const int myx = pre_x;
+          if (i0 + 32 < L) pre_x = i0 + 32 + lane < L ? (int)p[i0 + 32 + lane] : nrows;
+          else { pre_x = lane < nxL ? (int)a.tg.dsq[nxoff + lane] : nrows; have_pre = true; }
+          const uint32_t myaddr = lanebase + (uint32_t)(myx * QT);
           uint32_t buf[2][G][LW];
 #pragma unroll
           for (int g = 0; g < G; g++) tmem_ld<LW>(__shfl_sync(PA_FULL, myaddr, g), buf[0][g]);
@@ -203,22 +245,23 @@ __global__ void __launch_bounds__(msv_tmem_threads(Q), (Q <= 8 ? 2 : 1)) msv_tme
 #pragma unroll
           for (int r = 0; r < 32; r += G) {
             if (r >= nr) break;
-            constexpr int dummy = 0;
-            (void)dummy;
             if (r + G < 32) {
 #pragma unroll
               for (int g = 0; g < G; g++) tmem_ld<LW>(__shfl_sync(PA_FULL, myaddr, r + G + g), buf[((r / G) & 1) ^ 1][g]);
             }
 #pragma unroll
             for (int g = 0; g < G; g++) {
+              const uint32_t *srow = s_tab;
+              if constexpr (QS > 0) srow = s_tab + __shfl_sync(PA_FULL, myx, r + g) * SROW;
               tmem_wait_ld<LW>(buf[(r / G) & 1][g]);
-              ssv_row_h2<Q, LW>(w, m0, m1, buf[(r / G) & 1][g], lanem1);
+              ssv_row_h2<Q, QT, LW>(w, m0, m1, buf[(r / G) & 1][g], srow, lane, lanem1);
             }
           }
         }
         const int U = h16_bits_to_int(warp_max16x2(__vmaxs2(m0, m1)));
         if (U < Cp) continue;
-      }
+      } else
+        have_pre = false;
       ncand++;
       // ---- exact MSV recurrence (J state, overflow) for candidates; values < 256, exact in fp16
       int xJ = 0, xB = xB0;
@@ -226,8 +269,10 @@ __global__ void __launch_bounds__(msv_tmem_threads(Q), (Q <= 8 ? 2 : 1)) msv_tme
 #pragma unroll
       for (int q = 0; q < Q; q++) w[q] = 0;
       for (int i = 0; i < L; i++) {
-        uint32_t d[LW];
-        tmem_ld<LW>(lanebase + (uint32_t)((int)p[i] * Q), d);
+        const int x = p[i];
+        uint32_t d[LW], ds[QS > 0 ? QS : 1];
+        tmem_ld<LW>(lanebase + (uint32_t)(x * QT), d);
+        if constexpr (QS > 0) msv_load_row<QS>(s_tab + x * SROW, lane, ds);
         const uint32_t xBv = int_to_h16x2(xB);
         const uint32_t tt = __shfl_sync(PA_FULL, w[Q - 1], lanem1);
         const uint32_t carry = __byte_perm(tt, w[Q - 1], 0x5432);
@@ -235,7 +280,7 @@ __global__ void __launch_bounds__(msv_tmem_threads(Q), (Q <= 8 ? 2 : 1)) msv_tme
         uint32_t rm = 0;
 #pragma unroll
         for (int q = Q - 1; q >= 1; q--) {
-          w[q] = h2_add_relu(__vmaxs2(w[q - 1], xBv), d[q]);
+          w[q] = h2_add_relu(__vmaxs2(w[q - 1], xBv), q < QT ? d[q < QT ? q : 0] : ds[q >= QT ? q - QT : 0]);
           rm = __vmaxs2(rm, w[q]);
         }
         w[0] = h2_add_relu(__vmaxs2(carry, xBv), d[0]);
