@@ -73,6 +73,8 @@ typedef struct {
   uint64_t kernel_launches;                                /* CUDA kernels launched so far  */
   float ms_translate, ms_msv, ms_bias, ms_vit, ms_fwd, ms_domain; /* last call, CUDA events */
   float ms_h2d, ms_total;
+  float ms_domain_kernel;                                  /* domain_kernel alone (ms_domain adds D2H + host scoring) */
+  float reserved0;
 } pa_stats;
 
 /* per-hit column mapping result (pa_map_hits) */
@@ -126,9 +128,10 @@ int pa_get_stats(pa_ctx *ctx, pa_stats *st);
 int pa_score_all(pa_ctx *ctx, int hmm, float *msv, int32_t *msv_raw, float *vit, int32_t *vit_raw,
                  float *fwd, float *bias);
 
-/* Measured issue rate of the DPX integer pipe (no reference equivalent; roofline denominator).
- * mode 0 VIADDMNMX.S16x2.RELU, 1 VIMNMX3.S16x2, 2 SSV mix, 3 VIADDMNMX.S32. Result in giga
- * thread-instructions per second over the whole GPU. */
+/* Measured issue rates of the instructions the filters are built from (no reference equivalent;
+ * roofline denominators). mode 0 VIADDMNMX.S16x2.RELU, 1 VIMNMX3.S16x2, 2 DPX SSV mix (8 VIADDMNMX +
+ * 4 VIMNMX3), 3 VIADDMNMX.S32, 4 HFMA2.RELU, 5 fp16 SSV mix of msv_tmem_kernel (8 HFMA2.RELU + 4
+ * VIMNMX3.S16x2 per 16 cells). Result in giga thread-instructions per second over the whole GPU. */
 int pa_microbench_dpx(pa_ctx *ctx, int mode, double *ginstr_per_s);
 
 /* Hit -> reference-column mapping (extend_pos = 0). For hit h: model/aligned strings (PhyloAln

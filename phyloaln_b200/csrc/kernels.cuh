@@ -837,8 +837,12 @@ __global__ void __launch_bounds__(256) dpx_microbench_kernel(uint32_t *out, int 
       if (MODE == 1) v[i] = __vimax3_s16x2(v[i], d, m);                  // 3-input max
       if (MODE == 2) { v[i] = __viaddmax_s16x2_relu(v[i], d, 0u); if (i & 1) m = __vimax3_s16x2(m, v[i], v[i - 1]); }  // SSV mix
       if (MODE == 3) v[i] = (uint32_t)__viaddmax_s32((int)v[i], (int)d, -32768);  // Viterbi op
+      if (MODE == 4 || MODE == 5) {  // fp16x2 SSV cell op of msv_tmem_kernel: HFMA2.RELU (FMA pipe)
+        asm("fma.rn.relu.f16x2 %0, %0, %1, %2;" : "+r"(v[i]) : "r"(0x3c003c00u), "r"(d));
+        if (MODE == 5 && (i & 1)) m = __vimax3_s16x2(m, v[i], v[i - 1]);  // + running max (ALU pipe)
+      }
     }
-    d += 0x00010001u;
+    if (MODE >= 4) d ^= 0x80008000u; else d += 0x00010001u;
   }
   uint32_t r = m;
 #pragma unroll
