@@ -529,10 +529,22 @@ extern "C" int64_t pa_load_reads(pa_ctx *ctx, const char *nt, const uint64_t *of
   CK(ctx->d_tlen.ensure(ntargets64 + 1));
   cudaEventRecord(e1, ctx->stream);
   const int grid = std::min<uint64_t>((nreads + 7) / 8, (uint64_t)ctx->num_sms * 16);
-  if (nreads)
-    translate_kernel<<<std::max(grid, 1), 256, 0, ctx->stream>>>(ctx->d_nt.p, ctx->d_ntoff.p, nreads, moltype == PA_TRANSLATE ? 0 : 1,
-                                                               nfwd, nrev, ctx->d_codon.p, ctx->d_dsq.p, ctx->d_toff.p,
-                                                               ctx->d_tlen.p, ctx->d_flag.p);
+  if (nreads) {
+    if (moltype == PA_TRANSLATE) {
+#define PA_TR_LAUNCH(F, R)                                                                                                  \
+  translate_kernel<F, R><<<std::max(grid, 1), 256, 0, ctx->stream>>>(ctx->d_nt.p, ctx->d_ntoff.p, nreads, ctx->d_codon.p,   \
+                                                                     ctx->d_dsq.p, ctx->d_toff.p, ctx->d_tlen.p, ctx->d_flag.p)
+      if (nfwd == 3 && nrev == 3) PA_TR_LAUNCH(3, 3);
+      else if (nfwd == 3) PA_TR_LAUNCH(3, 0);
+      else if (nrev == 3) PA_TR_LAUNCH(1, 3);
+      else PA_TR_LAUNCH(1, 0);
+#undef PA_TR_LAUNCH
+    }
+    else
+      translate_generic_kernel<<<std::max(grid, 1), 256, 0, ctx->stream>>>(ctx->d_nt.p, ctx->d_ntoff.p, nreads, 1, nfwd, nrev,
+                                                                         ctx->d_codon.p, ctx->d_dsq.p, ctx->d_toff.p, ctx->d_tlen.p,
+                                                                         ctx->d_flag.p);
+  }
   ctx->stats.kernel_launches++;
   cudaEventRecord(e2, ctx->stream);
   int flag = 0;

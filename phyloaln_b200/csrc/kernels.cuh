@@ -128,75 +128,194 @@ __device__ __forceinline__ uint32_t target_base(unsigned long long ntoff, uint32
   return (uint32_t)(((2ull * ntoff + 3ull) & ~3ull) + 32ull * r);
 }
 
-// One warp per read. The read's nucleotides are staged once in shared memory as 4-bit IUPAC masks
-// (coalesced byte loads, one nt_mask() per base instead of one per codon use); each lane then emits
-// 4 consecutive residues of one frame as a single 32-bit store. HBM traffic = L bytes in,
-// ~2L bytes out per read (446 B for 150 bp).
+// Generic per-read routine (any length, both molecule types): every lane converts the nucleotides it
+// needs straight from global memory.  Used for nucleotide targets and for reads longer than the
+// staging buffer of translate_kernel.
 #define PA_TR_MAXL 1024
-__global__ void __launch_bounds__(256) translate_kernel(const char *__restrict__ nt, const unsigned long long *__restrict__ off,
-                                                        uint32_t nreads, int moltype, int nfwd, int nrev,
-                                                        const uint8_t *__restrict__ tab64, uint8_t *__restrict__ out,
-                                                        uint32_t *__restrict__ tgt_off, uint32_t *__restrict__ tgt_len,
-                                                        int *__restrict__ err) {
+__device__ void translate_read_generic(const char *__restrict__ nt, unsigned long long o, int L, uint32_t r, int moltype, int nfwd,
+                                       int nrev, const uint8_t *tab64, uint8_t *__restrict__ out, uint32_t *__restrict__ tgt_off,
+                                       uint32_t *__restrict__ tgt_len, int *__restrict__ err, int lane) {
+  const int nframes = nfwd + nrev;
+  auto mask_at = [&](int i) -> int {
+    int m = nt_mask((uint8_t)nt[o + i]);
+    if (m == 0) { atomicExch(err, 1); m = 15; }
+    return m;
+  };
+  uint32_t pos = target_base(o, r);
+  for (int f = 0; f < nframes; f++) {
+    const bool rev = (moltype == 1) ? (f == 1) : (f >= nfwd);
+    const int j = (moltype == 1) ? 0 : (rev ? f - nfwd : f);  // frame offset 0..2
+    const int step = moltype == 1 ? 1 : 3;
+    const int nres = moltype == 1 ? L : ((L - j) >= 3 ? (L - j) / 3 : 0);
+    const int nwords = (nres + 3) >> 2;
+    for (int w = lane; w < nwords; w += 32) {
+      uint32_t word = 0;
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const int c = 4 * w + q;
+        int code = 0;
+        if (c < nres) {
+          const int p0 = j + step * c;
+          if (moltype == 1) {
+            int m = rev ? comp_mask(mask_at(L - 1 - p0)) : mask_at(p0);
+            code = dna_code(m);
+          } else {
+            int m0, m1, m2;
+            if (!rev) { m0 = mask_at(p0); m1 = mask_at(p0 + 1); m2 = mask_at(p0 + 2); }
+            else { m0 = comp_mask(mask_at(L - 1 - p0)); m1 = comp_mask(mask_at(L - 2 - p0)); m2 = comp_mask(mask_at(L - 3 - p0)); }
+            code = codon_code(m0, m1, m2, tab64);
+          }
+        }
+        word |= (uint32_t)code << (8 * q);
+      }
+      *reinterpret_cast<uint32_t *>(out + pos + 4 * w) = word;
+    }
+    if (lane == 0) { tgt_off[(size_t)r * nframes + f] = pos; tgt_len[(size_t)r * nframes + f] = nres; }
+    pos += (nres + 3) & ~3;
+  }
+}
+
+__global__ void __launch_bounds__(256) translate_generic_kernel(const char *__restrict__ nt, const unsigned long long *__restrict__ off,
+                                                                uint32_t nreads, int moltype, int nfwd, int nrev,
+                                                                const uint8_t *__restrict__ tab64, uint8_t *__restrict__ out,
+                                                                uint32_t *__restrict__ tgt_off, uint32_t *__restrict__ tgt_len,
+                                                                int *__restrict__ err) {
   __shared__ uint8_t s_tab[64];
-  __shared__ uint8_t s_mask[8][PA_TR_MAXL];
   if (threadIdx.x < 64) s_tab[threadIdx.x] = tab64[threadIdx.x];
   __syncthreads();
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-  const int nframes = nfwd + nrev;
-  uint8_t *mk = s_mask[wib];
+  for (uint32_t r = blockIdx.x * wpb + wib; r < nreads; r += gridDim.x * wpb) {
+    const unsigned long long o = off[r];
+    translate_read_generic(nt, o, (int)(off[r + 1] - o), r, moltype, nfwd, nrev, s_tab, out, tgt_off, tgt_len, err, lane);
+  }
+}
+
+// Exact IUPAC path for one triplet (Biopython rules): forward residue and the residue of the reverse
+// complement.  Kept out of line: it runs for the ~0.3 % of triplets that contain a non-ACGTU letter.
+__device__ __noinline__ int translate_ambiguous(int m0, int m1, int m2, const uint8_t *tab64) {
+  auto one = [&](int a0, int a1, int a2) -> int {
+    uint32_t seen = 0;
+    int nstop = 0, ntot = 0;
+#pragma unroll 1
+    for (int x = a0; x; x &= x - 1)
+#pragma unroll 1
+      for (int y = a1; y; y &= y - 1)
+#pragma unroll 1
+        for (int z = a2; z; z &= z - 1) {
+          const int r = tab64[(__ffs(x) - 1) * 16 + (__ffs(y) - 1) * 4 + (__ffs(z) - 1)];
+          ntot++;
+          if (r == 27) nstop++;
+          else seen |= 1u << r;
+        }
+    if (nstop == ntot) return 27;
+    if (nstop > 0) return 26;
+    if (__popc(seen) == 1) return __ffs(seen) - 1;
+    if ((seen & ~((1u << 2) | (1u << 11))) == 0) return 21;  // D,N -> B
+    if ((seen & ~((1u << 3) | (1u << 13))) == 0) return 23;  // E,Q -> Z
+    if ((seen & ~((1u << 7) | (1u << 9))) == 0) return 22;   // I,L -> J
+    return 26;
+  };
+  return one(m0, m1, m2) | (one(comp_mask(m2), comp_mask(m1), comp_mask(m0)) << 8);
+}
+
+// Translation (reference lib/aln.py:233-259), HBM-bound design.  One warp per read:
+//   1. coalesced byte loads; a 256-byte table turns each character into a 2-bit code (A0 C1 T/U2 G3,
+//      either case; complement = code ^ 2), an "ambiguous" flag and its 4-bit IUPAC mask;
+//   2. lane q forms the 6-bit index of the triplet starting at q from its own code and its two right
+//      neighbours (warp shuffles, no shared-memory traffic) and looks it up twice in 64-byte tables:
+//      the forward codon table and the table of the reverse-complemented codon.  Position q yields
+//      exactly one forward residue (frame q % 3) and one reverse residue (frame (L-3-q) % 3);
+//   3. the two residues are scattered as bytes into the read's frame-major image in shared memory, which
+//      is then copied out with coalesced 32-bit stores.
+// HBM traffic per read: L bytes in, six 4-byte-padded frames out (446 B algorithmic for 150 bp).
+template <int NFWD, int NREV>
+__global__ void __launch_bounds__(256) translate_kernel(const char *__restrict__ nt, const unsigned long long *__restrict__ off,
+                                                        uint32_t nreads, const uint8_t *__restrict__ tab64,
+                                                        uint8_t *__restrict__ out, uint32_t *__restrict__ tgt_off,
+                                                        uint32_t *__restrict__ tgt_len, int *__restrict__ err) {
+  constexpr int NFR = NFWD + NREV;
+  __shared__ uint8_t s_tab[64], s_tabF[64], s_tabR[64], s_nt[256];
+  __shared__ __align__(16) uint8_t s_out[8][2 * PA_TR_MAXL + 32];
+  if (threadIdx.x < 64) {
+    s_tab[threadIdx.x] = tab64[threadIdx.x];
+    // my code order A0 C1 T2 G3 -> tab64 digit order T0 C1 A2 G3
+    const int f = threadIdx.x, c0 = f >> 4, c1 = (f >> 2) & 3, c2 = f & 3;
+    auto m = [](int c) { return c == 0 ? 2 : c == 2 ? 0 : c; };
+    s_tabF[f] = tab64[m(c0) * 16 + m(c1) * 4 + m(c2)];
+    s_tabR[f] = tab64[m(c2 ^ 2) * 16 + m(c1 ^ 2) * 4 + m(c0 ^ 2)];
+  }
+  {  // per character: bits 0-1 code, bit 2 = not A/C/G/T/U, bit 3 = not a nucleotide letter at all, bits 4-7 IUPAC mask
+    const int c = threadIdx.x;
+    const int mk = nt_mask((uint8_t)c);
+    const bool plain = mk == 1 || mk == 2 || mk == 4 || mk == 8;
+    s_nt[c] = (uint8_t)(((c >> 1) & 3) | (plain ? 0 : 4) | (mk == 0 ? 8 : 0) | ((mk ? mk : 15) << 4));
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wib = __shfl_sync(PA_FULL, (int)(threadIdx.x >> 5), 0), wpb = blockDim.x >> 5;
+  uint8_t *so = s_out[wib];
   for (uint32_t r = blockIdx.x * wpb + wib; r < nreads; r += gridDim.x * wpb) {
     const unsigned long long o = off[r];
     const int L = (int)(off[r + 1] - o);
-    const bool staged = L <= PA_TR_MAXL;
-    __syncwarp();
-    if (staged) {
-      bool bad = false;
-      for (int i = lane; i < L; i += 32) {
-        int m = nt_mask((uint8_t)nt[o + i]);
-        if (m == 0) { bad = true; m = 15; }
-        mk[i] = (uint8_t)m;
-      }
-      if (bad) atomicExch(err, 1);
-      __syncwarp();
+    if (L > PA_TR_MAXL) {
+      translate_read_generic(nt, o, L, r, 0, NFWD, NREV, s_tab, out, tgt_off, tgt_len, err, lane);
+      continue;
     }
-    auto mask_at = [&](int i) -> int {
-      if (staged) return mk[i];
-      int m = nt_mask((uint8_t)nt[o + i]);
-      if (m == 0) { atomicExch(err, 1); m = 15; }
-      return m;
-    };
-    uint32_t pos = target_base(o, r);
-    for (int f = 0; f < nframes; f++) {
-      const bool rev = (moltype == 1) ? (f == 1) : (f >= nfwd);
-      const int j = (moltype == 1) ? 0 : (rev ? f - nfwd : f);  // frame offset 0..2
-      const int step = moltype == 1 ? 1 : 3;
-      const int nres = moltype == 1 ? L : ((L - j) >= 3 ? (L - j) / 3 : 0);
-      const int nwords = (nres + 3) >> 2;
-      for (int w = lane; w < nwords; w += 32) {
-        uint32_t word = 0;
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-          const int c = 4 * w + q;
-          int code = 0;
-          if (c < nres) {
-            const int p0 = j + step * c;
-            if (moltype == 1) {
-              int m = rev ? comp_mask(mask_at(L - 1 - p0)) : mask_at(p0);
-              code = dna_code(m);
-            } else {
-              int m0, m1, m2;
-              if (!rev) { m0 = mask_at(p0); m1 = mask_at(p0 + 1); m2 = mask_at(p0 + 2); }
-              else { m0 = comp_mask(mask_at(L - 1 - p0)); m1 = comp_mask(mask_at(L - 2 - p0)); m2 = comp_mask(mask_at(L - 3 - p0)); }
-              code = codon_code(m0, m1, m2, s_tab);
-            }
-          }
-          word |= (uint32_t)code << (8 * q);
+    // frame geometry (warp-uniform): frame offset j has (L-j)/3 residues, frames are 4-byte padded
+    const int n0 = L >= 3 ? L / 3 : 0, n1 = L >= 4 ? (L - 1) / 3 : 0, n2 = L >= 5 ? (L - 2) / 3 : 0;
+    const int p0 = (n0 + 3) & ~3, p1 = (n1 + 3) & ~3, p2 = (n2 + 3) & ~3;
+    const int fb1 = p0, fb2 = p0 + p1;
+    const int rb0 = NFWD == 3 ? p0 + p1 + p2 : p0, rb1 = rb0 + p0, rb2 = rb1 + p1;
+    const int tot = rb0 + (NREV == 3 ? p0 + p1 + p2 : 0);
+    const uint32_t pos = target_base(o, r);
+    __syncwarp();
+    // the last word of every frame carries the zero padding
+    if (lane < NFR) {
+      const int j = lane < NFWD ? lane : lane - NFWD;
+      const int b = lane < NFWD ? (j == 0 ? 0 : j == 1 ? fb1 : fb2) : (j == 0 ? rb0 : j == 1 ? rb1 : rb2);
+      const int pj = j == 0 ? p0 : j == 1 ? p1 : p2;
+      if (pj) *reinterpret_cast<uint32_t *>(so + b + pj - 4) = 0u;
+    }
+    __syncwarp();
+    const int npos = L - 2;  // triplet start positions
+    int cur = lane < L ? (int)s_nt[(uint8_t)nt[o + lane]] : 4;
+    for (int q0 = 0; q0 < npos; q0 += 32) {
+      const int i1 = q0 + 32 + lane;
+      const int nxt = i1 < L ? (int)s_nt[(uint8_t)nt[o + i1]] : 4;
+      const int a1 = __shfl_sync(PA_FULL, cur, (lane + 1) & 31), b1 = __shfl_sync(PA_FULL, nxt, (lane + 1) & 31);
+      const int a2 = __shfl_sync(PA_FULL, cur, (lane + 2) & 31), b2 = __shfl_sync(PA_FULL, nxt, (lane + 2) & 31);
+      const int c1 = lane < 31 ? a1 : b1, c2 = lane < 30 ? a2 : b2;
+      const int q = q0 + lane;
+      if (q < npos) {
+        int aaF, aaR;
+        if (((cur | c1 | c2) & 4) == 0) {
+          const int f = (cur & 3) * 16 + (c1 & 3) * 4 + (c2 & 3);
+          aaF = s_tabF[f];
+          aaR = s_tabR[f];
+        } else {
+          if ((cur | c1 | c2) & 8) atomicExch(err, 1);
+          const int both = translate_ambiguous(cur >> 4, c1 >> 4, c2 >> 4, s_tab);
+          aaF = both & 0xff;
+          aaR = both >> 8;
         }
-        *reinterpret_cast<uint32_t *>(out + pos + 4 * w) = word;
+        const int cf = (q * 43691) >> 17, jf = q - 3 * cf;  // q / 3, q % 3 (q < 32768)
+        if (jf < NFWD) so[(jf == 0 ? 0 : jf == 1 ? fb1 : fb2) + cf] = (uint8_t)aaF;
+        if (NREV) {
+          const int qr = npos - 1 - q;
+          const int cr = (qr * 43691) >> 17, jr = qr - 3 * cr;
+          so[(jr == 0 ? rb0 : jr == 1 ? rb1 : rb2) + cr] = (uint8_t)aaR;
+        }
       }
-      if (lane == 0) { tgt_off[(size_t)r * nframes + f] = pos; tgt_len[(size_t)r * nframes + f] = nres; }
-      pos += (nres + 3) & ~3;
+      cur = nxt;
+    }
+    __syncwarp();
+    const uint32_t *so4 = reinterpret_cast<const uint32_t *>(so);
+    uint32_t *dst = reinterpret_cast<uint32_t *>(out + pos);
+    for (int w = lane; w < (tot >> 2); w += 32) dst[w] = so4[w];
+    if (lane < NFR) {
+      const int j = lane < NFWD ? lane : lane - NFWD;
+      const int b = lane < NFWD ? (j == 0 ? 0 : j == 1 ? fb1 : fb2) : (j == 0 ? rb0 : j == 1 ? rb1 : rb2);
+      tgt_off[(size_t)r * NFR + lane] = pos + b;
+      tgt_len[(size_t)r * NFR + lane] = (j == 0 ? n0 : j == 1 ? n1 : n2);
     }
   }
 }
