@@ -49,7 +49,7 @@ def test_invalid_nucleotide_is_an_error(gpu_ctx_factory):
     ctx.close()
 
 
-@pytest.mark.parametrize("M", [1, 3, 33, 64, 65, 130, 257, 450, 700])
+@pytest.mark.parametrize("M", [1, 3, 33, 64, 65, 130, 257, 450, 700, 1023, 1100, 2047])
 def test_raw_filter_scores_bit_exact(oracle, gpu_ctx_factory, M):
     rng = np.random.default_rng(100 + M)
     h = helpers.calibrated_hmm(f"syn{M}", M, seed=M)

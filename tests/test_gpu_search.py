@@ -115,3 +115,91 @@ def test_max_mode_and_nobias(oracle, gpu_ctx_factory):
         hits, model, aligned = ctx.search()
         compare_hits(oracle, hmms, seqs, hits, model, aligned, opts=oracle.default_opts(**ok))
         ctx.close()
+
+
+def test_nucleotide_mode_dna_profiles(oracle, gpu_ctx_factory):
+    """Config 3 shape: DNA-alphabet profiles against nucleotide targets (read + its reverse complement)."""
+    from phyloaln_b200 import hmmbuild_lite as hb, synth
+    rng = np.random.default_rng(31)
+    hmms = [helpers.calibrated_hmm(f"d{i}", M, seed=300 + i, bg_mix=0.1, abc="dna") for i, M in enumerate([90, 240, 700])]
+    reads = []
+    for i in range(600):
+        L = int(rng.integers(60, 200))
+        s = hb.random_sequences("dna", 1, L, rng)[0]
+        if i % 4 == 0:
+            h = hmms[int(rng.integers(len(hmms)))]
+            flen = min(h.M, L - 5)
+            a = int(rng.integers(1, h.M - flen + 2))
+            frag = synth.sample_protein(h, rng, a, a + flen - 1)
+            pos = int(rng.integers(0, L - flen + 1))
+            s = s[:pos] + frag + s[pos + flen:]
+            if i % 8 == 0:
+                s = oracle.revcomp(s)
+        if i % 50 == 0:
+            s = s[:10] + "NRY" + s[13:]
+        reads.append(s)
+    targets = []
+    for r in reads:
+        targets += [r, oracle.revcomp(r)]
+    ctx = gpu_ctx_factory()
+    for h in hmms:
+        ctx.add_hmm(h)
+    ctx.commit()
+    assert ctx.load_read_list(reads, moltype=1) == len(targets)
+    assert ctx.get_targets(len(targets), sum(map(len, targets))) == [t.upper() for t in targets]
+    hits, model, aligned = ctx.search()
+    n = compare_hits(oracle, hmms, targets, hits, model, aligned)
+    assert n > 40
+    # forward-only variant (-n / no_reverse)
+    assert ctx.load_read_list(reads, moltype=1, no_reverse=True) == len(reads)
+    hits, model, aligned = ctx.search()
+    assert compare_hits(oracle, hmms, reads, hits, model, aligned) > 20
+    ctx.close()
+
+
+def test_codon_mode_first_frame_only(oracle, gpu_ctx_factory):
+    """--codon: only frame 1 of the forward strand is translated (lib/aln.py:249-253, main.py:196-198)."""
+    from phyloaln_b200 import synth
+    rng = np.random.default_rng(12)
+    hmms = [helpers.calibrated_hmm(f"c{i}", M, seed=70 + i, bg_mix=0.1) for i, M in enumerate([60, 120])]
+    reads = synth.random_reads(1500, 150, rng)
+    synth.plant_reads(reads, hmms, 0.2, rng, sub_rate=0.02)
+    rl = [r.tobytes().decode() for r in reads]
+    frames = [p for r in rl for _, p in oracle.six_frames(r, 11, no_reverse=True, codon=True)]
+    assert len(frames) == len(rl)
+    ctx = gpu_ctx_factory()
+    for h in hmms:
+        ctx.add_hmm(h)
+    ctx.commit()
+    assert ctx.load_read_list(rl, moltype=0, gencode=11, no_reverse=True, codon_only=True) == len(frames)
+    hits, model, aligned = ctx.search()
+    assert compare_hits(oracle, hmms, frames, hits, model, aligned) > 10
+    ctx.close()
+
+
+def test_search_very_long_targets_and_profiles(oracle, gpu_ctx_factory):
+    """Config 4 extremes: targets up to 1,700 aa, profiles beyond 1,024 columns (hybrid TMEM + smem MSV)."""
+    from phyloaln_b200 import hmmbuild_lite as hb, synth
+    rng = np.random.default_rng(8)
+    hmms = [helpers.calibrated_hmm(f"V{i}", M, seed=140 + i, bg_mix=0.15, n=30) for i, M in enumerate([420, 1100, 1500])]
+    seqs = []
+    for i in range(60):
+        L = int(rng.integers(166, 1700))
+        s = hb.random_sequences("amino", 1, L, rng)[0]
+        if i % 2 == 0:
+            h = hmms[int(rng.integers(len(hmms)))]
+            a = int(rng.integers(1, h.M // 2))
+            b = int(rng.integers(a + 40, min(h.M, a + 400) + 1))
+            frag = synth.sample_protein(h, rng, a, b)
+            if len(frag) < L:
+                pos = int(rng.integers(0, L - len(frag)))
+                s = s[:pos] + frag + s[pos + len(frag):]
+        seqs.append(s)
+    ctx = gpu_ctx_factory()
+    for h in hmms:
+        ctx.add_hmm(h)
+    ctx.commit()
+    ctx.load_proteins(seqs)
+    hits, model, aligned = ctx.search()
+    assert compare_hits(oracle, hmms, seqs, hits, model, aligned) > 15
+    ctx.close()
