@@ -170,6 +170,7 @@ def main():
     ap.add_argument("--hmms", type=int, default=1000)
     ap.add_argument("--reads-per-step", type=int, default=131072)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-region", action="store_true", help="cudaProfilerStart/Stop around the timed resident steps (ncu --profile-from-start off)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -237,6 +238,8 @@ def main():
     launches_timed = 0
     for s in range(nsteps):
         l0 = ctx.stats()["kernel_launches"]
+        if args.profile_region and s == args.warmup:
+            capi.profiler_range(True)
         ctx.load_reads(chunks[s].reshape(-1), offs)            # reads resident after this call
         tr_ms = ctx.stats()["ms_translate"]
         barrier()
@@ -248,6 +251,8 @@ def main():
             times.append(dt)
             stats_acc.append(ctx.stats())
             launches_timed += stats_acc[-1]["kernel_launches"] - l0
+    if args.profile_region:
+        capi.profiler_range(False)
     # ---------------- end-to-end pass: host buffers in, hit records out ----------------
     e2e_times, d2h = [], 0
     for s in range(nsteps):

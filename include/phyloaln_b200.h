@@ -134,6 +134,10 @@ int pa_score_all(pa_ctx *ctx, int hmm, float *msv, int32_t *msv_raw, float *vit,
  * VIMNMX3.S16x2 per 16 cells). Result in giga thread-instructions per second over the whole GPU. */
 int pa_microbench_dpx(pa_ctx *ctx, int mode, double *ginstr_per_s);
 
+/* cudaProfilerStart / cudaProfilerStop (on != 0 / on == 0): lets `ncu --profile-from-start off` capture
+ * only the timed region of bench.py. No reference equivalent. */
+int pa_profiler_range(int on);
+
 /* Hit -> reference-column mapping (extend_pos = 0). For hit h: model/aligned strings (PhyloAln
  * form: upper case, '-' for gaps) at ali_off[h]..ali_off[h+1]; raw read nucleotides at
  * read_off[h]..; hmm_from/to, ali_from/to 1-based; frame 0..2 or -1 (nucleotide mode);

@@ -50,7 +50,8 @@ MAPREC_DTYPE = np.dtype(PaMapRec)
 
 EXPORTS = ["pa_abi_version", "pa_create", "pa_destroy", "pa_last_error", "pa_set_opts", "pa_add_hmm", "pa_set_evparam",
            "pa_commit_hmms", "pa_num_hmms", "pa_load_reads", "pa_load_proteins", "pa_num_frames", "pa_get_targets",
-           "pa_search", "pa_get_hits", "pa_hit_pool_bytes", "pa_get_stats", "pa_score_all", "pa_map_hits", "pa_microbench_dpx"]
+           "pa_search", "pa_get_hits", "pa_hit_pool_bytes", "pa_get_stats", "pa_score_all", "pa_map_hits", "pa_microbench_dpx",
+           "pa_profiler_range"]
 
 _lib = None
 
@@ -93,8 +94,14 @@ def load_library():
     L.pa_score_all.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp]
     L.pa_map_hits.argtypes = [vp, C.c_int32, C.c_char_p, C.c_char_p, vp, C.c_char_p] + [vp] * 10 + [i32, C.c_double, vp, vp, vp, vp, i64, i64]
     L.pa_microbench_dpx.argtypes = [vp, i32, C.POINTER(C.c_double)]
+    L.pa_profiler_range.argtypes = [i32]
     _lib = L
     return L
+
+
+def profiler_range(on: bool) -> None:
+    """cudaProfilerStart/Stop, for `ncu --profile-from-start off`."""
+    load_library().pa_profiler_range(1 if on else 0)
 
 
 class PaError(RuntimeError):

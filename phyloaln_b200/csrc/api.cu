@@ -7,6 +7,7 @@
 //   Pass2 list -> fwd_kernel -> Pass4 list -> domain_kernel -> domain records -> host scoring.
 // Lists are compacted with atomics between stages; capacity overflow is reported as an error
 // (-3) so the caller can shrink the chunk -- there is no CPU fallback anywhere.
+#include <cuda_profiler_api.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -139,6 +140,8 @@ static LenTabs make_lentabs(pa_ctx *ctx) {
 }
 
 extern "C" int pa_abi_version(void) { return PA_ABI_VERSION; }
+
+extern "C" int pa_profiler_range(int on) { return (on ? cudaProfilerStart() : cudaProfilerStop()) == cudaSuccess ? 0 : -1; }
 
 extern "C" pa_ctx *pa_create(int device, char *err, int errlen) {
   auto fail = [&](const char *what, cudaError_t e) -> pa_ctx * {
