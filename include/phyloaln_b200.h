@@ -152,6 +152,27 @@ int pa_map_hits(pa_ctx *ctx, int32_t nhits, const char *model, const char *align
                 double pos_freq, pa_maprec *rec, char *base_pool, char *codon_pool, int32_t *unmap_pool,
                 int64_t pool_cols_cap, int64_t unmap_cap);
 
+/* ---- native target preparation (host only; replaces the body of prepare_target(), lib/aln.py:274-433,
+ * and the text iteration of read_fastx(return_iter=True), lib/library.py:157-176).  Files are inflated and
+ * parsed in parallel; tagging, sliding-window splitting, exact-duplicate merging and the 10 MB chunk order are
+ * reproduced byte for byte (all.raw.fasta, total_counts.tsv, merged_redundance.txt). ---- */
+typedef struct pa_ingest pa_ingest;
+pa_ingest *pa_ingest_create(int merge_len, int split_len /* 0 = off */, int split_slide /* 0 = split_len/2 */, int nthreads);
+void pa_ingest_destroy(pa_ingest *ing);
+const char *pa_ingest_last_error(pa_ingest *ing);
+/* files in the order of the reference's loops: for species, for file j (file_index = j + 1); format guess|fastq|fasta */
+int pa_ingest_add_file(pa_ingest *ing, const char *path, const char *species, int file_index, const char *format);
+int pa_ingest_run(pa_ingest *ing);
+int64_t pa_ingest_num_records(pa_ingest *ing);
+/* borrowed views, valid until pa_ingest_destroy: the all.raw.fasta text, its record table (offsets/lengths of ids and
+ * sequences), the total_counts.tsv and merged_redundance.txt texts. Any pointer may be NULL. */
+int pa_ingest_views(pa_ingest *ing, const char **raw, uint64_t *raw_len, const uint64_t **id_off, const uint64_t **id_len,
+                    const uint64_t **seq_off, const uint64_t **seq_len, const char **counts, uint64_t *counts_len,
+                    const char **merged, uint64_t *merged_len);
+int pa_ingest_write(pa_ingest *ing, const char *raw_fasta, const char *total_counts, const char *merged_redundance);
+/* sequences [first, first+count) concatenated + offsets (count+1), ready for pa_load_reads */
+int64_t pa_ingest_pack(pa_ingest *ing, uint64_t first, uint64_t count, char *nt_out, uint64_t cap, uint64_t *off_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -7,5 +7,5 @@ NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 OUT=../libphyloaln_b200.so
 $NVCC -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -fmad=false \
   -Xcompiler -fPIC,-ffp-contract=off,-fno-fast-math,-O2 -shared \
-  -o $OUT api.cu profile.cpp "$@"
+  -o $OUT api.cu profile.cpp ingest.cpp -lz "$@"
 echo "built $OUT"

@@ -44,9 +44,41 @@ def read_raw_fasta(path: str):
     return ids, nt, off
 
 
+def prepare_target_step(outdir: str, rawdata: dict, args):
+    """Drop-in for ``prepare_target(rawdata, args)`` (lib/main.py:237 -> lib/aln.py:274-457) when the search
+    runs on the GPU: the native ingest writes ``all.raw.fasta``, ``total_counts.tsv`` and
+    ``merged_redundance.txt`` byte-identically to the reference; translation (raw2target) is not run on the
+    host at all -- it is fused into the GPU search -- so ``all.target.fasta`` is left as an empty placeholder
+    for the reference's final clean-up (lib/aln.py:892-895).  Touches ``ok/prepare_target.ok`` so the unchanged
+    ``prepare_target`` skips (lib/aln.py:277).  Returns the live :class:`ingest.Ingest` for ``hmmsearch_step``."""
+    from . import ingest
+    os.makedirs(os.path.join(outdir, "ok"), exist_ok=True)
+    ing = ingest.prepare_target(rawdata, args, outdir=outdir)
+    open(os.path.join(outdir, "all.target.fasta"), "w").close()
+    open(os.path.join(outdir, "ok", "prepare_target.ok"), "w").close()
+    return ing
+
+
+def reads_from_ingest(ing):
+    """(ids, nt, off) with read_raw_fasta's dictionary semantics, straight from the ingest's record table."""
+    ids = ing.ids()
+    nt, off = ing.pack()
+    if len(set(ids)) == len(ids):
+        return ids, nt, off
+    last = {}
+    for k, name in enumerate(ids):
+        last[name] = k                     # the LAST record of an id wins, at the id's first position
+    keep = list(last)                      # dict order = first appearance
+    raw = nt.tobytes()
+    seqs = [raw[int(off[last[n]]):int(off[last[n] + 1])] for n in keep]
+    off2 = np.zeros(len(keep) + 1, dtype=np.uint64)
+    off2[1:] = np.cumsum([len(x) for x in seqs])
+    return keep, np.frombuffer(b"".join(seqs) or b"\0", dtype=np.uint8), off2
+
+
 def hmmsearch_step(outdir: str, groups, mol_type: str = "prot", gencode: int = 1, no_reverse: bool = False,
                    codon: bool = False, hmmsearch_parameters=(), devices=(0,), raw_fasta: str | None = None,
-                   write_tbl: bool = True):
+                   write_tbl: bool = True, ingest=None):
     """Batched replacement of ``for g in groups: hmmsearch g.hmm all.target.fasta; extract_reads(g)``.
 
     Returns {g: number of hit_info rows}.  Raises on any failure (the reference returns (1, g) per
@@ -59,8 +91,11 @@ def hmmsearch_step(outdir: str, groups, mol_type: str = "prot", gencode: int = 1
     if not todo:
         return counts
     hmms = [read_hmm(os.path.join(outdir, "ref_hmm", g + ".hmm")) for g in todo]
-    raw_fasta = raw_fasta or os.path.join(outdir, "all.raw.fasta")
-    ids, nt, off = read_raw_fasta(raw_fasta)
+    if ingest is not None:
+        ids, nt, off = reads_from_ingest(ingest)
+    else:
+        raw_fasta = raw_fasta or os.path.join(outdir, "all.raw.fasta")
+        ids, nt, off = read_raw_fasta(raw_fasta)
     # '--codon' forces no_reverse in the reference (lib/main.py:196-198)
     if codon:
         no_reverse = True

@@ -1,0 +1,128 @@
+"""Native target preparation -- the host mirror of the reference's ``prepare_target``
+(/root/reference/lib/aln.py:274-433): FASTQ/FASTA(.gz) -> tagged, de-duplicated ``all.raw.fasta`` +
+``total_counts.tsv`` + ``merged_redundance.txt``, byte-identical to the reference's files.
+
+The work is done by ``pa_ingest_*`` in libphyloaln_b200.so (csrc/ingest.cpp: one inflate/parse thread per
+input file, then the reference's order-dependent single pass).  ``Ingest.pack`` hands contiguous read
+chunks straight to ``Context.load_reads`` so the GPU search never re-parses the FASTA text.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import capi
+
+
+def _lib():
+    L = capi.load_library()
+    if not getattr(L, "_ingest_ready", False):
+        vp, i32, i64, u64 = C.c_void_p, C.c_int, C.c_int64, C.c_uint64
+        L.pa_ingest_create.restype = vp
+        L.pa_ingest_create.argtypes = [i32, i32, i32, i32]
+        L.pa_ingest_destroy.argtypes = [vp]
+        L.pa_ingest_last_error.restype = C.c_char_p
+        L.pa_ingest_last_error.argtypes = [vp]
+        L.pa_ingest_add_file.argtypes = [vp, C.c_char_p, C.c_char_p, i32, C.c_char_p]
+        L.pa_ingest_run.argtypes = [vp]
+        L.pa_ingest_num_records.restype = i64
+        L.pa_ingest_num_records.argtypes = [vp]
+        L.pa_ingest_views.argtypes = [vp] + [vp] * 10
+        L.pa_ingest_write.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_char_p]
+        L.pa_ingest_pack.restype = i64
+        L.pa_ingest_pack.argtypes = [vp, u64, u64, vp, u64, vp]
+        L._ingest_ready = True
+    return L
+
+
+class Ingest:
+    """rawdata: {species: [files]} in the reference's iteration order (dict order, lib/aln.py:287-289)."""
+
+    def __init__(self, rawdata: dict, merge_len: int = 250, split_len: int | None = None, split_slide: int | None = None,
+                 file_format: str = "guess", threads: int | None = None):
+        self.L = _lib()
+        if split_len is not None and split_slide is None:
+            split_slide = int(split_len / 2)          # lib/main.py:207-208
+        self.h = self.L.pa_ingest_create(int(merge_len), int(split_len or 0), int(split_slide or 0),
+                                         int(threads or os.cpu_count() or 1))
+        for sp, files in rawdata.items():
+            for j, f in enumerate(files):
+                self._check(self.L.pa_ingest_add_file(self.h, os.fspath(f).encode(), sp.encode(), j + 1, file_format.encode()))
+        self._check(self.L.pa_ingest_run(self.h))
+        self.n = int(self.L.pa_ingest_num_records(self.h))
+
+    def _check(self, rc):
+        if rc < 0:
+            raise capi.PaError(f"ingest failed ({rc}): {self.L.pa_ingest_last_error(self.h).decode()}")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.pa_ingest_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _views(self):
+        raw, cnt, mrg = C.c_char_p(), C.c_char_p(), C.c_char_p()
+        rl, cl, ml = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        ptrs = [C.POINTER(C.c_uint64)() for _ in range(4)]
+        raw_p, cnt_p, mrg_p = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        self._check(self.L.pa_ingest_views(self.h, C.byref(raw_p), C.byref(rl), C.byref(ptrs[0]), C.byref(ptrs[1]),
+                                           C.byref(ptrs[2]), C.byref(ptrs[3]), C.byref(cnt_p), C.byref(cl), C.byref(mrg_p),
+                                           C.byref(ml)))
+        del raw, cnt, mrg
+        return raw_p, rl.value, ptrs, cnt_p, cl.value, mrg_p, ml.value
+
+    def raw_fasta(self) -> bytes:
+        raw_p, rl, *_ = self._views()
+        return C.string_at(raw_p, rl) if rl else b""
+
+    def total_counts(self) -> str:
+        _, _, _, cnt_p, cl, _, _ = self._views()
+        return C.string_at(cnt_p, cl).decode() if cl else ""
+
+    def merged_redundance(self) -> str:
+        *_, mrg_p, ml = self._views()
+        return C.string_at(mrg_p, ml).decode() if ml else ""
+
+    def ids(self) -> list[str]:
+        raw_p, rl, ptrs, *_ = self._views()
+        raw = C.string_at(raw_p, rl) if rl else b""
+        io = np.ctypeslib.as_array(ptrs[0], shape=(self.n,)) if self.n else np.zeros(0, np.uint64)
+        il = np.ctypeslib.as_array(ptrs[1], shape=(self.n,)) if self.n else np.zeros(0, np.uint64)
+        return [raw[int(o):int(o + l)].decode() for o, l in zip(io, il)]
+
+    def seq_lengths(self) -> np.ndarray:
+        _, _, ptrs, *_ = self._views()
+        return np.ctypeslib.as_array(ptrs[3], shape=(self.n,)).copy() if self.n else np.zeros(0, np.uint64)
+
+    def pack(self, first: int = 0, count: int | None = None):
+        """(nt uint8[], off uint64[count+1]) of records [first, first+count) for ``Context.load_reads``."""
+        count = self.n - first if count is None else count
+        cap = int(self.seq_lengths()[first:first + count].sum()) + 1
+        nt = np.zeros(cap, dtype=np.uint8)
+        off = np.zeros(count + 1, dtype=np.uint64)
+        got = self.L.pa_ingest_pack(self.h, first, count, nt.ctypes.data, cap, off.ctypes.data)
+        self._check(got)
+        return nt[:max(int(got), 1)], off
+
+    def write(self, outdir: str = "."):
+        """all.raw.fasta, total_counts.tsv, merged_redundance.txt exactly where the reference puts them."""
+        self._check(self.L.pa_ingest_write(self.h, os.path.join(outdir, "all.raw.fasta").encode(),
+                                           os.path.join(outdir, "total_counts.tsv").encode(),
+                                           os.path.join(outdir, "merged_redundance.txt").encode()))
+
+
+def prepare_target(rawdata: dict, args, outdir: str = ".") -> Ingest:
+    """Drop-in for the ingest half of the reference's prepare_target(rawdata, args): same arguments
+    (args.file_format, args.split_len, args.split_slide, args.merge_len, args.cpu), same three files."""
+    ing = Ingest(rawdata, merge_len=args.merge_len, split_len=args.split_len, split_slide=args.split_slide,
+                 file_format=args.file_format, threads=getattr(args, "cpu", None))
+    ing.write(outdir)
+    return ing

@@ -44,6 +44,27 @@ def test_config1_dropin_outputs_identical_to_golden(tmp_path):
     assert dropin.hmmsearch_step(str(out), GROUPS, mol_type="codon") == {}
 
 
+def test_config1_from_fastq_through_native_ingest(tmp_path):
+    """fq.gz -> native ingest -> GPU search: same hit_info files as the golden run that started from the
+    reference's all.raw.fasta."""
+    from argparse import Namespace
+    from phyloaln_b200 import dropin
+    out = tmp_path / "run"
+    (out / "ref_hmm").mkdir(parents=True)
+    for g in GROUPS:
+        shutil.copy(os.path.join(C1, "ref_hmm", g + ".hmm"), out / "ref_hmm" / (g + ".hmm"))
+    rd = os.path.join(C1, "reads")
+    rawdata = {"DMELA": [os.path.join(rd, "DMELA_1.fq.gz"), os.path.join(rd, "DMELA_2.fq.gz")],
+               "DWILL": [os.path.join(rd, "DWILL_1.fq.gz"), os.path.join(rd, "DWILL_2.fq.gz")]}
+    args = Namespace(file_format="guess", split_len=None, split_slide=None, merge_len=250, cpu=4)
+    ing = dropin.prepare_target_step(str(out), rawdata, args)
+    assert open(out / "total_counts.tsv").read() == open(os.path.join(C1, "total_counts.tsv")).read()
+    assert os.path.isfile(out / "ok" / "prepare_target.ok")
+    dropin.hmmsearch_step(str(out), GROUPS, mol_type="codon", gencode=1, ingest=ing)
+    for g in GROUPS:
+        assert open(out / "map" / (g + ".hit_info.tsv")).read() == open(os.path.join(C1, "hit_info", g + ".hit_info.tsv")).read(), g
+
+
 def test_config1_scores_within_tolerance(gpu_ctx_factory):
     from phyloaln_b200 import dropin, hmmio, search
     ids, nt, off = dropin.read_raw_fasta(os.path.join(C1, "all.raw.fasta.gz"))
