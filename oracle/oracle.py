@@ -19,7 +19,7 @@ _LIB = None
 class OrcOpts(C.Structure):
     _fields_ = [("F1", C.c_double), ("F2", C.c_double), ("F3", C.c_double), ("E", C.c_double),
                 ("domE", C.c_double), ("do_bias", C.c_int), ("do_null2", C.c_int), ("do_max", C.c_int),
-                ("Z", C.c_double), ("domZ", C.c_double)]
+                ("Z", C.c_double), ("domZ", C.c_double), ("simd_msv", C.c_int), ("reserved", C.c_int)]
 
 
 class OrcHit(C.Structure):
@@ -66,7 +66,7 @@ def lib():
         L.orc_digitize.argtypes = [C.c_int, C.c_char_p, C.c_int, C.c_void_p]
         L.orc_null1.restype = C.c_float
         L.orc_null1.argtypes = [C.c_int]
-        for f in (L.orc_msv, L.orc_vit):
+        for f in (L.orc_msv, L.orc_vit, L.orc_msv_simd):
             f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int)]
         L.orc_bias_filtersc.restype = C.c_float
         L.orc_bias_filtersc.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
@@ -103,7 +103,7 @@ DNA_SYMS = "ACGT-RYMKSWHBVDN*~"
 
 
 def default_opts(**kw) -> OrcOpts:
-    o = OrcOpts(0.02, 1e-3, 1e-5, 10.0, 10.0, 1, 1, 0, 0.0, 0.0)
+    o = OrcOpts(0.02, 1e-3, 1e-5, 10.0, 10.0, 1, 1, 0, 0.0, 0.0, 0, 0)
     for k, v in kw.items():
         setattr(o, k, v)
     return o
@@ -160,6 +160,13 @@ class Profile:
         sc, raw = C.c_float(), C.c_int()
         self.L.orc_msv(self.p, d.ctypes.data, len(seq), C.byref(sc), C.byref(raw))
         return sc.value, raw.value
+
+    def msv_simd(self, seq: str):
+        """(score, raw xJ) from the striped AVX2 filter, or None without AVX2."""
+        d = self.digitize(seq)
+        sc, raw = C.c_float(), C.c_int()
+        rc = self.L.orc_msv_simd(self.p, d.ctypes.data, len(seq), C.byref(sc), C.byref(raw))
+        return None if rc < 0 else (sc.value, raw.value)
 
     def vit(self, seq: str):
         d = self.digitize(seq)
@@ -218,8 +225,9 @@ class Profile:
         for i in range(nh):
             h = hits[i]
             d = {f: getattr(h, f) for f, _ in OrcHit._fields_}
-            d["model"] = mp.raw[h.ali_off:h.ali_off + h.ali_len].decode()
-            d["aligned"] = tp.raw[h.ali_off:h.ali_off + h.ali_len].decode()
+            # string_at copies just the slice; `.raw` would copy the whole pool for every hit
+            d["model"] = C.string_at(C.addressof(mp) + h.ali_off, h.ali_len).decode()
+            d["aligned"] = C.string_at(C.addressof(tp) + h.ali_off, h.ali_len).decode()
             out.append(d)
         trace = None
         if want_trace:

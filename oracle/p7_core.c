@@ -304,6 +304,8 @@ ORC_PROFILE *orc_profile_create(const ORC_HMM *h) {
   p->tsc = (float *)malloc(sizeof(float) * (M + 1) * 8);
   p->msc = (float *)malloc(sizeof(float) * Kp * (M + 1));
   p->rbv = (uint8_t *)malloc((size_t)Kp * (M + 1));
+  p->Qb = (M + 31) / 32;
+  p->rbv_s = NULL;
   p->rwv = (int16_t *)malloc(sizeof(int16_t) * Kp * (M + 1));
   p->twv = (int16_t *)malloc(sizeof(int16_t) * (M + 1) * 8);
   p->rfv = (float *)malloc(sizeof(float) * Kp * (M + 1));
@@ -364,6 +366,13 @@ ORC_PROFILE *orc_profile_create(const ORC_HMM *h) {
   }
   p->tbm_b = unbiased_byteify(p->scale_b, logf(2.0f / ((float)M * (float)(M + 1))));
   p->tec_b = unbiased_byteify(p->scale_b, logf(0.5f));
+  /* striped copy for orc_msv_simd: cell k -> vector (k-1) % Qb, byte lane (k-1) / Qb; padding costs 255 */
+  if (posix_memalign((void **)&p->rbv_s, 32, (size_t)Kp * p->Qb * 32) != 0) p->rbv_s = NULL;
+  if (p->rbv_s) {
+    memset(p->rbv_s, 255, (size_t)Kp * p->Qb * 32);
+    for (int x = 0; x < Kp; x++)
+      for (int k = 1; k <= M; k++) p->rbv_s[((size_t)x * p->Qb + (k - 1) % p->Qb) * 32 + (k - 1) / p->Qb] = p->rbv[x * (M + 1) + k];
+  }
 
   /* Viterbi words (A.5) */
   p->scale_w = (float)(500.0 / 0.69314718055994529);
@@ -390,6 +399,7 @@ void orc_profile_free(ORC_PROFILE *p) {
   free(p->tsc);
   free(p->msc);
   free(p->rbv);
+  free(p->rbv_s);
   free(p->rwv);
   free(p->twv);
   free(p->rfv);

@@ -54,6 +54,73 @@ int orc_msv(const ORC_PROFILE *p, const uint8_t *dsq, int L, float *ret_sc, int 
   return 0;
 }
 
+/* ---------------- MSV, striped AVX2 (the way HMMER's own filter is vectorised) ----------------
+ * Farrar striping over 32 unsigned-byte lanes; saturating adds/subs are the hardware's.  Same
+ * recurrence as orc_msv above, hence the same xJ byte and score: integer arithmetic is order-free.
+ * This is what bench.py times as the host-core baseline. */
+#if defined(__x86_64__)
+#include <immintrin.h>
+int orc_have_avx2(void) { return __builtin_cpu_supports("avx2") ? 1 : 0; }
+
+__attribute__((target("avx2"))) int orc_msv_simd(const ORC_PROFILE *p, const uint8_t *dsq, int L, float *ret_sc, int *xJ_raw) {
+  if (!p->rbv_s || !orc_have_avx2()) return -1;
+  const int Q = p->Qb;
+  uint8_t tjb = p7i_unbiased_byteify(p->scale_b, logf(3.0f / (float)(L + 3)));
+  int tjbm = (uint8_t)((int8_t)tjb + (int8_t)p->tbm_b);
+  int bias = p->bias_b, base = p->base_b, tec = p->tec_b;
+  __m256i dpbuf[64];
+  __m256i *dp = Q <= 64 ? dpbuf : (__m256i *)aligned_alloc(32, (size_t)Q * 32);
+  for (int q = 0; q < Q; q++) dp[q] = _mm256_setzero_si256();
+  const __m256i biasv = _mm256_set1_epi8((char)bias);
+  int xJ = 0, xB = sat_subu8(base, tjbm);
+  int overflow = 0;
+  for (int i = 1; i <= L; i++) {
+    const __m256i *rsc = (const __m256i *)(p->rbv_s + (size_t)dsq[i] * Q * 32);
+    const __m256i xBv = _mm256_set1_epi8((char)xB);
+    __m256i xEv = _mm256_setzero_si256();
+    /* previous row's last vector, shifted up one byte lane (lane 0 gets 0 = -inf) */
+    __m256i last = dp[Q - 1];
+    __m256i mpv = _mm256_alignr_epi8(last, _mm256_permute2x128_si256(last, last, 0x08), 15);
+    for (int q = 0; q < Q; q++) {
+      __m256i sv = _mm256_max_epu8(mpv, xBv);
+      sv = _mm256_adds_epu8(sv, biasv);
+      sv = _mm256_subs_epu8(sv, _mm256_load_si256(rsc + q));
+      xEv = _mm256_max_epu8(xEv, sv);
+      mpv = dp[q];
+      dp[q] = sv;
+    }
+    __m128i m = _mm_max_epu8(_mm256_castsi256_si128(xEv), _mm256_extracti128_si256(xEv, 1));
+    m = _mm_max_epu8(m, _mm_srli_si128(m, 8));
+    m = _mm_max_epu8(m, _mm_srli_si128(m, 4));
+    m = _mm_max_epu8(m, _mm_srli_si128(m, 2));
+    m = _mm_max_epu8(m, _mm_srli_si128(m, 1));
+    int xE = _mm_cvtsi128_si32(m) & 0xff;
+    if (sat_addu8(xE, bias) == 255) { overflow = 1; break; }
+    xE = sat_subu8(xE, tec);
+    if (xE > xJ) xJ = xE;
+    xB = sat_subu8(base > xJ ? base : xJ, tjbm);
+  }
+  if (dp != dpbuf) free(dp);
+  if (overflow) {
+    *ret_sc = INFINITY;
+    if (xJ_raw) *xJ_raw = -1;
+    return 1;
+  }
+  if (xJ_raw) *xJ_raw = xJ;
+  float sc = ((float)(xJ - tjb) - (float)base);
+  sc /= p->scale_b;
+  sc -= 3.0f;
+  *ret_sc = sc;
+  return 0;
+}
+#else
+int orc_have_avx2(void) { return 0; }
+int orc_msv_simd(const ORC_PROFILE *p, const uint8_t *dsq, int L, float *ret_sc, int *xJ_raw) {
+  (void)p; (void)dsq; (void)L; (void)ret_sc; (void)xJ_raw;
+  return -1;
+}
+#endif
+
 /* ---------------- Viterbi filter: signed saturating words ---------------- */
 static inline int sat_adds16(int a, int b) {
   int s = a + b;

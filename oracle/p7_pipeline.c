@@ -46,7 +46,7 @@ static int one_target(const ORC_PROFILE *p, const uint8_t *seq, int L, int tidx,
   float nullsc = orc_null1(L), usc, filtersc, vfsc = 0, fwdsc = 0, seq_score;
   double P;
   t.nullsc = nullsc;
-  orc_msv(p, dsq, L, &usc, &t.msv_xJ);
+  if (o->simd_msv == 0 || orc_msv_simd(p, dsq, L, &usc, &t.msv_xJ) < 0) orc_msv(p, dsq, L, &usc, &t.msv_xJ);
   t.usc = usc;
   seq_score = (float)((usc - nullsc) / LN2);
   P = orc_gumbel_surv(seq_score, ev[0], ev[1]);

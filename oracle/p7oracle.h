@@ -62,6 +62,8 @@ typedef struct {
   float *msc;          /* Kp*(M+1) log-odds match scores [x*(M+1)+k]          */
   /* MSV 8-bit */
   uint8_t *rbv;        /* Kp*(M+1) biased costs                               */
+  uint8_t *rbv_s;      /* striped copy for the AVX2 filter: Kp * Qb * 32 bytes (NULL until built) */
+  int Qb;              /* vectors per row = ceil(M/32)                        */
   uint8_t tbm_b, tec_b, base_b, bias_b;
   float scale_b;
   /* Viterbi 16-bit */
@@ -79,6 +81,8 @@ typedef struct {
   double E, domE;          /* 10 10 */
   int do_bias, do_null2, do_max;
   double Z, domZ;          /* <=0: set by number of targets / reported */
+  int simd_msv;            /* 1: MSV through the striped AVX2 filter (same numbers; bench.py's CPU baseline) */
+  int reserved;
 } ORC_OPTS;
 
 typedef struct {
@@ -120,6 +124,10 @@ void orc_profile_free(ORC_PROFILE *p);
 float orc_profile_tsc(const ORC_PROFILE *p, int k, int t);
 float orc_profile_msc(const ORC_PROFILE *p, int x, int k);
 int orc_profile_rbv(const ORC_PROFILE *p, int x, int k);
+/* Striped AVX2 MSV filter (Farrar layout, as HMMER's own SIMD filter): same result as orc_msv, bit for bit.
+ * Returns -1 if the CPU has no AVX2 (callers then use orc_msv). */
+int orc_msv_simd(const ORC_PROFILE *p, const uint8_t *dsq, int L, float *ret_sc, int *xJ_raw);
+int orc_have_avx2(void);
 int orc_profile_rwv(const ORC_PROFILE *p, int x, int k);
 int orc_profile_bytes(const ORC_PROFILE *p, int which);
 

@@ -210,8 +210,9 @@ class Context:
         pool = max(1, self.L.pa_hit_pool_bytes(self.h))
         mp, tp = C.create_string_buffer(pool), C.create_string_buffer(pool)
         self._check(self.L.pa_get_hits(self.h, _ptr(hits), n, mp, tp, pool), "pa_get_hits")
-        model = [mp.raw[o:o + l].decode() for o, l in zip(hits["ali_off"], hits["ali_len"])]
-        aligned = [tp.raw[o:o + l].decode() for o, l in zip(hits["ali_off"], hits["ali_len"])]
+        mraw, traw = mp.raw, tp.raw          # one copy of each pool, then slices
+        model = [mraw[o:o + l].decode() for o, l in zip(hits["ali_off"], hits["ali_len"])]
+        aligned = [traw[o:o + l].decode() for o, l in zip(hits["ali_off"], hits["ali_len"])]
         return hits, model, aligned
 
     def stats(self) -> dict:

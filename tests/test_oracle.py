@@ -247,3 +247,24 @@ def test_alignment_strings_are_consistent(oracle):
         nins += "." in m
         ndel += "-" in a
     assert nins > 0 and ndel > 0
+
+
+def test_simd_msv_equals_scalar_msv(oracle):
+    """The AVX2 striped MSV (bench.py's CPU baseline) returns the scalar filter's byte and score."""
+    import numpy as np
+    from tests import helpers
+    rng = np.random.default_rng(4)
+    for M in (1, 31, 32, 33, 200, 470, 2047):
+        h = helpers.calibrated_hmm(f"s{M}", M, seed=900 + M, n=8)
+        P = oracle.Profile.from_hmm(h)
+        seqs = helpers.protein_targets([h], 120, rng, Lmin=1, Lmax=120, plant_every=3)
+        seqs.append("*" + seqs[0] + "X*")
+        for s in seqs:
+            got = P.msv_simd(s)
+            if got is None:
+                pytest.skip("no AVX2 on this host")
+            assert got == P.msv(s), (M, s)
+    # and through the pipeline: same hits with and without the SIMD filter
+    a, _ = P.search(seqs, opts=oracle.default_opts(simd_msv=1), nthreads=2)
+    b, _ = P.search(seqs, nthreads=2)
+    assert [(x["target"], x["iali"], x["jali"], x["seq_bits"]) for x in a] == [(x["target"], x["iali"], x["jali"], x["seq_bits"]) for x in b]
