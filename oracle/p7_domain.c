@@ -5,15 +5,19 @@
  * Restates SURVEY.md Appendix A.7, A.8, A.10 (HMMER3 domain definition; the
  * reference consumes its output at /root/reference/lib/aln.py:511-561).
  *
- * Deviation (documented in DESIGN.md): regions that trip the multi-domain test
- * (rt3) are flagged but still resolved as ONE envelope; HMMER resolves them by
- * clustering 200 stochastic tracebacks (needs HMMER's RNG stream, unpinnable).
+ * Multi-domain regions (rt3) are resolved the way HMMER does (A.7): 200 stochastic tracebacks of the
+ * multihit Forward matrix of the region, single-linkage clustering of the sampled domain segments,
+ * clusters seen in >= 25 % of the traces become envelopes whose ends are the outermost end points used
+ * by >= 2 % of the traces.  Two documented deviations: the random stream is this file's own
+ * (xorshift64*, one stream per trace index, so the result does not depend on evaluation order; HMMER's
+ * is its Mersenne Twister reseeded per target and cannot be reproduced without its source), and null2 of
+ * such envelopes is computed by expectation like every other envelope instead of from the traces.
  */
-#include "p7oracle.h"
-#include "p7_internal.h"
 #include "p7_domain.h"
+#include "p7_internal.h"
 #include <ctype.h>
 #include <math.h>
+#include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -360,6 +364,210 @@ int p7d_rescore_envelope(const ORC_PROFILE *p, const uint8_t *dsq, int L, int ie
   return rc;
 }
 
+/* ---- multi-domain regions: stochastic traceback ensemble + clustering (A.7) ---- */
+#define P7D_NSAMPLES 200
+#define P7D_MAXSEG 8 /* domain segments kept per sampled trace (further ones are dropped) */
+typedef struct { int t, i, j, k, m; } P7D_SEG;
+
+static inline float p7d_rng_uniform(uint64_t *x) { /* xorshift64*, top 24 bits -> [0,1) */
+  *x ^= *x >> 12;
+  *x ^= *x << 25;
+  *x ^= *x >> 27;
+  return (float)((*x * 0x2545F4914F6CDD1Dull) >> 40) * (1.0f / 16777216.0f);
+}
+static inline uint64_t p7d_rng_seed(int t) { return 42ull * 0x9E3779B97F4A7C15ull + (uint64_t)(t + 1) * 0xBF58476D1CE4E5B9ull; }
+
+/* index drawn with probability p[i] / sum(p): serial sums in index order */
+static int p7d_choose(const float *pr, int n, float u) {
+  float tot = 0.0f;
+  for (int i = 0; i < n; i++) tot = tot + pr[i];
+  const float r = u * tot;
+  float cum = 0.0f;
+  int last = 0;
+  for (int i = 0; i < n; i++) {
+    if (pr[i] > 0.0f) last = i;
+    cum = cum + pr[i];
+    if (r < cum) return i;
+  }
+  return last;
+}
+
+/* One stochastic traceback of the multihit Forward matrix of a region (rows 0..Lr). Appends the
+ * trace's domain segments (first/last match state: residue i..j, node k..m). */
+static int p7d_sample_trace(const ORC_PROFILE *p, const P7I_MX *fx, const P7I_SPECIALS *sf, const int *ef, int Lr,
+                            const P7I_XF *xf, int t, P7D_SEG *out) {
+  const int M = p->M;
+  const size_t W = (size_t)M + 2;
+  const float *tf = p->tfv;
+  uint64_t rng = p7d_rng_seed(t);
+  int nseg = 0, i = Lr, k = 0;
+  int seg_j = 0, seg_m = 0, seg_i = 0, seg_k = 0, have_m = 0;
+  char st = 'C';
+  int guard = 0;
+  while (st != 'S' && guard++ < 8 * (Lr + M) + 64) {
+    float pr[4];
+    switch (st) {
+      case 'C':
+        if (i == 0) { st = 'S'; break; } /* cannot happen with positive probability */
+        pr[0] = scalbnf(sf[i - 1].xC * xf->tCC, ef[i - 1] - ef[i]);
+        pr[1] = sf[i].xE * xf->tEC;
+        if (p7d_choose(pr, 2, p7d_rng_uniform(&rng)) == 0) i--;
+        else st = 'E';
+        break;
+      case 'J':
+        if (i == 0) { st = 'S'; break; }
+        pr[0] = scalbnf(sf[i - 1].xJ * xf->tJJ, ef[i - 1] - ef[i]);
+        pr[1] = sf[i].xE * xf->tEJ;
+        if (p7d_choose(pr, 2, p7d_rng_uniform(&rng)) == 0) i--;
+        else st = 'E';
+        break;
+      case 'E': { /* all M_k, D_k of row i, k ascending, M before D */
+        const float *Mi = fx->M + (size_t)i * W, *Di = fx->D + (size_t)i * W;
+        float tot = 0.0f;
+        for (int kk = 1; kk <= M; kk++) { tot = tot + Mi[kk]; tot = tot + Di[kk]; }
+        const float r = p7d_rng_uniform(&rng) * tot;
+        float cum = 0.0f;
+        int ck = M, cs = 'M', found = 0;
+        for (int kk = 1; kk <= M && !found; kk++) {
+          if (Mi[kk] > 0.0f) { ck = kk; cs = 'M'; }
+          cum = cum + Mi[kk];
+          if (r < cum) { ck = kk; cs = 'M'; found = 1; break; }
+          if (Di[kk] > 0.0f) { ck = kk; cs = 'D'; }
+          cum = cum + Di[kk];
+          if (r < cum) { ck = kk; cs = 'D'; found = 1; break; }
+        }
+        k = ck;
+        st = (char)cs;
+        have_m = 0;
+      } break;
+      case 'M': {
+        if (!have_m) { seg_j = i; seg_m = k; have_m = 1; }
+        seg_i = i; seg_k = k;
+        const float *Mp = fx->M + (size_t)(i - 1) * W, *Ip = fx->I + (size_t)(i - 1) * W, *Dp = fx->D + (size_t)(i - 1) * W;
+        pr[0] = sf[i - 1].xB * tf[(k - 1) * 8 + ORC_BM];
+        pr[1] = k >= 2 ? Mp[k - 1] * tf[(k - 1) * 8 + ORC_MM] : 0.0f;
+        pr[2] = k >= 2 ? Ip[k - 1] * tf[(k - 1) * 8 + ORC_IM] : 0.0f;
+        pr[3] = k >= 2 ? Dp[k - 1] * tf[(k - 1) * 8 + ORC_DM] : 0.0f;
+        const int c = p7d_choose(pr, 4, p7d_rng_uniform(&rng));
+        i--;
+        if (c == 0) st = 'B';
+        else { k--; st = c == 1 ? 'M' : c == 2 ? 'I' : 'D'; }
+      } break;
+      case 'D': {
+        const float *Mi = fx->M + (size_t)i * W, *Di = fx->D + (size_t)i * W;
+        pr[0] = k >= 2 ? Mi[k - 1] * tf[(k - 1) * 8 + ORC_MD] : 0.0f;
+        pr[1] = k >= 2 ? Di[k - 1] * tf[(k - 1) * 8 + ORC_DD] : 0.0f;
+        const int c = p7d_choose(pr, 2, p7d_rng_uniform(&rng));
+        k--;
+        st = c == 0 ? 'M' : 'D';
+      } break;
+      case 'I': {
+        const float *Mp = fx->M + (size_t)(i - 1) * W, *Ip = fx->I + (size_t)(i - 1) * W;
+        pr[0] = Mp[k] * tf[k * 8 + ORC_MI];
+        pr[1] = Ip[k] * tf[k * 8 + ORC_II];
+        const int c = p7d_choose(pr, 2, p7d_rng_uniform(&rng));
+        i--;
+        st = c == 0 ? 'M' : 'I';
+      } break;
+      case 'B': {
+        if (have_m && nseg < P7D_MAXSEG) { out[nseg].t = t; out[nseg].i = seg_i; out[nseg].j = seg_j; out[nseg].k = seg_k; out[nseg].m = seg_m; nseg++; }
+        have_m = 0;
+        pr[0] = sf[i].xN * xf->tNB;
+        pr[1] = sf[i].xJ * xf->tJB;
+        st = p7d_choose(pr, 2, p7d_rng_uniform(&rng)) == 0 ? 'N' : 'J';
+      } break;
+      case 'N':
+        if (i == 0) st = 'S';
+        else i--;
+        break;
+      default: st = 'S';
+    }
+  }
+  return nseg;
+}
+
+static int p7d_linked(const P7D_SEG *a, const P7D_SEG *b) { /* min_overlap 0.8 of the smaller, max_diagdiff 4 */
+  int nov = (a->j < b->j ? a->j : b->j) - (a->i > b->i ? a->i : b->i) + 1;
+  int la = a->j - a->i + 1, lb = b->j - b->i + 1;
+  int n = la < lb ? la : lb;
+  if ((float)nov / (float)n < 0.8f) return 0;
+  nov = (a->m < b->m ? a->m : b->m) - (a->k > b->k ? a->k : b->k) + 1;
+  la = a->m - a->k + 1; lb = b->m - b->k + 1;
+  n = la < lb ? la : lb;
+  if ((float)nov / (float)n < 0.8f) return 0;
+  if (abs((a->k - a->i) - (b->k - b->i)) > 4) return 0;
+  if (abs((a->m - a->j) - (b->m - b->j)) > 4) return 0;
+  return 1;
+}
+
+/* Envelopes (target coordinates) of a multi-domain region ireg..jreg; returns their number (<= maxenv),
+ * ordered by start, then end. */
+int p7d_resolve_multidomain(const ORC_PROFILE *p, const uint8_t *dsq, int L, int ireg, int jreg, int *env_i, int *env_j,
+                            int maxenv) {
+  const int M = p->M, Lr = jreg - ireg + 1;
+  const uint8_t *sub = dsq + ireg - 1;
+  P7I_MX fx = mx_alloc(Lr, M);
+  P7I_SPECIALS *sf = (P7I_SPECIALS *)malloc(sizeof(P7I_SPECIALS) * (Lr + 1));
+  int *ef = (int *)malloc(sizeof(int) * (Lr + 1));
+  P7I_XF xf = p7i_xf_config(L, 1);
+  p7i_forward(p, sub, Lr, L, 1, &fx, sf, ef, NULL, NULL);
+  P7D_SEG *seg = (P7D_SEG *)malloc(sizeof(P7D_SEG) * P7D_NSAMPLES * P7D_MAXSEG);
+  int nseg = 0;
+  for (int t = 0; t < P7D_NSAMPLES; t++) nseg += p7d_sample_trace(p, &fx, sf, ef, Lr, &xf, t, seg + nseg);
+  /* single linkage: connected components by label propagation (label = smallest member index) */
+  int *lab = (int *)malloc(sizeof(int) * (nseg + 1));
+  for (int a = 0; a < nseg; a++) lab[a] = a;
+  for (int changed = 1; changed;) {
+    changed = 0;
+    for (int a = 0; a < nseg; a++)
+      for (int b = 0; b < nseg; b++)
+        if (lab[b] < lab[a] && p7d_linked(&seg[a], &seg[b])) { lab[a] = lab[b]; changed = 1; }
+  }
+  int nenv = 0;
+  int *cnt_i = (int *)calloc((size_t)Lr + 2, sizeof(int)), *cnt_j = (int *)calloc((size_t)Lr + 2, sizeof(int));
+  for (int c = 0; c < nseg; c++) {
+    if (lab[c] != c) continue; /* c is the representative (smallest index) of its cluster */
+    int ninc = 0, lastt = -1, imin = Lr + 1, imax = 0, jmin = Lr + 1, jmax = 0;
+    for (int a = c; a < nseg; a++) {
+      if (lab[a] != c) continue;
+      if (seg[a].t != lastt) { ninc++; lastt = seg[a].t; } /* segments are stored trace by trace */
+      cnt_i[seg[a].i]++;
+      cnt_j[seg[a].j]++;
+      if (seg[a].i < imin) imin = seg[a].i;
+      if (seg[a].i > imax) imax = seg[a].i;
+      if (seg[a].j < jmin) jmin = seg[a].j;
+      if (seg[a].j > jmax) jmax = seg[a].j;
+    }
+    if ((float)ninc / (float)P7D_NSAMPLES >= 0.25f) {
+      int bi, bj, arg = imin;
+      for (bi = imin; bi <= imax; bi++) {
+        if (cnt_i[bi] > cnt_i[arg]) arg = bi;
+        if ((float)cnt_i[bi] / (float)ninc >= 0.02f) break;
+      }
+      if (bi > imax) bi = arg;
+      arg = jmax;
+      for (bj = jmax; bj >= jmin; bj--) {
+        if (cnt_j[bj] > cnt_j[arg]) arg = bj;
+        if ((float)cnt_j[bj] / (float)ninc >= 0.02f) break;
+      }
+      if (bj < jmin) bj = arg;
+      if (nenv < maxenv && bj >= bi) { env_i[nenv] = bi + ireg - 1; env_j[nenv] = bj + ireg - 1; nenv++; }
+    }
+    for (int a = c; a < nseg; a++)
+      if (lab[a] == c) { cnt_i[seg[a].i] = 0; cnt_j[seg[a].j] = 0; }
+  }
+  /* order by start, then end (insertion sort; nenv is tiny) */
+  for (int a = 1; a < nenv; a++)
+    for (int b = a; b > 0 && (env_i[b] < env_i[b - 1] || (env_i[b] == env_i[b - 1] && env_j[b] < env_j[b - 1])); b--) {
+      int ti = env_i[b], tj = env_j[b];
+      env_i[b] = env_i[b - 1]; env_j[b] = env_j[b - 1];
+      env_i[b - 1] = ti; env_j[b - 1] = tj;
+    }
+  free(cnt_i); free(cnt_j); free(lab); free(seg); free(sf); free(ef);
+  mx_free(&fx);
+  return nenv;
+}
+
 /* Domain definition over a full target (A.7). doms[] capacity maxdom; alignment strings are written
  * consecutively (NUL-separated) into model/target pools. Returns ndom; *nregions, *nmulti set. */
 int p7d_define_domains(const ORC_PROFILE *p, const uint8_t *dsq, int L, int do_null2, float *n2sc,
@@ -384,16 +592,20 @@ int p7d_define_domains(const ORC_PROFILE *p, const uint8_t *dsq, int L, int do_n
       (*nregions)++;
       int multi = is_multidomain_region(btot, etot, i, j, rt3);
       if (multi) (*nmulti)++;
-      if (ndom < maxdom && poolcap - used > 2 * (j - i + 1) + 2 * p->M + 8) {
-        P7D_DOMAIN *d = &doms[ndom];
-        d->multidomain_region = multi;
-        d->ali_off = used;
-        int rc = p7d_rescore_envelope(p, dsq, L, i, j, do_null2, n2sc, d, model + used, target + used, poolcap - used);
-        if (rc == 0) {
-          used += d->ali_len + 1;
-          ndom++;
+      int env_i[P7D_MAXENV], env_j[P7D_MAXENV], nenv = 1;
+      env_i[0] = i; env_j[0] = j;
+      if (multi) nenv = p7d_resolve_multidomain(p, dsq, L, i, j, env_i, env_j, P7D_MAXENV);
+      for (int e = 0; e < nenv; e++)
+        if (ndom < maxdom && poolcap - used > 2 * (env_j[e] - env_i[e] + 1) + 2 * p->M + 8) {
+          P7D_DOMAIN *d = &doms[ndom];
+          d->multidomain_region = multi;
+          d->ali_off = used;
+          int rc = p7d_rescore_envelope(p, dsq, L, env_i[e], env_j[e], do_null2, n2sc, d, model + used, target + used, poolcap - used);
+          if (rc == 0) {
+            used += d->ali_len + 1;
+            ndom++;
+          }
         }
-      }
       i = -1;
       triggered = 0;
     }

@@ -9,14 +9,19 @@
 // scan, traceback) run on lane 0.  Float evaluation order is the canonical one shared with the
 // oracle (DESIGN.md "Canonical float order"), so regions, envelopes and tracebacks are bit-exact.
 //
-// Known deviation (same as the oracle): a region that trips the multi-domain test (rt3) is flagged
-// and resolved as one envelope instead of HMMER's stochastic-traceback clustering.
+// Regions that trip the multi-domain test (rt3) are resolved as HMMER does: 200 stochastic tracebacks of
+// the region's multihit Forward matrix (one trace per lane, own xorshift64* stream per trace index),
+// single-linkage clustering of the sampled segments (label propagation over all lanes), envelopes from
+// the clusters seen in >= 25 % of the traces.  Same arithmetic and order as oracle/p7_domain.c.
 #pragma once
 #include "kernels.cuh"
 
 namespace pa {
 
 #define PA_MAXREG 64
+#define PA_NSAMPLES 200   // stochastic tracebacks per multi-domain region (HMMER: 200)
+#define PA_MAXSEG 8      // domain segments kept per sampled trace
+#define PA_MAXENV 8      // envelopes kept per multi-domain region
 
 struct DomRec {
   uint32_t t;
@@ -54,7 +59,7 @@ struct DomainBufs {
 };
 
 struct SlabLayout {
-  size_t sf, sb, ef, eb, lin, reg, trk, tri, trs, mat, total;  // offsets in floats
+  size_t sf, sb, ef, eb, lin, reg, trk, tri, trs, seg, mat, total;  // offsets in floats
   size_t msz;
 };
 __host__ __device__ inline SlabLayout slab_layout(int maxL, int maxW, int maxM) {
@@ -70,6 +75,7 @@ __host__ __device__ inline SlabLayout slab_layout(int maxL, int maxW, int maxM) 
   s.trk = o; o += tr;
   s.tri = o; o += tr;
   s.trs = o; o += (tr + 3) / 4;
+  s.seg = o; o += 10 * (size_t)PA_NSAMPLES * PA_MAXSEG + PA_NSAMPLES + 4 * PA_MAXENV + 64;  // multi-domain regions: segraw 4x | segc 5x | lab 1x | nper | envl
   o = (o + 3) & ~(size_t)3;
   s.mat = o;
   s.msz = L1 * (size_t)maxW;
@@ -217,6 +223,257 @@ __device__ void backward_pass(const FwdTabs &T, const uint8_t *p, int L, int Lcf
 
 __device__ __forceinline__ int cell_of_k(int k, int B) { return ((k - 1) % B) * 32 + (k - 1) / B; }
 
+// Forward over sub[0..Ld-1] with the full matrix stored (rows 0..Ld at F* + i*W), specials and exponent
+// totals per row. xf: multihit or unihit configuration for the FULL target length.
+__device__ void forward_full(const FwdTabs &T, const uint8_t *sub, int Ld, const XF &xf, float *rows, float *FM, float *FI,
+                             float *FD, Specials *sf, int *ef, int lane, int *Ze_out, float *Zm_out) {
+  const int W = T.W, B = T.B;
+  for (int c = lane; c < 8 * W; c += 32) rows[c] = 0.0f;
+  for (int j = 0; j < B; j++) { FM[j * 32 + lane] = 0.0f; FI[j * 32 + lane] = 0.0f; FD[j * 32 + lane] = 0.0f; }
+  int Ze = 0;
+  float xN = 1.0f, xB = xf.tNB, xE = 0.0f, xJ = 0.0f, xC = 0.0f;
+  float *wP = rows + 6 * W;
+  if (lane == 0) { Specials s0; s0.xE = 0; s0.xN = xN; s0.xJ = 0; s0.xB = xB; s0.xC = 0; sf[0] = s0; ef[0] = 0; }
+  for (int i = 1; i <= Ld; i++) {
+    float *Mp = FM + (size_t)(i - 1) * W, *Ip = FI + (size_t)(i - 1) * W, *Dp = FD + (size_t)(i - 1) * W;
+    float *Mc = FM + (size_t)i * W, *Ic = FI + (size_t)i * W, *Dc = FD + (size_t)i * W;
+    for (int j = 0; j < B; j++) { Mc[j * 32 + lane] = 0.0f; Ic[j * 32 + lane] = 0.0f; Dc[j * 32 + lane] = 0.0f; }
+    xE = fwd_row(T, sub[i - 1], Mp, Ip, Dp, xB, Mc, Ic, Dc, wP, lane);
+    xN = __fmul_rn(xN, xf.tNN);
+    xJ = __fadd_rn(__fmul_rn(xJ, xf.tJJ), __fmul_rn(xE, xf.tEJ));
+    xC = __fadd_rn(__fmul_rn(xC, xf.tCC), __fmul_rn(xE, xf.tEC));
+    xB = __fadd_rn(__fmul_rn(xJ, xf.tJB), __fmul_rn(xN, xf.tNB));
+    if (xE > PA_RESCALE) {
+      const int e = ilogbf(xE);
+      scale_row(Mc, Ic, Dc, B, lane, e);
+      xN = scalbnf(xN, -e); xJ = scalbnf(xJ, -e); xC = scalbnf(xC, -e); xB = scalbnf(xB, -e); xE = scalbnf(xE, -e);
+      Ze += e;
+    }
+    if (lane == 0) { Specials s; s.xE = xE; s.xN = xN; s.xJ = xJ; s.xB = xB; s.xC = xC; sf[i] = s; ef[i] = Ze; }
+  }
+  *Ze_out = Ze;
+  *Zm_out = __fmul_rn(xC, xf.tCT);
+}
+
+// ---- multi-domain regions (oracle/p7_domain.c: p7d_sample_trace, p7d_linked, p7d_resolve_multidomain) ----
+__device__ __forceinline__ float md_uniform(unsigned long long &x) {
+  x ^= x >> 12;
+  x ^= x << 25;
+  x ^= x >> 27;
+  return __fmul_rn((float)((x * 0x2545F4914F6CDD1Dull) >> 40), 1.0f / 16777216.0f);
+}
+__device__ __forceinline__ int md_choose(const float *pr, int n, float u) {
+  float tot = 0.0f;
+  for (int i = 0; i < n; i++) tot = __fadd_rn(tot, pr[i]);
+  const float r = __fmul_rn(u, tot);
+  float cum = 0.0f;
+  int last = 0;
+  for (int i = 0; i < n; i++) {
+    if (pr[i] > 0.0f) last = i;
+    cum = __fadd_rn(cum, pr[i]);
+    if (r < cum) return i;
+  }
+  return last;
+}
+
+// One stochastic traceback, run by ONE lane. Writes up to PA_MAXSEG segments {i, j, k, m}; returns their number.
+__device__ int md_sample_trace(const FwdTabs &T, const float *FM, const float *FI, const float *FD, const Specials *sf,
+                               const int *ef, int Lr, const XF &xf, int t, int *seg4) {
+  const int M = T.M, B = T.B, W = T.W;
+  unsigned long long rng = 42ull * 0x9E3779B97F4A7C15ull + (unsigned long long)(t + 1) * 0xBF58476D1CE4E5B9ull;
+  int nseg = 0, i = Lr, k = 0;
+  int seg_j = 0, seg_m = 0, seg_i = 0, seg_k = 0, have_m = 0;
+  char st = 'C';
+  int guard = 0;
+  while (st != 'S' && guard++ < 8 * (Lr + M) + 64) {
+    float pr[4];
+    switch (st) {
+      case 'C':
+        if (i == 0) { st = 'S'; break; }
+        pr[0] = scalbnf(__fmul_rn(sf[i - 1].xC, xf.tCC), ef[i - 1] - ef[i]);
+        pr[1] = __fmul_rn(sf[i].xE, xf.tEC);
+        if (md_choose(pr, 2, md_uniform(rng)) == 0) i--;
+        else st = 'E';
+        break;
+      case 'J':
+        if (i == 0) { st = 'S'; break; }
+        pr[0] = scalbnf(__fmul_rn(sf[i - 1].xJ, xf.tJJ), ef[i - 1] - ef[i]);
+        pr[1] = __fmul_rn(sf[i].xE, xf.tEJ);
+        if (md_choose(pr, 2, md_uniform(rng)) == 0) i--;
+        else st = 'E';
+        break;
+      case 'E': {  // all M_k, D_k of row i, k ascending (k = l*B + j + 1 lives in cell j*32 + l), M before D
+        const float *Mi = FM + (size_t)i * W, *Di = FD + (size_t)i * W;
+        float tot = 0.0f;
+        for (int l = 0, kk = 1; l < 32 && kk <= M; l++)
+          for (int j = 0; j < B && kk <= M; j++, kk++) { tot = __fadd_rn(tot, Mi[j * 32 + l]); tot = __fadd_rn(tot, Di[j * 32 + l]); }
+        const float r = __fmul_rn(md_uniform(rng), tot);
+        float cum = 0.0f;
+        int ck = M, found = 0;
+        char cs = 'M';
+        for (int l = 0, kk = 1; l < 32 && kk <= M && !found; l++)
+          for (int j = 0; j < B && kk <= M; j++, kk++) {
+            const float vm = Mi[j * 32 + l], vd = Di[j * 32 + l];
+            if (vm > 0.0f) { ck = kk; cs = 'M'; }
+            cum = __fadd_rn(cum, vm);
+            if (r < cum) { ck = kk; cs = 'M'; found = 1; break; }
+            if (vd > 0.0f) { ck = kk; cs = 'D'; }
+            cum = __fadd_rn(cum, vd);
+            if (r < cum) { ck = kk; cs = 'D'; found = 1; break; }
+          }
+        k = ck;
+        st = cs;
+        have_m = 0;
+      } break;
+      case 'M': {
+        if (!have_m) { seg_j = i; seg_m = k; have_m = 1; }
+        seg_i = i; seg_k = k;
+        const float4 A = T.trA[cell_of_k(k, B)];
+        const size_t rb = (size_t)(i - 1) * W;
+        const int cp = k >= 2 ? cell_of_k(k - 1, B) : 0;
+        pr[0] = __fmul_rn(sf[i - 1].xB, A.x);
+        pr[1] = k >= 2 ? __fmul_rn(FM[rb + cp], A.y) : 0.0f;
+        pr[2] = k >= 2 ? __fmul_rn(FI[rb + cp], A.z) : 0.0f;
+        pr[3] = k >= 2 ? __fmul_rn(FD[rb + cp], A.w) : 0.0f;
+        const int c = md_choose(pr, 4, md_uniform(rng));
+        i--;
+        if (c == 0) st = 'B';
+        else { k--; st = c == 1 ? 'M' : c == 2 ? 'I' : 'D'; }
+      } break;
+      case 'D': {
+        const float4 Bq = T.trB[cell_of_k(k, B)];
+        const int cp = k >= 2 ? cell_of_k(k - 1, B) : 0;
+        pr[0] = k >= 2 ? __fmul_rn(FM[(size_t)i * W + cp], Bq.x) : 0.0f;
+        pr[1] = k >= 2 ? __fmul_rn(FD[(size_t)i * W + cp], Bq.y) : 0.0f;
+        const int c = md_choose(pr, 2, md_uniform(rng));
+        k--;
+        st = c == 0 ? 'M' : 'D';
+      } break;
+      case 'I': {
+        const int c0 = cell_of_k(k, B);
+        const float4 Bq = T.trB[c0];
+        pr[0] = __fmul_rn(FM[(size_t)(i - 1) * W + c0], Bq.z);
+        pr[1] = __fmul_rn(FI[(size_t)(i - 1) * W + c0], Bq.w);
+        const int c = md_choose(pr, 2, md_uniform(rng));
+        i--;
+        st = c == 0 ? 'M' : 'I';
+      } break;
+      case 'B': {
+        if (have_m && nseg < PA_MAXSEG) { seg4[4 * nseg] = seg_i; seg4[4 * nseg + 1] = seg_j; seg4[4 * nseg + 2] = seg_k; seg4[4 * nseg + 3] = seg_m; nseg++; }
+        have_m = 0;
+        pr[0] = __fmul_rn(sf[i].xN, xf.tNB);
+        pr[1] = __fmul_rn(sf[i].xJ, xf.tJB);
+        st = md_choose(pr, 2, md_uniform(rng)) == 0 ? 'N' : 'J';
+      } break;
+      case 'N':
+        if (i == 0) st = 'S';
+        else i--;
+        break;
+      default: st = 'S';
+    }
+  }
+  return nseg;
+}
+
+__device__ __forceinline__ bool md_linked(const int *a, const int *b) {  // {t, i, j, k, m}
+  int nov = min(a[2], b[2]) - max(a[1], b[1]) + 1;
+  int n = min(a[2] - a[1] + 1, b[2] - b[1] + 1);
+  if (__fdiv_rn((float)nov, (float)n) < 0.8f) return false;
+  nov = min(a[4], b[4]) - max(a[3], b[3]) + 1;
+  n = min(a[4] - a[3] + 1, b[4] - b[3] + 1);
+  if (__fdiv_rn((float)nov, (float)n) < 0.8f) return false;
+  if (abs((a[3] - a[1]) - (b[3] - b[1])) > 4) return false;
+  if (abs((a[4] - a[2]) - (b[4] - b[2])) > 4) return false;
+  return true;
+}
+
+// Envelopes of the multi-domain region ireg..jreg -> envl[2e], envl[2e+1] (target coordinates), ordered by
+// start then end. Whole warp. scratch: segraw 4*NS*MAXSEG | segc 5*NS*MAXSEG | lab NS*MAXSEG | nper NS; cnt_i/cnt_j: Lr+2 ints.
+__device__ int resolve_multidomain(const FwdTabs &T, const uint8_t *sub, int Lr, int Lfull, int ireg, float *rows, float *FM,
+                                   float *FI, float *FD, Specials *sf, int *ef, int *segscratch, int *cnt_i, int *cnt_j,
+                                   int *envl, int lane) {
+  const XF xf = xf_config(Lfull, 1);
+  int Ze;
+  float Zm;
+  forward_full(T, sub, Lr, xf, rows, FM, FI, FD, sf, ef, lane, &Ze, &Zm);
+  __syncwarp();
+  int *segraw = segscratch, *segc = segraw + 4 * PA_NSAMPLES * PA_MAXSEG, *lab = segc + 5 * PA_NSAMPLES * PA_MAXSEG,
+      *nper = lab + PA_NSAMPLES * PA_MAXSEG;
+  for (int t = lane; t < PA_NSAMPLES; t += 32)
+    nper[t] = md_sample_trace(T, FM, FI, FD, sf, ef, Lr, xf, t, segraw + 4 * t * PA_MAXSEG);
+  __syncwarp();
+  int nseg = 0;
+  if (lane == 0) {  // compact, trace by trace
+    for (int t = 0; t < PA_NSAMPLES; t++)
+      for (int q = 0; q < nper[t]; q++) {
+        const int *r = segraw + 4 * (t * PA_MAXSEG + q);
+        int *d = segc + 5 * nseg;
+        d[0] = t; d[1] = r[0]; d[2] = r[1]; d[3] = r[2]; d[4] = r[3];
+        lab[nseg] = nseg;
+        nseg++;
+      }
+  }
+  nseg = __shfl_sync(PA_FULL, nseg, 0);
+  __syncwarp();
+  // single linkage by label propagation: label = smallest member index of the connected component
+  for (;;) {
+    int changed = 0;
+    for (int a = lane; a < nseg; a += 32) {
+      int la = ((volatile int *)lab)[a];
+      for (int b = 0; b < nseg; b++) {
+        const int lb = ((volatile int *)lab)[b];
+        if (lb < la && md_linked(segc + 5 * a, segc + 5 * b)) { la = lb; changed = 1; }
+      }
+      ((volatile int *)lab)[a] = la;
+    }
+    __syncwarp();
+    if (!__any_sync(PA_FULL, changed)) break;
+  }
+  int nenv = 0;
+  if (lane == 0) {
+    for (int z = 0; z <= Lr; z++) { cnt_i[z] = 0; cnt_j[z] = 0; }
+    for (int c = 0; c < nseg; c++) {
+      if (lab[c] != c) continue;
+      int ninc = 0, lastt = -1, imin = Lr + 1, imax = 0, jmin = Lr + 1, jmax = 0;
+      for (int a = c; a < nseg; a++) {
+        if (lab[a] != c) continue;
+        const int *s = segc + 5 * a;
+        if (s[0] != lastt) { ninc++; lastt = s[0]; }
+        cnt_i[s[1]]++;
+        cnt_j[s[2]]++;
+        imin = min(imin, s[1]); imax = max(imax, s[1]);
+        jmin = min(jmin, s[2]); jmax = max(jmax, s[2]);
+      }
+      if (__fdiv_rn((float)ninc, (float)PA_NSAMPLES) >= 0.25f) {
+        int bi, bj, arg = imin;
+        for (bi = imin; bi <= imax; bi++) {
+          if (cnt_i[bi] > cnt_i[arg]) arg = bi;
+          if (__fdiv_rn((float)cnt_i[bi], (float)ninc) >= 0.02f) break;
+        }
+        if (bi > imax) bi = arg;
+        arg = jmax;
+        for (bj = jmax; bj >= jmin; bj--) {
+          if (cnt_j[bj] > cnt_j[arg]) arg = bj;
+          if (__fdiv_rn((float)cnt_j[bj], (float)ninc) >= 0.02f) break;
+        }
+        if (bj < jmin) bj = arg;
+        if (nenv < PA_MAXENV && bj >= bi) { envl[2 * nenv] = bi + ireg - 1; envl[2 * nenv + 1] = bj + ireg - 1; nenv++; }
+      }
+      for (int a = c; a < nseg; a++)
+        if (lab[a] == c) { cnt_i[segc[5 * a + 1]] = 0; cnt_j[segc[5 * a + 2]] = 0; }
+    }
+    for (int a = 1; a < nenv; a++)
+      for (int b = a; b > 0 && (envl[2 * b] < envl[2 * b - 2] || (envl[2 * b] == envl[2 * b - 2] && envl[2 * b + 1] < envl[2 * b - 1])); b--) {
+        const int ti = envl[2 * b], tj = envl[2 * b + 1];
+        envl[2 * b] = envl[2 * b - 2]; envl[2 * b + 1] = envl[2 * b - 1];
+        envl[2 * b - 2] = ti; envl[2 * b - 1] = tj;
+      }
+  }
+  nenv = __shfl_sync(PA_FULL, nenv, 0);
+  __syncwarp();
+  return nenv;
+}
+
 __global__ void __launch_bounds__(128) domain_kernel(DomArgs a) {
   const int lane = threadIdx.x & 31;
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -233,6 +490,8 @@ __global__ void __launch_bounds__(128) domain_kernel(DomArgs a) {
   int *reg = reinterpret_cast<int *>(slab + sl.reg);
   int *trk = reinterpret_cast<int *>(slab + sl.trk), *tri = reinterpret_cast<int *>(slab + sl.tri);
   char *trs = reinterpret_cast<char *>(slab + sl.trs);
+  int *segscratch = reinterpret_cast<int *>(slab + sl.seg);
+  int *envl = segscratch + 10 * PA_NSAMPLES * PA_MAXSEG + PA_NSAMPLES;
   float *FM = slab + sl.mat;                           // 6 matrices of maxL1 * maxW
   const size_t msz = sl.msz;
   float *FI = FM + msz, *FD = FI + msz, *BM = FD + msz, *BI = BM + msz, *BD = BI + msz;
@@ -295,38 +554,22 @@ __global__ void __launch_bounds__(128) domain_kernel(DomArgs a) {
     __syncwarp();
     int ndom = 0;
     for (int rg = 0; rg < nreg; rg++) {
-      const int ienv = reg[3 * rg], jenv = reg[3 * rg + 1], multi = reg[3 * rg + 2];
+     const int ireg = reg[3 * rg], jreg = reg[3 * rg + 1], multi = reg[3 * rg + 2];
+     int nenv = 1;
+     if (multi) {
+       nenv = resolve_multidomain(T, p + ireg - 1, jreg - ireg + 1, L, ireg, rows, FM, FI, FD, sf, ef, segscratch,
+                                  reinterpret_cast<int *>(ppN), reinterpret_cast<int *>(ppJ), envl, lane);
+     } else if (lane == 0) { envl[0] = ireg; envl[1] = jreg; }
+     __syncwarp();
+     for (int en = 0; en < nenv; en++) {
+      const int ienv = envl[2 * en], jenv = envl[2 * en + 1];
       const int Ld = jenv - ienv + 1;
       const uint8_t *sub = p + ienv - 1;  // sub[0..Ld-1]
       const XF xf = xf_config(L, 0);
       // ---- unihit Forward, full matrix
-      for (int c = lane; c < 8 * W; c += 32) rows[c] = 0.0f;
-      for (int j = 0; j < B; j++) { FM[j * 32 + lane] = 0.0f; FI[j * 32 + lane] = 0.0f; FD[j * 32 + lane] = 0.0f; }
       int Ze = 0;
       float Zm;
-      {
-        float xN = 1.0f, xB = xf.tNB, xE = 0.0f, xJ = 0.0f, xC = 0.0f;
-        float *wP = rows + 6 * W;
-        if (lane == 0) { Specials s0; s0.xE = 0; s0.xN = xN; s0.xJ = 0; s0.xB = xB; s0.xC = 0; sf[0] = s0; ef[0] = 0; }
-        for (int i = 1; i <= Ld; i++) {
-          float *Mp = FM + (size_t)(i - 1) * W, *Ip = FI + (size_t)(i - 1) * W, *Dp = FD + (size_t)(i - 1) * W;
-          float *Mc = FM + (size_t)i * W, *Ic = FI + (size_t)i * W, *Dc = FD + (size_t)i * W;
-          for (int j = 0; j < B; j++) { Mc[j * 32 + lane] = 0.0f; Ic[j * 32 + lane] = 0.0f; Dc[j * 32 + lane] = 0.0f; }
-          xE = fwd_row(T, sub[i - 1], Mp, Ip, Dp, xB, Mc, Ic, Dc, wP, lane);
-          xN = __fmul_rn(xN, xf.tNN);
-          xJ = __fadd_rn(__fmul_rn(xJ, xf.tJJ), __fmul_rn(xE, xf.tEJ));
-          xC = __fadd_rn(__fmul_rn(xC, xf.tCC), __fmul_rn(xE, xf.tEC));
-          xB = __fadd_rn(__fmul_rn(xJ, xf.tJB), __fmul_rn(xN, xf.tNB));
-          if (xE > PA_RESCALE) {
-            const int e = ilogbf(xE);
-            scale_row(Mc, Ic, Dc, B, lane, e);
-            xN = scalbnf(xN, -e); xJ = scalbnf(xJ, -e); xC = scalbnf(xC, -e); xB = scalbnf(xB, -e); xE = scalbnf(xE, -e);
-            Ze += e;
-          }
-          if (lane == 0) { Specials s; s.xE = xE; s.xN = xN; s.xJ = xJ; s.xB = xB; s.xC = xC; sf[i] = s; ef[i] = Ze; }
-        }
-        Zm = __fmul_rn(xC, xf.tCT);
-      }
+      forward_full(T, sub, Ld, xf, rows, FM, FI, FD, sf, ef, lane, &Ze, &Zm);
       // ---- unihit Backward, full matrix
       for (int c = lane; c < 8 * W; c += 32) rows[c] = 0.0f;
       backward_pass(T, sub, Ld, L, 0, rows, BM, BI, BD, sb, eb, lane);
@@ -601,6 +844,7 @@ __global__ void __launch_bounds__(128) domain_kernel(DomArgs a) {
       }
       ndom++;
       __syncwarp();
+     }
     }
   }
 }

@@ -203,3 +203,36 @@ def test_search_very_long_targets_and_profiles(oracle, gpu_ctx_factory):
     hits, model, aligned = ctx.search()
     assert compare_hits(oracle, hmms, seqs, hits, model, aligned) > 15
     ctx.close()
+
+
+def test_multidomain_regions_are_resolved_by_trace_clustering(oracle, gpu_ctx_factory):
+    """Tandem copies of a profile fragment inside one region trip the rt3 test; the region is split into
+    envelopes by 200 stochastic tracebacks + single-linkage clustering, identically on GPU and oracle."""
+    from phyloaln_b200 import hmmbuild_lite as hb, synth
+    rng = np.random.default_rng(11)
+    hmms = [helpers.calibrated_hmm("tandA", 120, seed=77, bg_mix=0.1, n=40), helpers.calibrated_hmm("tandB", 300, seed=78, bg_mix=0.1, n=40)]
+    seqs = []
+    for t in range(80):
+        h = hmms[t % 2]
+        a = int(rng.integers(1, h.M // 4))
+        b = int(rng.integers(h.M // 2, h.M + 1))
+        ncopy = 2 + (t % 5 == 0)
+        parts = [hb.random_sequences("amino", 1, int(rng.integers(5, 40)), rng)[0]]
+        for c in range(ncopy):
+            parts.append(synth.sample_protein(h, rng, a, b))
+            if t % 2:
+                parts.append(hb.random_sequences("amino", 1, int(rng.integers(0, 12)), rng)[0])
+        parts.append(hb.random_sequences("amino", 1, int(rng.integers(5, 40)), rng)[0])
+        seqs.append("".join(parts))
+    ctx = gpu_ctx_factory()
+    for h in hmms:
+        ctx.add_hmm(h)
+    ctx.commit()
+    ctx.load_proteins(seqs)
+    hits, model, aligned = ctx.search()
+    n = compare_hits(oracle, hmms, seqs, hits, model, aligned)
+    multi = hits[hits["multidomain_region"] == 1]
+    assert len(multi) >= 40 and n >= 150
+    # a flagged region really was split: several domains share it
+    assert (multi["ndom_in_seq"] >= 2).all()
+    ctx.close()
