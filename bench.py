@@ -127,7 +127,7 @@ def cpu_reference_run(hmms, reads, threads: int, seconds_target: float = 15.0):
     """Oracle on the host cores over a bounded sample; returns (reads/s vs ALL profiles, description, gcups)."""
     from oracle import oracle as O
     from phyloaln_b200 import hmmbuild_lite as hb
-    n_h = min(len(hmms), 16)
+    n_h = min(len(hmms), 48)
     sub = hmms[:n_h]
     profs = []
     for h in sub:
@@ -189,7 +189,7 @@ def main():
         if rank != 0:
             return
         threads = os.cpu_count() or 1
-        reads = make_reads(max(2000, args.reads_per_step // 8), hmms, seed=1002)
+        reads = make_reads(max(2000, min(args.reads_per_step, 65536)), hmms, seed=1002)
         vals = []
         desc = ""
         for s in range(args.warmup + args.steps):
