@@ -52,14 +52,14 @@ def make_reads(n: int, hmms, seed: int, frac: float = 0.01):
     return reads
 
 
-def calibrate_on_gpu(ctx, hmms, seed=42, n=200):
+def calibrate_on_gpu(ctx, hmms, seed=42, n=200, abc="amino"):
     """STATS LOCAL for synthetic profiles, scored by the GPU kernels themselves (hmmbuild's job)."""
     import math
     from phyloaln_b200 import hmmbuild_lite as hb
     rng = np.random.default_rng(seed)
-    s200 = hb.random_sequences("amino", n, 200, rng)
-    s100 = hb.random_sequences("amino", n, 100, rng)
-    ntot = ctx.load_proteins(s200 + s100)
+    s200 = hb.random_sequences(abc, n, 200, rng)
+    s100 = hb.random_sequences(abc, n, 100, rng)
+    ntot = ctx.load_proteins(s200 + s100, abc=0 if abc == "amino" else 1)
     for i, h in enumerate(hmms):
         r = ctx.score_all(i, ntot, want=("msv", "vit", "fwd"))
         lam = math.log(2.0) + 1.44 / (h.M * hb.mean_match_relent_bits(h))

@@ -110,6 +110,7 @@ struct pa_ctx {
   DevBuf<Pass1> d_p1;
   DevBuf<Pass2> d_p2a, d_p2b;
   DevBuf<Pass4> d_p4;
+  DevBuf<unsigned long long> d_msvwork;   // per MSV launch: next work item
   DevBuf<unsigned long long> d_counters;  // [0]=p1 [1]=p2a [2]=p2b [3]=p4 [4]=ssv cand [5..] domain
   DomainBufs dom;
 
@@ -179,7 +180,7 @@ extern "C" void pa_destroy(pa_ctx *ctx) {
   ctx->d_lidx.release(); ctx->d_codon.release(); ctx->d_flag.release();
   ctx->d_L.release(); ctx->d_nullsc.release(); ctx->d_biasA.release(); ctx->d_biasB.release(); ctx->d_tjb.release();
   ctx->d_xwmove.release(); ctx->d_thrJ.release(); ctx->d_L2li.release();
-  ctx->d_p1.release(); ctx->d_p2a.release(); ctx->d_p2b.release(); ctx->d_p4.release(); ctx->d_counters.release();
+  ctx->d_p1.release(); ctx->d_p2a.release(); ctx->d_p2b.release(); ctx->d_p4.release(); ctx->d_counters.release(); ctx->d_msvwork.release();
   ctx->dom.release();
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;

@@ -384,6 +384,7 @@ struct MsvArgs {
   const int16_t *thrJ;     // [hmm*nL + li] minimal passing xJ (0..256)
   int nL;
   uint32_t tile;           // targets per work item
+  unsigned long long *work;  // msv_tmem_kernel: next work item (dynamic distribution over CTAs), zeroed per launch
   Pass1 *out;
   unsigned long long *out_count;
   unsigned long long out_cap;

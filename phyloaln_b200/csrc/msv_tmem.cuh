@@ -168,6 +168,7 @@ __global__ void __launch_bounds__(MsvTmemCfg<Q>::THREADS, MsvTmemCfg<Q>::MINB) m
   constexpr int SROW = QS * 32;                       // words per shared-memory row
   extern __shared__ __align__(16) uint32_t s_tab[];  // (nrows + 1) * SROW words (hybrid only)
   __shared__ uint32_t s_slot;
+  __shared__ unsigned long long s_item;
   // the shuffle tells the compiler that the warp index (and everything derived from it: target index,
   // length, loop bounds) is warp-uniform, so shuffles inside those loops need no divergence guards
   const int lane = threadIdx.x & 31, wib = __shfl_sync(PA_FULL, (int)(threadIdx.x >> 5), 0), wpb = blockDim.x >> 5;
@@ -178,7 +179,14 @@ __global__ void __launch_bounds__(MsvTmemCfg<Q>::THREADS, MsvTmemCfg<Q>::MINB) m
   int cur_h = -1;
   unsigned long long ncand = 0;
   const int lanem1 = (lane + 31) & 31;
-  for (unsigned long long item = blockIdx.x; item < nitems; item += gridDim.x) {
+  // work items (profile-major) are handed out through an atomic counter: CTAs finish within one item of
+  // each other, and neighbouring items share the profile, so the TMEM table is refilled rarely
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) s_item = atomicAdd(a.work, 1ull);
+    __syncthreads();
+    const unsigned long long item = s_item;
+    if (item >= nitems) break;
     const int h = a.hmm_list[item / ntiles];
     const uint32_t tile = (uint32_t)(item % ntiles);
     const DevHmm &hm = a.hmms[h];
