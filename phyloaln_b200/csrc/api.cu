@@ -65,6 +65,8 @@ struct pa_ctx {
   std::string err;
   pa_opts opts{0.02, 1e-3, 1e-5, 1, 1, 0, 0};
   cudaStream_t stream = nullptr;
+  cudaStream_t side[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // concurrent per-class launches
+  cudaEvent_t side_ev[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   int num_sms = 148;
   size_t smem_optin = 0;
 
@@ -80,6 +82,7 @@ struct pa_ctx {
   std::map<int, std::pair<int, int>> q_groups;  // Q -> (offset, count) in d_hmm_lists
   int maxB = 1, maxM = 1;
   std::vector<std::pair<int, std::pair<int, int>>> vit_classes;  // (Bv, (first rank, last rank + 1))
+  std::vector<int> rank_B;  // canonical Forward block size B of the profile at each rank (ranks are sorted by B)
   DevBuf<unsigned int> d_sort;  // cnt | start | cursor, each nh + 1
 
   // targets
@@ -182,6 +185,8 @@ extern "C" void pa_destroy(pa_ctx *ctx) {
   ctx->d_xwmove.release(); ctx->d_thrJ.release(); ctx->d_L2li.release();
   ctx->d_p1.release(); ctx->d_p2a.release(); ctx->d_p2b.release(); ctx->d_p4.release(); ctx->d_counters.release(); ctx->d_msvwork.release();
   ctx->dom.release();
+  for (auto &st : ctx->side) if (st) cudaStreamDestroy(st);
+  for (auto &ev : ctx->side_ev) if (ev) cudaEventDestroy(ev);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -377,10 +382,13 @@ extern "C" int pa_commit_hmms(pa_ctx *ctx) {
   {  // profile rank in (Bv, index) order: the sorted survivor list is then contiguous per Viterbi class
     std::vector<int> ord(nh);
     for (int h = 0; h < nh; h++) ord[h] = h;
-    std::stable_sort(ord.begin(), ord.end(), [&](int x, int y) { return ctx->h_dev[x].Bv < ctx->h_dev[y].Bv; });
+    // by B: the Viterbi classes (Bv = class of B, monotone in B) stay contiguous, and so do the exact-B groups of fwd_kernel_t
+    std::stable_sort(ord.begin(), ord.end(), [&](int x, int y) { return ctx->h_dev[x].B < ctx->h_dev[y].B; });
+    ctx->rank_B.assign(nh, 1);
     ctx->vit_classes.clear();
     for (int r = 0; r < nh; r++) {
       ctx->h_dev[ord[r]].rank = r;
+      ctx->rank_B[r] = ctx->h_dev[ord[r]].B;
       const int bv = ctx->h_dev[ord[r]].Bv;
       if (ctx->vit_classes.empty() || ctx->vit_classes.back().first != bv) ctx->vit_classes.push_back({bv, {r, r + 1}});
       else ctx->vit_classes.back().second.second = r + 1;
@@ -703,19 +711,74 @@ static cudaError_t dispatch_msv(pa_ctx *ctx, int Q, MsvArgs &a, int nrows) {
   return cudaErrorInvalidValue;
 }
 
+static cudaError_t side_fork(pa_ctx *ctx);
+static cudaError_t side_join(pa_ctx *ctx);
+
 template <int BT>
-static cudaError_t launch_vit(pa_ctx *ctx, VitArgs &v) {
+static cudaError_t launch_vit(pa_ctx *ctx, VitArgs &v, cudaStream_t st) {
   const unsigned long long n = v.end - v.begin;
   if (n == 0) return cudaSuccess;
   const int grid = (int)std::min<unsigned long long>((n + 3) / 4, (unsigned long long)ctx->num_sms * 16);
-  vit_kernel<BT><<<grid, 128, 0, ctx->stream>>>(v);
+  vit_kernel<BT><<<grid, 128, 0, st>>>(v);
   ctx->stats.kernel_launches++;
   return cudaGetLastError();
 }
-static cudaError_t dispatch_vit(pa_ctx *ctx, int Bv, VitArgs &v) {
+static cudaError_t dispatch_vit(pa_ctx *ctx, int Bv, VitArgs &v, cudaStream_t st) {
   switch (Bv) {
-#define C_(b) case b: return launch_vit<b>(ctx, v);
+#define C_(b) case b: return launch_vit<b>(ctx, v, st);
     C_(1) C_(2) C_(3) C_(4) C_(6) C_(8) C_(10) C_(12) C_(14) C_(16) C_(20) C_(24) C_(28) C_(32) C_(40) C_(48) C_(56) C_(64)
+#undef C_
+  }
+  return cudaErrorInvalidValue;
+}
+
+// Fork: side streams wait for everything queued on the main stream; join: the main stream waits for them.
+// Used to run the per-class launches of one stage concurrently (few, long pairs per class otherwise serialise).
+static cudaError_t side_fork(pa_ctx *ctx) {
+  for (int i = 0; i < 8; i++)
+    if (!ctx->side[i]) { cudaError_t e = cudaStreamCreateWithFlags(&ctx->side[i], cudaStreamNonBlocking); if (e != cudaSuccess) return e; }
+  for (int i = 0; i < 9; i++)
+    if (!ctx->side_ev[i]) { cudaError_t e = cudaEventCreateWithFlags(&ctx->side_ev[i], cudaEventDisableTiming); if (e != cudaSuccess) return e; }
+  cudaError_t e = cudaEventRecord(ctx->side_ev[8], ctx->stream);
+  if (e != cudaSuccess) return e;
+  for (int i = 0; i < 8; i++) { e = cudaStreamWaitEvent(ctx->side[i], ctx->side_ev[8], 0); if (e != cudaSuccess) return e; }
+  return cudaSuccess;
+}
+static cudaError_t side_join(pa_ctx *ctx) {
+  for (int i = 0; i < 8; i++) {
+    cudaError_t e = cudaEventRecord(ctx->side_ev[i], ctx->side[i]);
+    if (e != cudaSuccess) return e;
+    e = cudaStreamWaitEvent(ctx->stream, ctx->side_ev[i], 0);
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+
+template <int B>
+static cudaError_t launch_fwd_t(pa_ctx *ctx, FwdTArgs &a, cudaStream_t st) {
+  const unsigned long long n = a.end - a.begin;
+  if (n == 0) return cudaSuccess;
+  // B <= 32: rows in registers, 4 warps per block. B > 32: 4 shared-memory rows per warp, as many warps as fit in ~96 KB
+  const size_t per_warp = B <= 32 ? 0 : (size_t)4 * B * 32 * 4;
+  int wpb = 4;
+  if (per_warp) wpb = (int)std::max<size_t>(1, std::min<size_t>(4, (96 * 1024) / per_warp));
+  const size_t smem = per_warp * wpb;
+  if (smem) {
+    cudaError_t e = cudaFuncSetAttribute(fwd_kernel_t<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  const int grid = (int)std::min<unsigned long long>((n + wpb - 1) / wpb, (unsigned long long)ctx->num_sms * 32);
+  fwd_kernel_t<B><<<grid, wpb * 32, smem, st>>>(a);
+  ctx->stats.kernel_launches++;
+  return cudaGetLastError();
+}
+static cudaError_t dispatch_fwd_t(pa_ctx *ctx, int B, FwdTArgs &a, cudaStream_t st) {
+  switch (B) {
+#define C_(b) case b: return launch_fwd_t<b>(ctx, a, st);
+    C_(1) C_(2) C_(3) C_(4) C_(5) C_(6) C_(7) C_(8) C_(9) C_(10) C_(11) C_(12) C_(13) C_(14) C_(15) C_(16)
+    C_(17) C_(18) C_(19) C_(20) C_(21) C_(22) C_(23) C_(24) C_(25) C_(26) C_(27) C_(28) C_(29) C_(30) C_(31) C_(32)
+    C_(33) C_(34) C_(35) C_(36) C_(37) C_(38) C_(39) C_(40) C_(41) C_(42) C_(43) C_(44) C_(45) C_(46) C_(47) C_(48)
+    C_(49) C_(50) C_(51) C_(52) C_(53) C_(54) C_(55) C_(56) C_(57) C_(58) C_(59) C_(60) C_(61) C_(62) C_(63) C_(64)
 #undef C_
   }
   return cudaErrorInvalidValue;

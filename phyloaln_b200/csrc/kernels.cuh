@@ -913,26 +913,141 @@ struct FwdArgs {
   int all_pairs;       // score_all: emit every input with its forward result, in input order
 };
 
-__global__ void __launch_bounds__(256) fwd_kernel(FwdArgs a) {
-  extern __shared__ __align__(16) float s_fwd[];
+// ---------------------------------------------------------------------------------------------
+// Forward filter, block size known at compile time (B = ceil(M/32), the canonical lane block).
+// Same arithmetic in the same order as fwd_row/fwd_parser above (and oracle/p7_filters.c), so the
+// scores are bit-identical; what changes is where the row lives and how much the compiler can overlap:
+//   B <= 32  M/I/D/P of the lane's block in registers (4B floats), loops fully unrolled
+//   B  > 32  same code over shared-memory rows [j][lane] (conflict-free), 4 rows per warp instead of 7
+// Pairs arrive sorted by profile, one launch per distinct B.
+template <int B>
+struct FwdRegRows {
+  float m[B], i[B], d[B], p[B];
+  __device__ __forceinline__ FwdRegRows(float *, int) {}
+  __device__ __forceinline__ float &M(int j) { return m[j]; }
+  __device__ __forceinline__ float &I(int j) { return i[j]; }
+  __device__ __forceinline__ float &D(int j) { return d[j]; }
+  __device__ __forceinline__ float &P(int j) { return p[j]; }
+};
+template <int B>
+struct FwdSmemRows {
+  float *b;
+  __device__ __forceinline__ FwdSmemRows(float *base, int lane) : b(base + lane) {}
+  __device__ __forceinline__ float &M(int j) { return b[j * 32]; }
+  __device__ __forceinline__ float &I(int j) { return b[(B + j) * 32]; }
+  __device__ __forceinline__ float &D(int j) { return b[(2 * B + j) * 32]; }
+  __device__ __forceinline__ float &P(int j) { return b[(3 * B + j) * 32]; }
+};
+
+template <int B, class Rows>
+__device__ __forceinline__ int fwd_pair_t(const FwdTabs &T, const uint8_t *p, int L, int lane, float *smem_rows, float *mant) {
+  constexpr int W = B * 32;
+  Rows R(smem_rows, lane);
+#pragma unroll
+  for (int j = 0; j < B; j++) { R.M(j) = 0.0f; R.I(j) = 0.0f; R.D(j) = 0.0f; R.P(j) = 0.0f; }
+  const int nv = min(B, max(0, T.M - lane * B));  // valid cells of this lane
+  const XF xf = xf_config(L, 1);
+  float xN = 1.0f, xB = xf.tNB, xE = 0.0f, xJ = 0.0f, xC = 0.0f;
+  int etot = 0;
+  for (int i = 0; i < L; i++) {
+    const float *em = T.em + (size_t)p[i] * W;
+    float mL = __shfl_up_sync(PA_FULL, R.M(B - 1), 1), iL = __shfl_up_sync(PA_FULL, R.I(B - 1), 1),
+          dL = __shfl_up_sync(PA_FULL, R.D(B - 1), 1);
+    if (lane == 0) mL = iL = dL = 0.0f;
+    // M and I, in place: descending j reads the previous row's j-1 before it is overwritten
+#pragma unroll
+    for (int j = B - 1; j >= 0; j--) {
+      if (j < nv) {
+        const int c = j * 32 + lane;
+        const float4 A = __ldg(T.trA + c);
+        const float4 Bq = __ldg(T.trB + c);
+        const float e = __ldg(em + c);
+        const float pm = j ? R.M(j > 0 ? j - 1 : 0) : mL, pi = j ? R.I(j > 0 ? j - 1 : 0) : iL, pd = j ? R.D(j > 0 ? j - 1 : 0) : dL;
+        float t = __fmul_rn(xB, A.x);
+        t = __fadd_rn(t, __fmul_rn(pm, A.y));
+        t = __fadd_rn(t, __fmul_rn(pi, A.z));
+        t = __fadd_rn(t, __fmul_rn(pd, A.w));
+        const float ni = __fadd_rn(__fmul_rn(R.M(j), Bq.z), __fmul_rn(R.I(j), Bq.w));
+        R.M(j) = __fmul_rn(t, e);
+        R.I(j) = ni;
+      }
+    }
+    // D chain: in-lane serial prefix, scan across lanes, fix-up
+    float mcL = __shfl_up_sync(PA_FULL, R.M(B - 1), 1);
+    if (lane == 0) mcL = 0.0f;
+    float LA = 0.0f, LP = 1.0f;
+#pragma unroll
+    for (int j = 0; j < B; j++) {
+      if (j < nv) {
+        const float4 Bq = __ldg(T.trB + j * 32 + lane);
+        const float a = __fmul_rn(j ? R.M(j > 0 ? j - 1 : 0) : mcL, Bq.x);
+        if (j == 0) { LA = a; LP = Bq.y; }
+        else { LA = __fadd_rn(a, __fmul_rn(LA, Bq.y)); LP = __fmul_rn(LP, Bq.y); }
+        R.D(j) = LA;
+        R.P(j) = LP;
+      }
+    }
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const float a2 = __shfl_up_sync(PA_FULL, LA, o), p2 = __shfl_up_sync(PA_FULL, LP, o);
+      if (lane >= o) { LA = __fadd_rn(LA, __fmul_rn(LP, a2)); LP = __fmul_rn(LP, p2); }
+    }
+    float cin = __shfl_up_sync(PA_FULL, LA, 1);
+    if (lane == 0) cin = 0.0f;
+    float sacc = 0.0f;
+#pragma unroll
+    for (int j = 0; j < B; j++) {
+      if (j < nv) {
+        const float d = __fadd_rn(R.D(j), __fmul_rn(R.P(j), cin));
+        R.D(j) = d;
+        sacc = __fadd_rn(sacc, __fadd_rn(R.M(j), d));
+      }
+    }
+    xE = lane_sum(sacc);
+    xN = __fmul_rn(xN, xf.tNN);
+    xJ = __fadd_rn(__fmul_rn(xJ, xf.tJJ), __fmul_rn(xE, xf.tEJ));
+    xC = __fadd_rn(__fmul_rn(xC, xf.tCC), __fmul_rn(xE, xf.tEC));
+    xB = __fadd_rn(__fmul_rn(xJ, xf.tJB), __fmul_rn(xN, xf.tNB));
+    if (xE > PA_RESCALE) {
+      const int e = ilogbf(xE);
+#pragma unroll
+      for (int j = 0; j < B; j++) { R.M(j) = scalbnf(R.M(j), -e); R.I(j) = scalbnf(R.I(j), -e); R.D(j) = scalbnf(R.D(j), -e); }
+      xN = scalbnf(xN, -e); xJ = scalbnf(xJ, -e); xC = scalbnf(xC, -e); xB = scalbnf(xB, -e); xE = scalbnf(xE, -e);
+      etot += e;
+    }
+  }
+  *mant = __fmul_rn(xC, xf.tCT);
+  return etot;
+}
+
+struct FwdTArgs {
+  FwdArgs f;
+  unsigned long long begin, end;  // range of f.in handled by this launch (all pairs share the block size B)
+};
+
+template <int B>
+__global__ void __launch_bounds__(128) fwd_kernel_t(FwdTArgs a) {
+  extern __shared__ __align__(16) float s_fwdt[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-  float *sm = s_fwd + (size_t)wib * a.maxB * 32 * 7;
-  for (unsigned long long i = (unsigned long long)blockIdx.x * wpb + wib; i < a.n_in; i += (unsigned long long)gridDim.x * wpb) {
-    Pass2 r = a.in[i];
-    const DevHmm &hm = a.hmms[r.h];
-    const FwdTabs T = fwd_tabs(hm, a.tab);
-    const int L = (int)a.tg.len[r.t];
+  float *rows = s_fwdt + (size_t)wib * 4 * B * 32;  // used only when B > 32
+  for (unsigned long long i = a.begin + (unsigned long long)blockIdx.x * wpb + wib; i < a.end; i += (unsigned long long)gridDim.x * wpb) {
+    const Pass2 r = a.f.in[i];
+    const DevHmm &hm = a.f.hmms[r.h];
+    const FwdTabs T = fwd_tabs(hm, a.f.tab);
+    const int L = (int)a.f.tg.len[r.t];
     float mant;
-    const int e = fwd_parser(T, a.tg.dsq + a.tg.off[r.t], L, L, 1, sm, lane, &mant, nullptr, nullptr);
+    int e;
+    if constexpr (B <= 32) e = fwd_pair_t<B, FwdRegRows<B>>(T, a.f.tg.dsq + a.f.tg.off[r.t], L, lane, rows, &mant);
+    else e = fwd_pair_t<B, FwdSmemRows<B>>(T, a.f.tg.dsq + a.f.tg.off[r.t], L, lane, rows, &mant);
     const float fwdsc = (float)((double)e * PA_LN2 + log((double)mant));
     const float seq = (float)((double)(fwdsc - r.filtersc) / PA_LN2);
-    if (lane == 0 && (a.all_pairs || seq >= hm.thrF3)) {
+    if (lane == 0 && (a.f.all_pairs || seq >= hm.thrF3)) {
       Pass4 o;
       o.t = r.t; o.h = r.h; o.pad = 0; o.filtersc = r.filtersc; o.fexp = e; o.fmant = mant;
-      if (a.all_pairs) a.out[i] = o;
+      if (a.f.all_pairs) a.f.out[i] = o;
       else {
-        unsigned long long idx = atomicAdd(a.out_count, 1ull);
-        if (idx < a.out_cap) a.out[idx] = o;
+        unsigned long long idx = atomicAdd(a.f.out_count, 1ull);
+        if (idx < a.f.out_cap) a.f.out[idx] = o;
       }
     }
   }
