@@ -79,7 +79,12 @@ struct pa_ctx {
   DevBuf<int> d_vit;
   DevBuf<float> d_fwd;
   DevBuf<int> d_hmm_lists;
-  std::map<int, std::pair<int, int>> q_groups;  // Q -> (offset, count) in d_hmm_lists
+  std::map<int, std::pair<int, int>> q_groups;  // Q -> (offset, count) in d_hmm_lists (all profiles: score_all / single-profile runs)
+  std::map<int, std::pair<int, int>> q_groups_rest;  // same, profiles that are not in a pack (d_hmm_lists_rest)
+  DevBuf<int> d_hmm_lists_rest;
+  std::vector<DevPack> h_packs;   // packed narrow profiles (msv_pack_kernel)
+  DevBuf<DevPack> d_packs;
+  DevBuf<int> d_packmem;
   int maxB = 1, maxM = 1;
   std::vector<std::pair<int, std::pair<int, int>>> vit_classes;  // (Bv, (first rank, last rank + 1))
   std::vector<int> rank_B;  // canonical Forward block size B of the profile at each rank (ranks are sorted by B)
@@ -178,7 +183,7 @@ extern "C" pa_ctx *pa_create(int device, char *err, int errlen) {
 extern "C" void pa_destroy(pa_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
-  ctx->d_hmms.release(); ctx->d_msv.release(); ctx->d_msvh.release(); ctx->d_vit.release(); ctx->d_fwd.release(); ctx->d_hmm_lists.release(); ctx->d_sort.release();
+  ctx->d_hmms.release(); ctx->d_msv.release(); ctx->d_msvh.release(); ctx->d_vit.release(); ctx->d_fwd.release(); ctx->d_hmm_lists.release(); ctx->d_hmm_lists_rest.release(); ctx->d_packs.release(); ctx->d_packmem.release(); ctx->d_sort.release();
   ctx->d_nt.release(); ctx->d_ntoff.release(); ctx->d_dsq.release(); ctx->d_toff.release(); ctx->d_tlen.release();
   ctx->d_lidx.release(); ctx->d_codon.release(); ctx->d_flag.release();
   ctx->d_L.release(); ctx->d_nullsc.release(); ctx->d_biasA.release(); ctx->d_biasB.release(); ctx->d_tjb.release();
@@ -393,6 +398,82 @@ extern "C" int pa_commit_hmms(pa_ctx *ctx) {
       if (ctx->vit_classes.empty() || ctx->vit_classes.back().first != bv) ctx->vit_classes.push_back({bv, {r, r + 1}});
       else ctx->vit_classes.back().second.second = r + 1;
     }
+  }
+  // ---- packs of narrow profiles for msv_pack_kernel (first-fit decreasing into 64 half-lanes of 16 cells)
+  std::vector<int> packmem;
+  std::vector<char> packed(nh, 0);
+  ctx->h_packs.clear();
+  if (ctx->msv_impl == 0 && getenv("PA_MSV_NOPACK") == nullptr) {
+    const int Kp0 = ctx->hmms[0].Kp;
+    if (msv_tmem_cols_needed(16, Kp0) <= 512) {
+      std::vector<int> cand;
+      for (int h = 0; h < nh; h++)
+        if (ctx->hmms[h].M / 16 + 1 <= 64) cand.push_back(h);
+      std::stable_sort(cand.begin(), cand.end(), [&](int x, int y) { return ctx->hmms[x].M > ctx->hmms[y].M; });
+      std::vector<std::vector<int>> bins;
+      std::vector<int> fill;
+      for (int h : cand) {
+        const int n = ctx->hmms[h].M / 16 + 1;
+        size_t b = 0;
+        while (b < bins.size() && fill[b] + n > 64) b++;
+        if (b == bins.size()) { bins.emplace_back(); fill.push_back(0); }
+        bins[b].push_back(h);
+        fill[b] += n;
+      }
+      for (auto &bin : bins) {
+        DevPack pk;
+        pk.nrows = Kp0;
+        pk.nmem = (int)bin.size();
+        pk.mem_off = (int)packmem.size();
+        while (msvh.size() % 4) msvh.push_back(0);
+        pk.msvh_off = msvh.size();
+        msvh.resize(msvh.size() + (size_t)Kp0 * 16 * 32, 0);
+        uint32_t *tab = msvh.data() + pk.msvh_off;
+        std::vector<int> owner(64, -1), first(64, 0);
+        int s = 0;
+        for (int h : bin) {
+          const int n = ctx->hmms[h].M / 16 + 1;
+          packmem.push_back(h); packmem.push_back(s); packmem.push_back(n);
+          for (int z = 0; z < n; z++) { owner[s + z] = h; first[s + z] = s; }
+          s += n;
+          packed[h] = 1;
+        }
+        for (int x = 0; x < Kp0; x++)
+          for (int q = 0; q < 16; q++)
+            for (int lane = 0; lane < 32; lane++) {
+              uint16_t half[2];
+              for (int hf = 0; hf < 2; hf++) {
+                const int hl = 2 * lane + hf, h = owner[hl];
+                int delta = PA_MSV_DEAD;
+                if (h >= 0) {
+                  const HostProfile &hp = ctx->hmms[h];
+                  const int k = (hl - first[hl]) * 16 + q + 1;
+                  if (k <= hp.M) delta = (int)hp.bias_b - (int)hp.rbv[(size_t)x * (hp.M + 1) + k];
+                }
+                half[hf] = h16_exact(delta);
+              }
+              tab[((size_t)x * 16 + q) * 32 + lane] = (uint32_t)half[0] | ((uint32_t)half[1] << 16);
+            }
+        ctx->h_packs.push_back(pk);
+      }
+    }
+  }
+  CK(ctx->d_packs.ensure(ctx->h_packs.size() + 1));
+  if (!ctx->h_packs.empty()) CK(cudaMemcpy(ctx->d_packs.p, ctx->h_packs.data(), sizeof(DevPack) * ctx->h_packs.size(), cudaMemcpyHostToDevice));
+  CK(ctx->d_packmem.ensure(packmem.size() + 1));
+  if (!packmem.empty()) CK(cudaMemcpy(ctx->d_packmem.p, packmem.data(), packmem.size() * 4, cudaMemcpyHostToDevice));
+  {  // per-Q lists of the profiles that stay on the per-profile kernels
+    std::map<int, std::vector<int>> rest;
+    for (int h = 0; h < nh; h++)
+      if (!packed[h]) rest[ctx->h_dev[h].Q].push_back(h);
+    std::vector<int> lists;
+    ctx->q_groups_rest.clear();
+    for (auto &kv : rest) {
+      ctx->q_groups_rest[kv.first] = {(int)lists.size(), (int)kv.second.size()};
+      lists.insert(lists.end(), kv.second.begin(), kv.second.end());
+    }
+    CK(ctx->d_hmm_lists_rest.ensure(lists.size() + 1));
+    if (!lists.empty()) CK(cudaMemcpy(ctx->d_hmm_lists_rest.p, lists.data(), lists.size() * 4, cudaMemcpyHostToDevice));
   }
   CK(ctx->d_sort.ensure(3 * ((size_t)nh + 1)));
   CK(ctx->d_hmms.ensure(nh));

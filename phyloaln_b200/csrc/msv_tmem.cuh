@@ -316,4 +316,173 @@ __global__ void __launch_bounds__(MsvTmemCfg<Q>::THREADS, MsvTmemCfg<Q>::MINB) m
   tmem_dealloc(tbase, (uint32_t)ncols);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Packed profiles.  The per-row cost of the SSV loop has a fixed part (address shuffle, R2UR, LDTM,
+// carry shuffle, loop) that is amortised over Q words, so narrow profiles run at 55-69 cells/clk/SM
+// while Q = 16 reaches 89.  A *pack* concatenates several profiles into one 1024-cell striped model
+// with Q = 16: profile p owns the half-lanes [s, s + n), n = M/16 + 1, so that (i) every half-lane
+// (16 consecutive cells held by one 16-bit half of a lane) belongs to one profile, (ii) the last cell of
+// every profile is dead padding (delta -20000), which is exactly the u(i-1, 0) = 0 boundary of the next
+// profile's first column, (iii) padding is at most 16 cells per profile instead of 64.  The two 16-bit
+// halves of the running maximum stay separate in VIMNMX3.S16x2, so the per-profile maximum is a masked
+// warp reduction after the last row.  Candidates of a member are re-run with the exact MSV recurrence
+// on the pack's table; only the member's own half-lanes enter its row maximum.
+struct DevPack {
+  unsigned long long msvh_off;  // fp16x2 table [x][q < 16][lane]
+  int nrows, nmem, mem_off;     // members: d_packmem[mem_off + 3*i] = {profile index, first half-lane, half-lanes}
+};
+struct MsvPackArgs {
+  MsvArgs a;  // hmm_list/nlist unused; tab = fp16 pool
+  const DevPack *packs;
+  const int *packmem;
+  int npacks;
+};
+
+template <int G>
+__global__ void __launch_bounds__(1024, 1) msv_pack_kernel(MsvPackArgs pa_, int ncols) {
+  constexpr int Q = 16, QT = 16, LW = 16;
+  const MsvArgs &a = pa_.a;
+  __shared__ uint32_t s_slot;
+  __shared__ unsigned long long s_item;
+  const int lane = threadIdx.x & 31, wib = __shfl_sync(PA_FULL, (int)(threadIdx.x >> 5), 0), wpb = blockDim.x >> 5;
+  const uint32_t tbase = tmem_alloc(&s_slot, (uint32_t)ncols);
+  const uint32_t lanebase = tbase + ((uint32_t)((wib & 3) * 32) << 16);
+  const uint32_t ntiles = (a.tg.n + a.tile - 1) / a.tile;
+  const unsigned long long nitems = (unsigned long long)pa_.npacks * ntiles;
+  int cur_pk = -1;
+  unsigned long long ncand = 0;
+  const int lanem1 = (lane + 31) & 31;
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) s_item = atomicAdd(a.work, 1ull);
+    __syncthreads();
+    const unsigned long long item = s_item;
+    if (item >= nitems) break;
+    const int pk = (int)(item / ntiles);
+    const uint32_t tile = (uint32_t)(item % ntiles);
+    const DevPack pack = pa_.packs[pk];
+    const int nrows = pack.nrows;
+    const int *mem = pa_.packmem + pack.mem_off;
+    if (pk != cur_pk) {
+      tmem_cta_sync();
+      if (wib < 4) {
+        const uint32_t *src = a.tab + pack.msvh_off;
+        for (int x = 0; x < nrows; x++)
+#pragma unroll
+          for (int q = 0; q < QT; q++) tmem_st1(lanebase + x * QT + q, __ldg(src + (x * QT + q) * 32 + lane));
+        const uint32_t dead = int_to_h16x2(PA_MSV_DEAD);
+#pragma unroll
+        for (int q = 0; q < LW; q++) tmem_st1(lanebase + nrows * QT + q, dead);
+        tmem_wait_st();
+      }
+      tmem_cta_sync();
+      cur_pk = pk;
+    }
+    const uint32_t t1 = min(a.tg.n, (tile + 1) * a.tile);
+    uint32_t t = tile * a.tile + wib;
+    int nxL = 0, nxli = 0;
+    uint32_t nxoff = 0;
+    if (t < t1) { nxL = (int)a.tg.len[t]; nxoff = a.tg.off[t]; nxli = a.tg.lidx[t]; }
+    int pre_x = 0;
+    bool have_pre = false;
+    for (; t < t1; t += wpb) {
+      const int L = nxL, li = nxli;
+      const uint8_t *p = a.tg.dsq + nxoff;
+      if (t + wpb < t1) { nxL = (int)a.tg.len[t + wpb]; nxoff = a.tg.off[t + wpb]; nxli = a.tg.lidx[t + wpb]; }
+      else nxL = 0;
+      if (L == 0) { have_pre = false; continue; }
+      // ---- SSV pass over the whole pack
+      uint32_t w[Q];
+#pragma unroll
+      for (int q = 0; q < Q; q++) w[q] = 0;
+      uint32_t m0 = 0, m1 = 0;
+      if (!have_pre) pre_x = lane < L ? (int)p[lane] : nrows;
+      for (int i0 = 0; i0 < L; i0 += 32) {
+        const int nr = min(32, L - i0);
+        const int myx = pre_x;
+        if (i0 + 32 < L) pre_x = i0 + 32 + lane < L ? (int)p[i0 + 32 + lane] : nrows;
+        else { pre_x = lane < nxL ? (int)a.tg.dsq[nxoff + lane] : nrows; have_pre = true; }
+        const uint32_t myaddr = lanebase + (uint32_t)(myx * QT);
+        uint32_t buf[2][G][LW];
+#pragma unroll
+        for (int g = 0; g < G; g++) tmem_ld<LW>(__shfl_sync(PA_FULL, myaddr, g), buf[0][g]);
+#pragma unroll
+        for (int r = 0; r < 32; r += G) {
+          if (r >= nr) break;
+          if (r + G < 32) {
+#pragma unroll
+            for (int g = 0; g < G; g++) tmem_ld<LW>(__shfl_sync(PA_FULL, myaddr, r + G + g), buf[((r / G) & 1) ^ 1][g]);
+          }
+#pragma unroll
+          for (int g = 0; g < G; g++) {
+            tmem_wait_ld<LW>(buf[(r / G) & 1][g]);
+            ssv_row_h2<Q, QT, LW>(w, m0, m1, buf[(r / G) & 1][g], nullptr, lane, lanem1);
+          }
+        }
+      }
+      const uint32_t mm = __vmaxs2(m0, m1);                 // lo: max of half-lane 2*lane, hi: of half-lane 2*lane + 1
+      const int mlo = (int)(short)(mm & 0xffff), mhi = (int)(short)(mm >> 16);
+      const int tjb = a.tjb_li[li];
+      // ---- per member: candidate test, exact MSV re-run
+      for (int mi = 0; mi < pack.nmem; mi++) {
+        const int h = mem[3 * mi], hs = mem[3 * mi + 1], hn = mem[3 * mi + 2];
+        const DevHmm &hm = a.hmms[h];
+        const int bias = hm.bias, base = hm.base, tec = hm.tec, tbm = hm.tbm;
+        const int T = a.thrJ[(size_t)h * a.nL + li];
+        const int tjbm = (tjb + tbm) & 0xff;
+        const int xB0 = max(base - tjbm, 0);
+        const int C = min(255 - bias, min(base + 1 + tec, T + tec));
+        const int Cp = C - xB0;
+        const bool lo_in = (unsigned)(2 * lane - hs) < (unsigned)hn, hi_in = (unsigned)(2 * lane + 1 - hs) < (unsigned)hn;
+        if (Cp > 0) {
+          const int v = max(lo_in ? mlo : 0, hi_in ? mhi : 0);
+          const int U = h16_bits_to_int(__reduce_max_sync(PA_FULL, v));
+          if (U < Cp) continue;
+        }
+        ncand++;
+        const uint32_t keep = (lo_in ? 0x0000ffffu : 0u) | (hi_in ? 0xffff0000u : 0u);
+        int xJ = 0, xB = xB0;
+        bool overflow = false;
+#pragma unroll
+        for (int q = 0; q < Q; q++) w[q] = 0;
+        for (int i = 0; i < L; i++) {
+          const int x = p[i];
+          uint32_t d[LW];
+          tmem_ld<LW>(lanebase + (uint32_t)(x * QT), d);
+          const uint32_t xBv = int_to_h16x2(xB);
+          const uint32_t tt = __shfl_sync(PA_FULL, w[Q - 1], lanem1);
+          const uint32_t carry = __byte_perm(tt, w[Q - 1], 0x5432);
+          tmem_wait_ld<LW>(d);
+          uint32_t rm = 0;
+#pragma unroll
+          for (int q = Q - 1; q >= 1; q--) {
+            w[q] = h2_add_relu(__vmaxs2(w[q - 1], xBv), d[q]);
+            rm = __vmaxs2(rm, w[q]);
+          }
+          w[0] = h2_add_relu(__vmaxs2(carry, xBv), d[0]);
+          rm = __vmaxs2(rm, w[0]) & keep;   // only this member's half-lanes
+          int xE = h16_bits_to_int(warp_max16x2(rm));
+          if (xE >= 255 - bias) { overflow = true; break; }
+          xE = max(xE - tec, 0);
+          xJ = max(xJ, xE);
+          xB = max(max(base, xJ) - tjbm, 0);
+        }
+        if (overflow) xJ = -1;
+        if (overflow || xJ >= T) {
+          if (lane == 0) {
+            unsigned long long idx = atomicAdd(a.out_count, 1ull);
+            if (idx < a.out_cap) {
+              Pass1 r;
+              r.t = t; r.h = (uint16_t)h; r.xJ = (int16_t)xJ;
+              a.out[idx] = r;
+            }
+          }
+        }
+      }
+    }
+  }
+  if (lane == 0 && ncand) atomicAdd(a.n_ssv_cand, ncand);
+  tmem_dealloc(tbase, (uint32_t)ncols);
+}
+
 }  // namespace pa
