@@ -306,7 +306,7 @@ def main():
     ms_stage = {k: float(np.mean([s[k] for s in stats_acc])) for k in
                 ("ms_translate", "ms_msv", "ms_bias", "ms_vit", "ms_fwd", "ms_domain", "ms_domain_kernel", "ms_total")}
     cells_per_step = 296.0 * args.reads_per_step * sumM        # residues/read (50+49+49)*2 x sum of M
-    padded_cells_per_step = 296.0 * args.reads_per_step * sum(64 * (h.M // 64 + 1) for h in hmms)
+    padded_cells_per_step = 296.0 * args.reads_per_step * sum(16 * (h.M // 16 + 1) if h.M < 1024 else 64 * (h.M // 64 + 1) for h in hmms)
     msv_cells_s = cells_per_step / (ms_msv * 1e-3)
     gcups = cells_per_step * world / (tot / args.steps) / 1e9
     last = stats_acc[-1]
@@ -322,7 +322,7 @@ def main():
             # The dominant kernel is bound by instruction issue on the FMA + ALU pipes, not by HBM or the tensor cores
             # (max-plus recurrence with loop-carried dependences; emission table resident in TMEM).  achieved / peak are
             # in the SURVEY 8d unit: algorithmic 4 integer lane-ops per DP cell.
-            "roofline": {"bound": "int_dpx", "kernel": "msv_tmem_kernel<Q,2> (SSV in fp16x2 HFMA2.RELU + VIMNMX3.S16x2, table in TMEM; inline exact MSV)",
+            "roofline": {"bound": "int_dpx", "kernel": "msv_pack_kernel<2> + msv_tmem_kernel<17..32,2> (SSV in fp16x2 HFMA2.RELU + VIMNMX3.S16x2, packed profile tables in TMEM; inline exact MSV)",
                          "achieved": 4.0 * msv_cells_s / 1e12, "peak": 4.0 * peak_cells / 1e12,
                          "unit": "T 16-bit lane-op/s (algorithmic 4 per DP cell)",
                          "frac": msv_cells_s / peak_cells, "traffic": None,
@@ -333,8 +333,11 @@ def main():
                                         "8 HFMA2.RELU + 4 VIMNMX3.S16x2 per 16 cells, registers only",
                          "frac_of_dpx_only_mix_peak": msv_cells_s / peak_cells_dpx,
                          "tmem_read_B_per_clk_per_sm": 2.0 * padded_cells_per_step / (ms_msv * 1e-3) / sm_clk / 148.0,
-                         "binding_resource": "warp instruction issue: ~22.7 issued instructions per 512-cell row of which 12 are the "
-                                             "HFMA2/VIMNMX3 work (ncu: issue active 79 %, fp16 pipe 57 %, ALU 49 %; profiles/)",
+                         "binding_resource": "warp instruction issue + the half-rate HFMA2 pipe: 36.4 issued instructions per 1,024-cell row "
+                                             "of which 24 are the HFMA2/VIMNMX3 work (ncu: issue active 80 %, fp16 pipe 66 %, ALU 54 %; "
+                                             "profiles/r1c_ncu_full_kernels.md)",
+                         "traffic_note": "DRAM traffic is not the bound: ncu dram bytes of the MSV launches = 38.5 MB per 32,768-read step "
+                                         "(targets + tables); the emission tables live in TMEM",
                          "ginstr_per_s": dpx},
             "roofline_translate": tr_roof,
             "stage_ms": ms_stage,
