@@ -236,3 +236,29 @@ def test_multidomain_regions_are_resolved_by_trace_clustering(oracle, gpu_ctx_fa
     # a flagged region really was split: several domains share it
     assert (multi["ndom_in_seq"] >= 2).all()
     ctx.close()
+
+
+def test_packed_profiles_boundaries(oracle, gpu_ctx_factory):
+    """Profile packing (msv_pack_kernel): widths around the 16-cell half-lane and the 1,024-cell pack limits,
+    many tiny profiles in one pack, a profile that fills a pack alone, one that is too wide to be packed."""
+    rng = np.random.default_rng(21)
+    Ms = [1, 2, 15, 16, 17, 31, 32, 33, 47, 48, 63, 64, 65, 127, 128, 500, 1007, 1008, 1023, 1024, 1040]
+    hmms = [helpers.calibrated_hmm(f"pk{M}", M, seed=600 + M, bg_mix=0.1, n=24) for M in Ms]
+    seqs = helpers.protein_targets(hmms, 700, rng, Lmin=5, Lmax=70, plant_every=2)
+    ctx = gpu_ctx_factory()
+    for h in hmms:
+        ctx.add_hmm(h)
+    ctx.commit()
+    ctx.load_proteins(seqs)
+    hits, model, aligned = ctx.search()
+    n = compare_hits(oracle, hmms, seqs, hits, model, aligned)
+    assert n > 100
+    assert len(set(int(x) for x in hits["hmm"])) >= 12   # hits spread over the packed profiles
+    # the funnel counts agree with the oracle as well (every pair, candidate or not)
+    st = ctx.stats()
+    past_msv = 0
+    for h in hmms:
+        _, tr = oracle.Profile.from_hmm(h).search(seqs, nthreads=8)
+        past_msv += int((tr["stage"] >= 1).sum())
+    assert st["n_past_msv"] == past_msv
+    ctx.close()
