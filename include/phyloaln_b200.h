@@ -20,8 +20,10 @@
  *                                loaded profiles against the loaded target chunk.
  *   pa_get_hits                  the information extract_reads() pulls out of the hmmsearch
  *                                text report via Bio.SearchIO (lib/aln.py:511-558).
- *   pa_map_hits                  pretreat_hits()'s terminal trimming + read_hit.__init__'s
- *                                column walk (lib/assemble.py:767-873, 13-306; extend_pos=0).
+ *   pa_map_hits / pa_map_hits_ex pretreat_hits() (short-hit drop, -b outgroup pre-filter, terminal
+ *                                trimming; lib/assemble.py:767-873), read_hit.__init__'s column walk and
+ *                                --extend_pos extension (:13-306) and read_hit.consensus()'s per-column
+ *                                accumulation (:309-633).
  *   pa_score_all                 (no reference equivalent) raw filter scores for every
  *                                (profile, target) pair: E-value calibration and parity tests.
  */
@@ -33,7 +35,7 @@
 extern "C" {
 #endif
 
-#define PA_ABI_VERSION 1
+#define PA_ABI_VERSION 2
 #define PA_AMINO 0
 #define PA_DNA 1
 
@@ -87,7 +89,31 @@ typedef struct {
   int32_t strand;               /* +1 / -1                                                  */
   int32_t col_off, ncols;       /* into base/codon pools: ncols = qend-qstart+1             */
   int32_t unmap_off, n_unmap;   /* into the unmapped-position pool                          */
+  int32_t ext_start, ext_end;   /* columns added by --extend_pos (already inside qstart/qend/ncols) */
 } pa_maprec;
+
+/* options of pa_map_hits_ex = the arguments of pretreat_hits() / read_hit() (lib/assemble.py:767, :13) */
+typedef struct {
+  int32_t trim_pos;        /* --trim_pos (5)                                                  */
+  int32_t extend_pos;      /* --extend_pos (0 = off)                                          */
+  int32_t gencode;         /* --gencode: translation of the flanking codons during extension  */
+  int32_t prefilter;       /* pretreat_hits' `outgroup_score and no_assemble` pre-filter (-b) */
+  double pos_freq;         /* --pos_freq (0.2)                                                */
+  double outgroup_weight;  /* --outgroup_weight (1)                                           */
+} pa_map_opts;
+
+/* optional accumulation request of pa_map_hits_ex = read_hit.consensus() (lib/assemble.py:309-633):
+ * kept hit h adds rep[h] to hist[(bin_row[bin[h]] + col - 1)*96 + k*32 + sym] for every reference column
+ * col it covers (k = codon position 0..2, or 0 in nucleotide mode; sym as in `comp`), records the smallest
+ * contributing hit index in `first` (same shape, INT32_MAX = none; Python dict insertion order) and widens
+ * qrange[2*bin] / qrange[2*bin+1] (min qstart / max qend; caller initialises). bin[h] < 0 = skip. */
+typedef struct {
+  const int32_t *bin, *rep;
+  int32_t nbins;
+  const int64_t *bin_row; /* nbins + 1 */
+  int32_t *hist, *first;  /* bin_row[nbins] * 96 each, host memory, overwritten */
+  int32_t *qrange;        /* nbins * 2, host memory, read and updated           */
+} pa_accum;
 
 int pa_abi_version(void);
 pa_ctx *pa_create(int device, char *err, int errlen);
@@ -151,6 +177,18 @@ int pa_map_hits(pa_ctx *ctx, int32_t nhits, const char *model, const char *align
                 const int32_t *comp, const int64_t *comp_off, const int32_t *ncols_ref, int trim_pos,
                 double pos_freq, pa_maprec *rec, char *base_pool, char *codon_pool, int32_t *unmap_pool,
                 int64_t pool_cols_cap, int64_t unmap_cap);
+/* Same with every option of the reference: --extend_pos extension of untrimmed ends (lib/assemble.py:82-150,
+ * 203-298), the -b outgroup pre-filter (lib/assemble.py:771-798; out_score = get_ref_score()'s outgroup_score as
+ * rows of ncols_ref[h] doubles starting at out_score[out_off[h]], n_out[h] rows incl. PhyloAln_Alt, NaN = the
+ * sequence has no score in that column; may be NULL), and the consensus accumulation (acc may be NULL).
+ * Pools need sum(hmm_to-hmm_from+2 + 2*extend_pos) columns. */
+int pa_map_hits_ex(pa_ctx *ctx, int32_t nhits, const char *model, const char *aligned, const int64_t *ali_off,
+                   const char *reads, const int64_t *read_off, const int32_t *hmm_from, const int32_t *hmm_to,
+                   const int32_t *ali_from, const int32_t *ali_to, const int32_t *frame, const int32_t *strand,
+                   const int32_t *comp, const int64_t *comp_off, const int32_t *ncols_ref, const double *out_score,
+                   const int64_t *out_off, const int32_t *n_out, const pa_map_opts *opts, const pa_accum *acc,
+                   pa_maprec *rec, char *base_pool, char *codon_pool, int32_t *unmap_pool, int64_t pool_cols_cap,
+                   int64_t unmap_cap);
 
 /* ---- native target preparation (host only; replaces the body of prepare_target(), lib/aln.py:274-433,
  * and the text iteration of read_fastx(return_iter=True), lib/library.py:157-176).  Files are inflated and

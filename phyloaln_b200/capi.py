@@ -42,7 +42,17 @@ class PaMapRec(C.Structure):
     _fields_ = [("keep", C.c_int32), ("qstart", C.c_int32), ("qend", C.c_int32), ("ali_from", C.c_int32),
                 ("ali_to", C.c_int32), ("start_trim", C.c_int32), ("end_trim", C.c_int32), ("read_from", C.c_int32),
                 ("read_to", C.c_int32), ("strand", C.c_int32), ("col_off", C.c_int32), ("ncols", C.c_int32),
-                ("unmap_off", C.c_int32), ("n_unmap", C.c_int32)]
+                ("unmap_off", C.c_int32), ("n_unmap", C.c_int32), ("ext_start", C.c_int32), ("ext_end", C.c_int32)]
+
+
+class PaMapOpts(C.Structure):
+    _fields_ = [("trim_pos", C.c_int32), ("extend_pos", C.c_int32), ("gencode", C.c_int32), ("prefilter", C.c_int32),
+                ("pos_freq", C.c_double), ("outgroup_weight", C.c_double)]
+
+
+class PaAccum(C.Structure):
+    _fields_ = [("bin", C.c_void_p), ("rep", C.c_void_p), ("nbins", C.c_int32), ("bin_row", C.c_void_p),
+                ("hist", C.c_void_p), ("first", C.c_void_p), ("qrange", C.c_void_p)]
 
 
 HIT_DTYPE = np.dtype(PaHit)
@@ -50,7 +60,7 @@ MAPREC_DTYPE = np.dtype(PaMapRec)
 
 EXPORTS = ["pa_abi_version", "pa_create", "pa_destroy", "pa_last_error", "pa_set_opts", "pa_add_hmm", "pa_set_evparam",
            "pa_commit_hmms", "pa_num_hmms", "pa_load_reads", "pa_load_proteins", "pa_num_frames", "pa_get_targets",
-           "pa_search", "pa_get_hits", "pa_hit_pool_bytes", "pa_get_stats", "pa_score_all", "pa_map_hits", "pa_microbench_dpx",
+           "pa_search", "pa_get_hits", "pa_hit_pool_bytes", "pa_get_stats", "pa_score_all", "pa_map_hits", "pa_map_hits_ex", "pa_microbench_dpx",
            "pa_profiler_range"]
 
 _lib = None
@@ -93,6 +103,8 @@ def load_library():
     L.pa_get_stats.argtypes = [vp, C.POINTER(PaStats)]
     L.pa_score_all.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp]
     L.pa_map_hits.argtypes = [vp, C.c_int32, C.c_char_p, C.c_char_p, vp, C.c_char_p] + [vp] * 10 + [i32, C.c_double, vp, vp, vp, vp, i64, i64]
+    L.pa_map_hits_ex.argtypes = ([vp, C.c_int32, C.c_char_p, C.c_char_p, vp, C.c_char_p] + [vp] * 13 +
+                                 [C.POINTER(PaMapOpts), C.POINTER(PaAccum), vp, vp, vp, vp, i64, i64])
     L.pa_microbench_dpx.argtypes = [vp, i32, C.POINTER(C.c_double)]
     L.pa_profiler_range.argtypes = [i32]
     _lib = L

@@ -23,7 +23,8 @@
 #include "kernels.cuh"
 #include "msv_tmem.cuh"
 #include "domain.cuh"
-#include "mapping.cuh"
+#include "gencode.hpp"
+#include "ctx_access.hpp"
 #include "profile.hpp"
 
 using namespace pa;
@@ -502,28 +503,6 @@ extern "C" int pa_commit_hmms(pa_ctx *ctx) {
 // ---------------------------------------------------------------------------------------------
 // targets
 // ---------------------------------------------------------------------------------------------
-static const char *kGenCodes[][2] = {
-    {"1", "FFLLSSSSYY**CC*WLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG"},
-    {"2", "FFLLSSSSYY**CCWWLLLLPPPPHHQQRRRRIIMMTTTTNNKKSS**VVVVAAAADDEEGGGG"},
-    {"3", "FFLLSSSSYY**CCWWTTTTPPPPHHQQRRRRIIMMTTTTNNKKSSRRVVVVAAAADDEEGGGG"},
-    {"4", "FFLLSSSSYY**CCWWLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG"},
-    {"5", "FFLLSSSSYY**CCWWLLLLPPPPHHQQRRRRIIMMTTTTNNKKSSSSVVVVAAAADDEEGGGG"},
-    {"6", "FFLLSSSSYYQQCC*WLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG"},
-    {"9", "FFLLSSSSYY**CCWWLLLLPPPPHHQQRRRRIIIMTTTTNNNKSSSSVVVVAAAADDEEGGGG"},
-    {"10", "FFLLSSSSYY**CCCWLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG"},
-    {"11", "FFLLSSSSYY**CC*WLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG"},
-    {"12", "FFLLSSSSYY**CC*WLLLSPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG"},
-    {"13", "FFLLSSSSYY**CCWWLLLLPPPPHHQQRRRRIIMMTTTTNNKKSSGGVVVVAAAADDEEGGGG"},
-    {"14", "FFLLSSSSYYY*CCWWLLLLPPPPHHQQRRRRIIIMTTTTNNNKSSSSVVVVAAAADDEEGGGG"},
-    {"15", "FFLLSSSSYY*QCC*WLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG"},
-    {"16", "FFLLSSSSYY*LCC*WLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG"},
-    {"21", "FFLLSSSSYY**CCWWLLLLPPPPHHQQRRRRIIMMTTTTNNNKSSSSVVVVAAAADDEEGGGG"},
-    {"22", "FFLLSS*SYY*LCC*WLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG"},
-    {"23", "FF*LSSSSYY**CC*WLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG"},
-    {"24", "FFLLSSSSYY**CCWWLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSSKVVVVAAAADDEEGGGG"},
-    {"25", "FFLLSSSSYY**CCGWLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG"},
-    {"26", "FFLLSSSSYY**CC*WLLLAPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG"},
-};
 
 // distinct-length tables + lidx after d_tlen is known; h_tlen must be filled
 static int build_length_tables(pa_ctx *ctx) {
@@ -595,16 +574,7 @@ extern "C" int64_t pa_load_reads(pa_ctx *ctx, const char *nt, const uint64_t *of
   if (ntargets64 >= (1ull << 32)) { ctx->err = "too many targets in one chunk"; return -2; }
   uint8_t tab64[64];
   memset(tab64, 26, 64);
-  if (moltype == PA_TRANSLATE) {
-    const char *aa = nullptr;
-    char key[16];
-    snprintf(key, sizeof(key), "%d", gencode);
-    for (auto &g : kGenCodes)
-      if (!strcmp(g[0], key)) aa = g[1];
-    if (!aa) { ctx->err = "unsupported genetic code table"; return -2; }
-    const char *syms = "ACDEFGHIKLMNPQRSTVWY-BJZOUX*";
-    for (int i = 0; i < 64; i++) tab64[i] = (uint8_t)(strchr(syms, aa[i]) - syms);
-  }
+  if (moltype == PA_TRANSLATE && !codon_table(gencode, tab64)) { ctx->err = "unsupported genetic code table"; return -2; }
   cudaEvent_t e0, e1, e2;
   cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2);
   cudaEventRecord(e0, ctx->stream);
@@ -903,3 +873,11 @@ static int check_targets_ready(pa_ctx *ctx) {
 }
 
 #include "search_impl.inc"
+
+// accessors for the other translation units (ctx_access.hpp)
+cudaStream_t pa_ctx_stream(pa_ctx *ctx) { return ctx->stream; }
+int pa_ctx_device(pa_ctx *ctx) { return ctx->device; }
+int pa_ctx_num_sms(pa_ctx *ctx) { return ctx->num_sms; }
+void pa_ctx_set_error(pa_ctx *ctx, const std::string &msg) { ctx->err = msg; }
+void pa_ctx_count_launches(pa_ctx *ctx, int n) { ctx->stats.kernel_launches += n; }
+

@@ -1,9 +1,11 @@
-"""Hit -> reference-column mapping on the GPU (host wrapper of pa_map_hits).
+"""Hit -> reference-column mapping on the GPU (host wrapper of pa_map_hits_ex).
 
-Drop-in for the per-hit work of the reference's assemble.py main loop with default settings
-(/root/reference/lib/assemble.py:1964-1988): ``pretreat_hits`` (:767-873, terminal trimming) and
-``read_hit.__init__`` (:13-306 with extend_pos=0).  Consensus assembly, outgroup filtering and
-cross-contamination stay on the host as the reference does them.
+Drop-in for the per-hit work of the reference's assemble.py main loop
+(/root/reference/lib/assemble.py:1964-1988): ``pretreat_hits`` (:767-873: short-hit drop, the ``-b``
+outgroup-score pre-filter, terminal trimming), ``read_hit.__init__`` (:13-306, incl. ``--extend_pos``) and,
+for ``-b -z consensus*``, the per-species accumulation of ``read_hit.consensus`` (:309-633).  Contig
+assembly, the outgroup decision on assembled sequences and cross-contamination stay on the host as the
+reference does them.
 """
 from __future__ import annotations
 
@@ -12,6 +14,9 @@ import ctypes as C
 import numpy as np
 
 from . import capi
+
+SYMS = "ABCDEFGHIJKLMNOPQRSTUVWXYZ-*"
+INT_MAX = 2**31 - 1
 
 
 def comp_symbol(ch: str) -> int:
@@ -36,12 +41,18 @@ def composition_table(site_composition: dict) -> np.ndarray:
     return tab
 
 
-def map_hits(ctx: capi.Context, rows, reads: dict, comps: dict, trim_pos: int = 5, pos_freq: float = 0.2):
-    """rows: hit_info.tsv rows (10 fields, any str/int mix); reads: id -> raw nucleotides;
-    comps: query name -> composition_table(). Returns a list of dicts (None = dropped hit)."""
+def outgroup_table(outgroup_score: dict, ncols: int) -> np.ndarray:
+    """get_ref_score()'s outgroup_score {seqid: {col: score}} (incl. 'PhyloAln_Alt') -> float64 [nseq, ncols],
+    NaN where the sequence has no score (column outside its valid ranges)."""
+    tab = np.full((len(outgroup_score), ncols), np.nan, dtype=np.float64)
+    for s, (_, d) in enumerate(outgroup_score.items()):
+        for col, v in d.items():
+            tab[s, int(col) - 1] = float(v)
+    return tab
+
+
+def _run(ctx, rows, reads, comps, trim_pos, pos_freq, extend_pos, gencode, out_scores, outgroup_weight, accum):
     n = len(rows)
-    if n == 0:
-        return []
     genes = sorted({str(r[0]) for r in rows})
     goff, tabs, o = {}, [], 0
     for g in genes:
@@ -63,20 +74,68 @@ def map_hits(ctx: capi.Context, rows, reads: dict, comps: dict, trim_pos: int = 
     frame = np.ascontiguousarray([-1 if str(r[7]) == "None" else int(r[7]) for r in rows], dtype=np.int32)
     comp_off = np.ascontiguousarray([goff[str(r[0])][0] for r in rows], dtype=np.int64)
     ncols_ref = np.ascontiguousarray([goff[str(r[0])][1] for r in rows], dtype=np.int32)
-    cols_cap = int(np.maximum(hmm_to - hmm_from + 1, 0).sum() + n + 8)
+    out_tab = out_off = n_out = None
+    if out_scores:
+        ooff, parts, o = {}, [], 0
+        for g in genes:
+            t = np.ascontiguousarray(out_scores[g], dtype=np.float64)
+            assert t.shape[1] == goff[g][1]
+            ooff[g] = (o, t.shape[0])
+            parts.append(t.ravel())
+            o += t.size
+        out_tab = np.ascontiguousarray(np.concatenate(parts))
+        out_off = np.ascontiguousarray([ooff[str(r[0])][0] for r in rows], dtype=np.int64)
+        n_out = np.ascontiguousarray([ooff[str(r[0])][1] for r in rows], dtype=np.int32)
+    cols_cap = int(np.maximum(hmm_to - hmm_from + 1, 0).sum() + n * (1 + 2 * extend_pos) + 8)
     un_cap = int(3 * ali_off[-1] + 3 * n + 8)
     rec = np.zeros(n, dtype=capi.MAPREC_DTYPE)
     base = np.zeros(cols_cap, np.uint8)
     codon = np.zeros(3 * cols_cap, np.uint8)
     unmap = np.zeros(un_cap, np.int32)
+    opts = capi.PaMapOpts(trim_pos, extend_pos, gencode, 1 if out_scores else 0, pos_freq, outgroup_weight)
     P = capi._ptr
-    rc = ctx.L.pa_map_hits(ctx.h, n, model, aligned, P(ali_off), rdcat, P(read_off), P(hmm_from), P(hmm_to), P(ali_from),
-                           P(ali_to), P(frame), P(strand), P(comp), P(comp_off), P(ncols_ref), trim_pos, C.c_double(pos_freq),
-                           P(rec), P(base), P(codon), P(unmap), cols_cap, un_cap)
-    ctx._check(rc, "pa_map_hits")
+    acc_p, keep_alive = None, None
+    if accum is not None:
+        bins, reps = accum
+        keys = []
+        for r, b in zip(rows, bins):
+            if b is not None and (str(r[0]), b) not in keys:
+                keys.append((str(r[0]), b))
+        kidx = {k: i for i, k in enumerate(keys)}
+        bin_row = np.zeros(len(keys) + 1, np.int64)
+        bin_row[1:] = np.cumsum([goff[k[0]][1] for k in keys])
+        bin_i = np.ascontiguousarray([-1 if b is None else kidx[(str(r[0]), b)] for r, b in zip(rows, bins)], dtype=np.int32)
+        rep_i = np.ascontiguousarray(reps, dtype=np.int32)
+        hist = np.zeros((int(bin_row[-1]), 3, 32), np.int32)
+        first = np.zeros((int(bin_row[-1]), 3, 32), np.int32)
+        qrange = np.empty((max(len(keys), 1), 2), np.int32)
+        qrange[:, 0], qrange[:, 1] = INT_MAX, 0
+        keep_alive = (keys, bin_row, bin_i, rep_i, hist, first, qrange)
+        if keys:
+            acc_p = C.pointer(capi.PaAccum(P(bin_i), P(rep_i), len(keys), P(bin_row), P(hist), P(first), P(qrange)))
+    rc = ctx.L.pa_map_hits_ex(ctx.h, n, model, aligned, P(ali_off), rdcat, P(read_off), P(hmm_from), P(hmm_to), P(ali_from),
+                              P(ali_to), P(frame), P(strand), P(comp), P(comp_off), P(ncols_ref), P(out_tab), P(out_off), P(n_out),
+                              C.byref(opts), acc_p, P(rec), P(base), P(codon), P(unmap), cols_cap, un_cap)
+    ctx._check(rc, "pa_map_hits_ex")
+    return rec, base, codon, unmap, frame, keep_alive
+
+
+def map_hits(ctx: capi.Context, rows, reads: dict, comps: dict, trim_pos: int = 5, pos_freq: float = 0.2, extend_pos: int = 0,
+             gencode: int = 1, out_scores: dict | None = None, outgroup_weight: float = 1.0):
+    """rows: hit_info.tsv rows (10 fields, any str/int mix); reads: id -> raw nucleotides;
+    comps: query name -> composition_table(); out_scores (the reference's `-b` pre-filter): query name ->
+    outgroup_table(). Returns a list of dicts (None = dropped hit)."""
+    if len(rows) == 0:
+        return []
+    rec, base, codon, unmap, frame, _ = _run(ctx, rows, reads, comps, trim_pos, pos_freq, extend_pos, gencode, out_scores,
+                                             outgroup_weight, None)
+    return _records(rec, base, codon, unmap, frame)
+
+
+def _records(rec, base, codon, unmap, frame):
     out = []
     bb, cb = base.tobytes(), codon.tobytes()
-    for h in range(n):
+    for h in range(len(rec)):
         r = rec[h]
         if not r["keep"]:
             out.append(None)
@@ -84,7 +143,51 @@ def map_hits(ctx: capi.Context, rows, reads: dict, comps: dict, trim_pos: int = 
         co, nc = int(r["col_off"]), int(r["ncols"])
         out.append({"qstart": int(r["qstart"]), "qend": int(r["qend"]), "ali_from": int(r["ali_from"]), "ali_to": int(r["ali_to"]),
                     "start_trim": int(r["start_trim"]), "end_trim": int(r["end_trim"]),
+                    "ext_start": int(r["ext_start"]), "ext_end": int(r["ext_end"]),
                     "interval": [int(r["read_from"]), int(r["read_to"]), "+" if r["strand"] > 0 else "-"],
                     "base": bb[co:co + nc].decode(), "codon": cb[3 * co:3 * (co + nc)].decode() if frame[h] >= 0 else None,
                     "unmap": sorted(int(x) for x in unmap[int(r["unmap_off"]):int(r["unmap_off"]) + int(r["n_unmap"])])})
     return out
+
+
+def consensus_hits(ctx: capi.Context, rows, reads: dict, comps: dict, species, reps, trim_pos: int = 5, pos_freq: float = 0.2,
+                   extend_pos: int = 0, gencode: int = 1, out_scores: dict | None = None, outgroup_weight: float = 1.0):
+    """The `-b -z consensus*` branch of the reference's hit loop (lib/assemble.py:1973-1974, 1985-1986): every kept
+    hit of species sp is folded into ONE read_hit per (alignment, sp) by read_hit.consensus (:309-633).
+
+    species[h]: bin label of hit h (None = skip); reps[h]: number of merged duplicate reads it stands for.
+    Returns (per-hit records, {(query, sp): {"qstart", "qend", "seq_comp"}}) where seq_comp has the reference's
+    structure and Python dict insertion order: {col: {1: {nt: n}, 2: {...}, 3: {...}}} (codon modes) or
+    {col: {nt: n}} (nucleotide mode)."""
+    if len(rows) == 0:
+        return [], {}
+    rec, base, codon, unmap, frame, acc = _run(ctx, rows, reads, comps, trim_pos, pos_freq, extend_pos, gencode, out_scores,
+                                               outgroup_weight, (species, reps))
+    keys, bin_row, bin_i, _, hist, first, qrange = acc
+    out = {}
+    for b, key in enumerate(keys):
+        hits = np.nonzero((bin_i == b) & (rec["keep"] != 0))[0]
+        if len(hits) == 0:
+            continue
+        nucl = frame[hits[0]] < 0
+        r0 = int(bin_row[b])
+        H, F = hist[r0:int(bin_row[b + 1])], first[r0:int(bin_row[b + 1])]
+        lo, hi = int(qrange[b, 0]), int(qrange[b, 1])
+        # insertion order of the columns: by first contributing hit, and inside that hit walk / start extension / end extension
+        order = []
+        for col in range(lo, hi + 1):
+            f = int(F[col - 1].min())
+            if f == INT_MAX:
+                continue
+            r = rec[f]
+            q0, q1 = int(r["qstart"]) + int(r["ext_start"]), int(r["qend"]) - int(r["ext_end"])
+            within = (0, col) if q0 <= col <= q1 else ((1, -col) if col < q0 else (2, col))
+            order.append((f, within, col))
+        comp = {}
+        for _, _, col in sorted(order):
+            def one(k):
+                syms = [s for s in range(32) if H[col - 1, k, s]]
+                return {SYMS[s]: int(H[col - 1, k, s]) for s in sorted(syms, key=lambda s: int(F[col - 1, k, s]))}
+            comp[col] = one(0) if nucl else {1: one(0), 2: one(1), 3: one(2)}
+        out[key] = {"qstart": lo, "qend": hi, "seq_comp": comp}
+    return _records(rec, base, codon, unmap, frame), out
