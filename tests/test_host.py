@@ -35,7 +35,7 @@ def test_no_gpu_is_a_loud_error():
 def test_struct_layouts_match_header():
     from phyloaln_b200 import capi
     import ctypes
-    assert ctypes.sizeof(capi.PaHit) == 120 and ctypes.sizeof(capi.PaMapRec) == 56 and ctypes.sizeof(capi.PaOpts) == 40
+    assert ctypes.sizeof(capi.PaHit) == 120 and ctypes.sizeof(capi.PaMapRec) == 64 and ctypes.sizeof(capi.PaMapOpts) == 32 and ctypes.sizeof(capi.PaAccum) == 56 and ctypes.sizeof(capi.PaOpts) == 40
     assert capi.HIT_DTYPE.itemsize == 120
 
 
