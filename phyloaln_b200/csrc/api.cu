@@ -112,6 +112,7 @@ struct pa_ctx {
   DevBuf<float> d_nullsc, d_biasA, d_biasB;
   DevBuf<uint8_t> d_tjb;
   DevBuf<int16_t> d_xwmove, d_thrJ;
+  DevBuf<uint16_t> d_scJ;
   DevBuf<uint16_t> d_L2li;
   int nL = 0;
 
@@ -188,7 +189,7 @@ extern "C" void pa_destroy(pa_ctx *ctx) {
   ctx->d_nt.release(); ctx->d_ntoff.release(); ctx->d_dsq.release(); ctx->d_toff.release(); ctx->d_tlen.release();
   ctx->d_lidx.release(); ctx->d_codon.release(); ctx->d_flag.release();
   ctx->d_L.release(); ctx->d_nullsc.release(); ctx->d_biasA.release(); ctx->d_biasB.release(); ctx->d_tjb.release();
-  ctx->d_xwmove.release(); ctx->d_thrJ.release(); ctx->d_L2li.release();
+  ctx->d_xwmove.release(); ctx->d_thrJ.release(); ctx->d_scJ.release(); ctx->d_L2li.release();
   ctx->d_p1.release(); ctx->d_p2a.release(); ctx->d_p2b.release(); ctx->d_p4.release(); ctx->d_counters.release(); ctx->d_msvwork.release();
   ctx->dom.release();
   for (auto &st : ctx->side) if (st) cudaStreamDestroy(st);
@@ -439,6 +440,7 @@ extern "C" int pa_commit_hmms(pa_ctx *ctx) {
           s += n;
           packed[h] = 1;
         }
+        for (int hl = 0; hl < 64; hl++) packmem.push_back(owner[hl]);  // per half-lane owner, read by msv_pack_kernel
         for (int x = 0; x < Kp0; x++)
           for (int q = 0; q < 16; q++)
             for (int lane = 0; lane < 32; lane++) {
@@ -853,8 +855,9 @@ static int sort_by_profile(pa_ctx *ctx, const Pass2 *in, Pass2 *out, unsigned lo
 static int launch_thresholds(pa_ctx *ctx, int all_pass) {
   const int nh = (int)ctx->hmms.size();
   CK(ctx->d_thrJ.ensure((size_t)nh * ctx->nL));
+  CK(ctx->d_scJ.ensure((size_t)nh * ctx->nL));
   const int n = nh * ctx->nL;
-  msv_threshold_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_hmms.p, nh, make_lentabs(ctx), ctx->d_thrJ.p, all_pass);
+  msv_threshold_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_hmms.p, nh, make_lentabs(ctx), ctx->d_thrJ.p, ctx->d_scJ.p, all_pass);
   ctx->stats.kernel_launches++;
   return 0;
 }

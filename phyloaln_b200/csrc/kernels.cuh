@@ -16,6 +16,7 @@
 // k = l*B+1 .. (l+1)*B, B = ceil(M/32); per-profile tables are stored [j][lane] so that every
 // table access of a warp is one fully coalesced 128/512-byte request.
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -382,6 +383,7 @@ struct MsvArgs {
   Targets tg;
   const uint8_t *tjb_li;   // per length index
   const int16_t *thrJ;     // [hmm*nL + li] minimal passing xJ (0..256)
+  const uint16_t *scJ;     // [hmm*nL + li] fp16 bits of the sticky-SSV scale 32*ceil(2048/Cp) (Cp = 1: +inf; Cp <= 0: 0xffff)
   int nL;
   uint32_t tile;           // targets per work item
   unsigned long long *work;  // msv_tmem_kernel: next work item (dynamic distribution over CTAs), zeroed per launch
@@ -511,7 +513,7 @@ __global__ void __launch_bounds__(256, 2) msv_kernel(MsvArgs a) {
 }
 
 // per (profile, length) minimal passing MSV xJ byte
-__global__ void msv_threshold_kernel(const DevHmm *hmms, int nh, LenTabs lt, int16_t *thrJ, int all_pass) {
+__global__ void msv_threshold_kernel(const DevHmm *hmms, int nh, LenTabs lt, int16_t *thrJ, uint16_t *scJ, int all_pass) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= nh * lt.n) return;
   int h = idx / lt.n, li = idx % lt.n;
@@ -528,6 +530,16 @@ __global__ void msv_threshold_kernel(const DevHmm *hmms, int nh, LenTabs lt, int
   }
   if (all_pass) T = 0;
   thrJ[idx] = (int16_t)T;
+  // candidate threshold of the SSV pass (same expression as in the MSV kernels) -> sticky scale
+  const int tjbm = (tjb + hm.tbm) & 0xff;
+  const int xB0 = max(hm.base - tjbm, 0);
+  const int C = min(255 - hm.bias, min(hm.base + 1 + hm.tec, T + hm.tec));
+  const int Cp = C - xB0;
+  uint16_t sc;
+  if (Cp <= 0) sc = 0xffffu;
+  else if (Cp == 1) sc = 0x7c00u;
+  else sc = __half_as_ushort(__int2half_rn(32 * ((2048 + Cp - 1) / Cp)));
+  scJ[idx] = sc;
 }
 
 __device__ __forceinline__ float msv_score_from_xJ(const DevHmm &hm, int xJ, int tjb) {

@@ -157,6 +157,43 @@ __device__ __forceinline__ void ssv_row_h2(uint32_t (&w)[Q], uint32_t &m0, uint3
   if (Q & 1) m1 = __vmaxs2(m1, w[Q - 1]);
 }
 
+// relu(d * s + c) on two fp16 lanes: HFMA2.RELU d, s, c
+__device__ __forceinline__ uint32_t h2_fma_relu(uint32_t d, uint32_t s, uint32_t c) {
+  uint32_t r;
+  asm("fma.rn.relu.f16x2 %0, %1, %2, %3;" : "=r"(r) : "r"(d), "r"(s), "r"(c));
+  return r;
+}
+
+// "Sticky" SSV row: no running maximum at all.  Cell values are kept as n * 32 with n = u * m, m = ceil(2048 / Cp)
+// (Cp = the pair's candidate threshold, 2..255): n < 2048 is an exact fp16 integer multiple of 32, and the first
+// cell whose true value reaches u >= ceil(2048 / m) (<= Cp) produces n * 32 >= 65536, which rounds to +inf.  inf is
+// absorbing under fma with a finite product, so it rides down the diagonal (through dead cells, around the striped
+// model) until the last row, where one look at the registers tells whether ANY cell of the pair reached the
+// threshold.  The scale s = m * 32 is the second fma operand (the table keeps the plain deltas), so the row is
+// 16 HFMA2 + the carry for 1,024 cells instead of 16 HFMA2 + 8 VIMNMX3.  A pair flagged this way is a superset of
+// the exact candidate set (threshold ceil(2048 / m) <= Cp); candidates are re-run with the exact recurrence.
+template <int Q, int QT, int LW>
+__device__ __forceinline__ void ssv_row_sticky(uint32_t (&w)[Q], const uint32_t sc, const uint32_t (&dt)[LW], const uint32_t *srow,
+                                               int lane, int lanem1) {
+  constexpr int QS = Q - QT;
+  uint32_t ds[QS > 0 ? QS : 1];
+  if constexpr (QS > 0) msv_load_row<QS>(srow, lane, ds);
+  const uint32_t tt = __shfl_sync(PA_FULL, w[Q - 1], lanem1);
+  const uint32_t carry = __byte_perm(tt, w[Q - 1], 0x5432);
+#pragma unroll
+  for (int q = Q - 1; q >= 1; q--) w[q] = h2_fma_relu(q < QT ? dt[q < QT ? q : 0] : ds[q >= QT ? q - QT : 0], sc, w[q - 1]);
+  w[0] = h2_fma_relu(dt[0], sc, carry);
+}
+// max over the row registers, as fp16 bit patterns (all values >= 0; +inf = 0x7c00, NaN = 0x7fff)
+template <int Q>
+__device__ __forceinline__ uint32_t row_max_bits(const uint32_t (&w)[Q]) {
+  uint32_t m = w[0];
+#pragma unroll
+  for (int q = 1; q + 1 < Q; q += 2) m = __vimax3_s16x2(m, w[q], w[q + 1]);
+  if ((Q & 1) == 0) m = __vmaxs2(m, w[Q - 1]);
+  return m;
+}
+
 // G rows per prefetch group (double-buffered): the LDTMs of group g+1 are in flight while group g
 // is computed.  The residues of the next 32-row block (of this target or of the warp's next target)
 // and the next target's metadata are fetched one block ahead, so no global-memory latency sits on
@@ -236,7 +273,7 @@ __global__ void __launch_bounds__(MsvTmemCfg<Q>::THREADS, MsvTmemCfg<Q>::MINB) m
         // ---- SSV pass: u(i,k) = relu(u(i-1,k-1) + delta(x_i,k)), running max over all cells
 #pragma unroll
         for (int q = 0; q < Q; q++) w[q] = 0;
-        uint32_t m0 = 0, m1 = 0;
+        const uint32_t sc = (uint32_t)a.scJ[(size_t)h * a.nL + li] * 0x10001u;
         if (!have_pre) pre_x = lane < L ? (int)p[lane] : nrows;
         for (int i0 = 0; i0 < L; i0 += 32) {
           const int nr = min(32, L - i0);
@@ -262,12 +299,12 @@ __global__ void __launch_bounds__(MsvTmemCfg<Q>::THREADS, MsvTmemCfg<Q>::MINB) m
               const uint32_t *srow = s_tab;
               if constexpr (QS > 0) srow = s_tab + __shfl_sync(PA_FULL, myx, r + g) * SROW;
               tmem_wait_ld<LW>(buf[(r / G) & 1][g]);
-              ssv_row_h2<Q, QT, LW>(w, m0, m1, buf[(r / G) & 1][g], srow, lane, lanem1);
+              ssv_row_sticky<Q, QT, LW>(w, sc, buf[(r / G) & 1][g], srow, lane, lanem1);
             }
           }
         }
-        const int U = h16_bits_to_int(warp_max16x2(__vmaxs2(m0, m1)));
-        if (U < Cp) continue;
+        const uint32_t mx = row_max_bits<Q>(w);
+        if (!__any_sync(PA_FULL, (mx & 0xffffu) >= 0x7c00u || (mx >> 16) >= 0x7c00u)) continue;
       } else
         have_pre = false;
       ncand++;
@@ -363,6 +400,8 @@ __global__ void __launch_bounds__(1024, 1) msv_pack_kernel(MsvPackArgs pa_, int 
     const DevPack pack = pa_.packs[pk];
     const int nrows = pack.nrows;
     const int *mem = pa_.packmem + pack.mem_off;
+    // owners of this lane's two half-lanes (-1: none), after the member triples
+    const int own_lo = mem[3 * pack.nmem + 2 * lane], own_hi = mem[3 * pack.nmem + 2 * lane + 1];
     if (pk != cur_pk) {
       tmem_cta_sync();
       if (wib < 4) {
@@ -395,7 +434,11 @@ __global__ void __launch_bounds__(1024, 1) msv_pack_kernel(MsvPackArgs pa_, int 
       uint32_t w[Q];
 #pragma unroll
       for (int q = 0; q < Q; q++) w[q] = 0;
-      uint32_t m0 = 0, m1 = 0;
+      // per half-lane scale of its owner for this length (0xffff: the owner takes every pair, Cp <= 0)
+      const uint32_t sc_lo = own_lo >= 0 ? (uint32_t)a.scJ[(size_t)own_lo * a.nL + li] : 0u;
+      const uint32_t sc_hi = own_hi >= 0 ? (uint32_t)a.scJ[(size_t)own_hi * a.nL + li] : 0u;
+      const uint32_t sc = sc_lo | (sc_hi << 16);
+      const bool always = __any_sync(PA_FULL, sc_lo == 0xffffu || sc_hi == 0xffffu);
       if (!have_pre) pre_x = lane < L ? (int)p[lane] : nrows;
       for (int i0 = 0; i0 < L; i0 += 32) {
         const int nr = min(32, L - i0);
@@ -416,12 +459,20 @@ __global__ void __launch_bounds__(1024, 1) msv_pack_kernel(MsvPackArgs pa_, int 
 #pragma unroll
           for (int g = 0; g < G; g++) {
             tmem_wait_ld<LW>(buf[(r / G) & 1][g]);
-            ssv_row_h2<Q, QT, LW>(w, m0, m1, buf[(r / G) & 1][g], nullptr, lane, lanem1);
+            ssv_row_sticky<Q, QT, LW>(w, sc, buf[(r / G) & 1][g], nullptr, lane, lanem1);
           }
         }
       }
-      const uint32_t mm = __vmaxs2(m0, m1);                 // lo: max of half-lane 2*lane, hi: of half-lane 2*lane + 1
-      const int mlo = (int)(short)(mm & 0xffff), mhi = (int)(short)(mm >> 16);
+      // half-lanes that hold an absorbed +inf after the last row: bit 2*lane (+1)
+      const uint32_t mx = row_max_bits<Q>(w);
+      const uint32_t even = __ballot_sync(PA_FULL, (mx & 0xffffu) >= 0x7c00u && sc_lo != 0xffffu);
+      const uint32_t odd = __ballot_sync(PA_FULL, (mx >> 16) >= 0x7c00u && sc_hi != 0xffffu);
+      if ((even | odd) == 0u && !always) continue;
+      unsigned long long hot = 0;
+      for (int b = 0; b < 32; b++) hot |= ((unsigned long long)((even >> b) & 1u) << (2 * b)) | ((unsigned long long)((odd >> b) & 1u) << (2 * b + 1));
+      // an inf seen in cell c was born at most L-1 cells up the diagonal: a member owning half-lanes [hs, hs+hn) is a
+      // candidate iff some hot half-lane lies in [hs, hs + hn + ceil((L-1)/16)] (cyclic over the 64 half-lanes)
+      const int reach = (L + 14) / 16;
       const int tjb = a.tjb_li[li];
       // ---- per member: candidate test, exact MSV re-run
       for (int mi = 0; mi < pack.nmem; mi++) {
@@ -435,9 +486,10 @@ __global__ void __launch_bounds__(1024, 1) msv_pack_kernel(MsvPackArgs pa_, int 
         const int Cp = C - xB0;
         const bool lo_in = (unsigned)(2 * lane - hs) < (unsigned)hn, hi_in = (unsigned)(2 * lane + 1 - hs) < (unsigned)hn;
         if (Cp > 0) {
-          const int v = max(lo_in ? mlo : 0, hi_in ? mhi : 0);
-          const int U = h16_bits_to_int(__reduce_max_sync(PA_FULL, v));
-          if (U < Cp) continue;
+          const int cnt = hn + reach;
+          const unsigned long long win0 = cnt >= 64 ? ~0ull : ((1ull << cnt) - 1ull);
+          const unsigned long long win = hs ? ((win0 << hs) | (win0 >> (64 - hs))) : win0;
+          if ((hot & win) == 0ull) continue;
         }
         ncand++;
         const uint32_t keep = (lo_in ? 0x0000ffffu : 0u) | (hi_in ? 0xffff0000u : 0u);
