@@ -221,8 +221,9 @@ def main():
     # measured integer-pipe peak (thread-instructions/s); lane-ops = 2 per packed instruction
     dpx = {m: ctx.microbench_dpx(i) for i, m in enumerate(["viaddmnmx_s16x2_relu", "vimnmx3_s16x2", "ssv_mix_dpx", "viaddmnmx_s32",
                                                            "hfma2_relu", "ssv_mix_hfma2"])}
-    # issue-rate ceiling of the SSV inner loop (registers only, no table fetch): 12 instructions = 16 cells
-    peak_cells = dpx["ssv_mix_hfma2"] * 1e9 * 16.0 / 12.0
+    # ceiling of the SSV inner loop (registers only, no table fetch): one half-rate HFMA2.RELU per two cells
+    peak_cells = dpx["hfma2_relu"] * 1e9 * 2.0
+    peak_cells_mix = dpx["ssv_mix_hfma2"] * 1e9 * 16.0 / 12.0   # the earlier loop: 8 HFMA2 + 4 VIMNMX3 per 16 cells
     peak_cells_dpx = dpx["ssv_mix_dpx"] * 1e9 * 16.0 / 12.0
 
     nsteps = args.warmup + args.steps
@@ -322,20 +323,20 @@ def main():
             # The dominant kernel is bound by instruction issue on the FMA + ALU pipes, not by HBM or the tensor cores
             # (max-plus recurrence with loop-carried dependences; emission table resident in TMEM).  achieved / peak are
             # in the SURVEY 8d unit: algorithmic 4 integer lane-ops per DP cell.
-            "roofline": {"bound": "int_dpx", "kernel": "msv_pack_kernel<2> + msv_tmem_kernel<17..32,2> (SSV in fp16x2 HFMA2.RELU + VIMNMX3.S16x2, packed profile tables in TMEM; inline exact MSV)",
+            "roofline": {"bound": "int_dpx", "kernel": "msv_pack_kernel<2> + msv_tmem_kernel<17..32,2> (sticky-inf SSV: one fp16x2 HFMA2.RELU per two cells, no running maximum; packed profile tables in TMEM; inline exact MSV)",
                          "achieved": 4.0 * msv_cells_s / 1e12, "peak": 4.0 * peak_cells / 1e12,
                          "unit": "T 16-bit lane-op/s (algorithmic 4 per DP cell)",
                          "frac": msv_cells_s / peak_cells, "traffic": None,
                          "msv_gcups": msv_cells_s / 1e9,
                          "useful_cells_per_clk_per_sm": msv_cells_s / sm_clk / 148.0,
                          "padded_cells_per_clk_per_sm": padded_cells_per_step / (ms_msv * 1e-3) / sm_clk / 148.0,
-                         "peak_source": "measured in this run (pa_microbench_dpx mode 5): issue rate of the kernel's own inner-loop mix, "
-                                        "8 HFMA2.RELU + 4 VIMNMX3.S16x2 per 16 cells, registers only",
+                         "peak_source": "measured in this run (pa_microbench_dpx mode 4): issue rate of HFMA2.RELU (half rate on the FMA pipe), "
+                                        "the only per-cell instruction of the SSV loop, x 2 cells, registers only",
+                         "frac_of_hfma2_vimnmx3_mix_peak": msv_cells_s / peak_cells_mix,
                          "frac_of_dpx_only_mix_peak": msv_cells_s / peak_cells_dpx,
                          "tmem_read_B_per_clk_per_sm": 2.0 * padded_cells_per_step / (ms_msv * 1e-3) / sm_clk / 148.0,
-                         "binding_resource": "warp instruction issue + the half-rate HFMA2 pipe: 36.4 issued instructions per 1,024-cell row "
-                                             "of which 24 are the HFMA2/VIMNMX3 work (ncu: issue active 80 %, fp16 pipe 66 %, ALU 54 %; "
-                                             "profiles/r1c_ncu_full_kernels.md)",
+                         "binding_resource": "the half-rate HFMA2 pipe (16 HFMA2.RELU per 1,024-cell warp row = 32 pipe cycles) and warp "
+                                             "instruction issue (profiles/r1d_ncu_full_kernels.md)",
                          "traffic_note": "DRAM traffic is not the bound: ncu dram bytes of the MSV launches = 38.5 MB per 32,768-read step "
                                          "(targets + tables); the emission tables live in TMEM",
                          "ginstr_per_s": dpx},
