@@ -147,6 +147,9 @@ int64_t pa_search(pa_ctx *ctx);
 int64_t pa_get_hits(pa_ctx *ctx, pa_hit *hits, int64_t cap, char *model_pool, char *target_pool,
                     int64_t poolcap);
 int64_t pa_hit_pool_bytes(pa_ctx *ctx); /* bytes needed for each string pool of pa_get_hits */
+/* posterior-probability annotation of every alignment (the "PP" line of the hmmsearch text report: '0'..'9', '*',
+ * '.' for deletes), same offsets/lengths as the pools of pa_get_hits. Returns bytes written or <0. */
+int64_t pa_get_hit_pp(pa_ctx *ctx, char *pp_pool, int64_t poolcap);
 int pa_get_stats(pa_ctx *ctx, pa_stats *st);
 
 /* Raw filter scores (nats) of profile `hmm` for all loaded targets; any output may be NULL.

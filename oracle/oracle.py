@@ -213,7 +213,7 @@ class Profile:
         dsq = np.zeros(max(1, len(cat)), dtype=np.uint8)
         self.L.orc_digitize(self.abc, cat, len(cat), dsq.ctypes.data)
         maxhits = max(1024, 4 * n)
-        poolcap = max(1 << 20, 8 * len(cat) + 4 * self.M * 64)
+        poolcap = max(1 << 20, 16 * len(cat) + 8 * self.M * 64)
         hits = (OrcHit * maxhits)()
         mp, tp = C.create_string_buffer(poolcap), C.create_string_buffer(poolcap)
         tr = (OrcTrace * max(1, n))() if want_trace else None
@@ -228,6 +228,7 @@ class Profile:
             # string_at copies just the slice; `.raw` would copy the whole pool for every hit
             d["model"] = C.string_at(C.addressof(mp) + h.ali_off, h.ali_len).decode()
             d["aligned"] = C.string_at(C.addressof(tp) + h.ali_off, h.ali_len).decode()
+            d["pp"] = C.string_at(C.addressof(tp) + h.ali_off + h.ali_len + 1, h.ali_len).decode()
             out.append(d)
         trace = None
         if want_trace:

@@ -99,7 +99,12 @@ static void tr_push(TRACE *t, char st, int k, int i) {
 
 /* Rescore dsq[ienv..jenv] (1-based, inside the full target dsq[1..L]) in unihit mode with the
  * length model of the full target. Fills dom; n2sc[ienv..jenv] set (null2 by expectation).
- * model/target receive HMMER-style alignment lines (NUL-terminated). Returns 0, or 1 if no M state. */
+ * model/target receive HMMER-style alignment lines (NUL-terminated); the posterior-probability line (HMMER's "PP"
+ * annotation: p7_alidisplay_EncodePostProb, '.' for deletes) follows target's NUL, so a domain takes 2*(ali_len+1)
+ * bytes of each pool. Returns 0, or 1 if no M state. */
+/* HMMER's p7_alidisplay_EncodePostProb */
+static char p7d_pp_char(float p) { return (p + 0.05 >= 1.0) ? '*' : (char)((int)((p + 0.05) * 10.0) + '0'); }
+
 int p7d_rescore_envelope(const ORC_PROFILE *p, const uint8_t *dsq, int L, int ienv, int jenv, int do_null2,
                          float *n2sc, P7D_DOMAIN *dom, char *model, char *target, int alicap) {
   int M = p->M, Ld = jenv - ienv + 1;
@@ -331,28 +336,37 @@ int p7d_rescore_envelope(const ORC_PROFILE *p, const uint8_t *dsq, int L, int ie
     rc = 1;
     dom->ali_len = 0;
     model[0] = target[0] = 0;
+    if (alicap > 1) model[1] = target[1] = 0;
   } else {
     int n = 0;
     dom->hmmfrom = tr.k[z1];
     dom->hmmto = tr.k[z2];
     dom->iali = tr.i[z1] + ienv - 1;
     dom->jali = tr.i[z2] + ienv - 1;
-    for (int z = z1; z <= z2 && n < alicap - 1; z++) {
+    char *pp = (char *)malloc((size_t)alicap);
+    for (int z = z1; z <= z2 && 2 * (n + 1) < alicap - 1; z++) {
       char st = tr.st[z];
       if (st == 'M') {
         model[n] = p->hmm->cons[tr.k[z]];
         target[n] = (char)toupper((unsigned char)orc_sym(p->abc, sub[tr.i[z]]));
+        pp[n] = p7d_pp_char(bx.M[(size_t)tr.i[z] * W + tr.k[z]]);
       } else if (st == 'I') {
         model[n] = '.';
         target[n] = (char)tolower((unsigned char)orc_sym(p->abc, sub[tr.i[z]]));
+        pp[n] = p7d_pp_char(bx.I[(size_t)tr.i[z] * W + tr.k[z]]);
       } else if (st == 'D') {
         model[n] = p->hmm->cons[tr.k[z]];
         target[n] = '-';
+        pp[n] = '.';
       } else
         continue;
       n++;
     }
     model[n] = target[n] = 0;
+    memcpy(target + n + 1, pp, (size_t)n);
+    target[2 * n + 1] = 0;
+    memset(model + n + 1, 0, (size_t)n + 1);
+    free(pp);
     dom->ali_len = n;
   }
   free(tr.st); free(tr.k); free(tr.i);
@@ -596,13 +610,13 @@ int p7d_define_domains(const ORC_PROFILE *p, const uint8_t *dsq, int L, int do_n
       env_i[0] = i; env_j[0] = j;
       if (multi) nenv = p7d_resolve_multidomain(p, dsq, L, i, j, env_i, env_j, P7D_MAXENV);
       for (int e = 0; e < nenv; e++)
-        if (ndom < maxdom && poolcap - used > 2 * (env_j[e] - env_i[e] + 1) + 2 * p->M + 8) {
+        if (ndom < maxdom && poolcap - used > 4 * (env_j[e] - env_i[e] + 1) + 4 * p->M + 16) {
           P7D_DOMAIN *d = &doms[ndom];
           d->multidomain_region = multi;
           d->ali_off = used;
           int rc = p7d_rescore_envelope(p, dsq, L, env_i[e], env_j[e], do_null2, n2sc, d, model + used, target + used, poolcap - used);
           if (rc == 0) {
-            used += d->ali_len + 1;
+            used += 2 * (d->ali_len + 1);
             ndom++;
           }
         }

@@ -144,7 +144,7 @@ static int one_target(const ORC_PROFILE *p, const uint8_t *seq, int L, int tidx,
         h->fwdsc = fwdsc; h->nullsc = nullsc; h->seq_lnP = lnP;
         h->ali_off = doms[d].ali_off; h->ali_len = doms[d].ali_len;
         h->multidomain_region = doms[d].multidomain_region;
-        *pool_used = doms[d].ali_off + doms[d].ali_len + 1;
+        *pool_used = doms[d].ali_off + 2 * (doms[d].ali_len + 1);
       }
     }
     free(n2sc);
@@ -169,7 +169,7 @@ int orc_search(const ORC_PROFILE *p, const uint8_t *dsq, const int64_t *off, int
 #pragma omp parallel for schedule(dynamic, 64) num_threads(nthreads)
   for (int t = 0; t < n; t++) {
     int L = (int)(off[t + 1] - off[t]);
-    int cap = 4 * L + 4 * p->M + 64;
+    int cap = 8 * L + 8 * p->M + 128;
     ORC_HIT tmp[MAXDOM_PER_SEQ];
     char *m = (char *)malloc((size_t)cap), *g = (char *)malloc((size_t)cap);
     int pu = 0;

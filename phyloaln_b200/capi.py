@@ -60,7 +60,7 @@ MAPREC_DTYPE = np.dtype(PaMapRec)
 
 EXPORTS = ["pa_abi_version", "pa_create", "pa_destroy", "pa_last_error", "pa_set_opts", "pa_add_hmm", "pa_set_evparam",
            "pa_commit_hmms", "pa_num_hmms", "pa_load_reads", "pa_load_proteins", "pa_num_frames", "pa_get_targets",
-           "pa_search", "pa_get_hits", "pa_hit_pool_bytes", "pa_get_stats", "pa_score_all", "pa_map_hits", "pa_map_hits_ex", "pa_microbench_dpx",
+           "pa_search", "pa_get_hits", "pa_get_hit_pp", "pa_hit_pool_bytes", "pa_get_stats", "pa_score_all", "pa_map_hits", "pa_map_hits_ex", "pa_microbench_dpx",
            "pa_profiler_range"]
 
 _lib = None
@@ -98,6 +98,8 @@ def load_library():
     L.pa_search.argtypes = [vp]
     L.pa_get_hits.restype = i64
     L.pa_get_hits.argtypes = [vp, vp, i64, vp, vp, i64]
+    L.pa_get_hit_pp.restype = i64
+    L.pa_get_hit_pp.argtypes = [vp, vp, i64]
     L.pa_hit_pool_bytes.restype = i64
     L.pa_hit_pool_bytes.argtypes = [vp]
     L.pa_get_stats.argtypes = [vp, C.POINTER(PaStats)]
@@ -226,6 +228,14 @@ class Context:
         model = [mraw[o:o + l].decode() for o, l in zip(hits["ali_off"], hits["ali_len"])]
         aligned = [traw[o:o + l].decode() for o, l in zip(hits["ali_off"], hits["ali_len"])]
         return hits, model, aligned
+
+    def hit_pp(self, hits):
+        """PP annotation line of every alignment of the last search() (same order as its hits)."""
+        pool = max(1, self.L.pa_hit_pool_bytes(self.h))
+        pp = C.create_string_buffer(pool)
+        self._check(self.L.pa_get_hit_pp(self.h, pp, pool), "pa_get_hit_pp")
+        raw = pp.raw
+        return [raw[o:o + l].decode() for o, l in zip(hits["ali_off"], hits["ali_len"])]
 
     def stats(self) -> dict:
         st = PaStats()

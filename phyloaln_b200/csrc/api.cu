@@ -125,7 +125,7 @@ struct pa_ctx {
   DomainBufs dom;
 
   std::vector<pa_hit> hits;
-  std::string model_pool, target_pool;
+  std::string model_pool, target_pool, pp_pool;
   pa_stats stats{};
 };
 

@@ -83,6 +83,12 @@ __host__ __device__ inline SlabLayout slab_layout(int maxL, int maxW, int maxM) 
   return s;
 }
 
+// HMMER's p7_alidisplay_EncodePostProb: '0'..'9', '*' from 0.95
+__device__ __forceinline__ char pp_char(float p) {
+  const double q = (double)p + 0.05;
+  return q >= 1.0 ? '*' : (char)((int)(q * 10.0) + '0');
+}
+
 struct DomArgs {
   const DevHmm *hmms;
   const float *tab;
@@ -812,26 +818,29 @@ __global__ void __launch_bounds__(128) domain_kernel(DomArgs a) {
       unsigned long long ridx = 0, poff = 0, roff = 0;
       if (lane == 0) {
         ridx = atomicAdd(a.rec_count, 1ull);
-        poff = atomicAdd(a.pool_count, (unsigned long long)(ali_len + 1));
+        poff = atomicAdd(a.pool_count, (unsigned long long)(2 * (ali_len + 1)));  // aligned line, then its PP line
         roff = atomicAdd(a.res_count, (unsigned long long)Ld);
-        if (ridx >= a.rec_cap || poff + ali_len + 1 > a.pool_cap || roff + Ld > a.res_cap) {
+        if (ridx >= a.rec_cap || poff + 2 * (ali_len + 1) > a.pool_cap || roff + Ld > a.res_cap) {
           atomicOr(a.status, 1);
         } else {
           const char *cons = a.cons + a.cons_off[r.h];
           int n = 0;
           for (int z = z1; z >= z2; z--) {
             const char st = trs[z];
-            char mch, tch;
-            if (st == 'M') { mch = cons[trk[z]]; tch = syms[sub[tri[z] - 1]]; }
-            else if (st == 'I') { mch = '.'; tch = syms[sub[tri[z] - 1]] | 0x20; }
-            else if (st == 'D') { mch = cons[trk[z]]; tch = '-'; }
+            char mch, tch, pch;
+            // posterior probability of the aligned state (B* holds pp since the decoding step): HMMER's PP line
+            if (st == 'M') { mch = cons[trk[z]]; tch = syms[sub[tri[z] - 1]]; pch = pp_char(BM[(size_t)tri[z] * W + cell_of_k(trk[z], B)]); }
+            else if (st == 'I') { mch = '.'; tch = syms[sub[tri[z] - 1]] | 0x20; pch = pp_char(BI[(size_t)tri[z] * W + cell_of_k(trk[z], B)]); }
+            else if (st == 'D') { mch = cons[trk[z]]; tch = '-'; pch = '.'; }
             else continue;
             a.model[poff + n] = mch;
             a.aligned[poff + n] = tch;
+            a.aligned[poff + ali_len + 1 + n] = pch;
             n++;
           }
           a.model[poff + n] = 0;
           a.aligned[poff + n] = 0;
+          a.aligned[poff + 2 * ali_len + 1] = 0;
           for (int q = 0; q < Ld; q++) a.res[roff + q] = sub[q];
           DomRec d;
           d.t = r.t; d.h = r.h; d.multi = (uint16_t)multi; d.surv = (int)w; d.dom_idx = ndom;

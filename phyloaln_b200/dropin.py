@@ -16,6 +16,7 @@ import os
 
 import numpy as np
 
+from .hmmer_text import write_text_report
 from .hmmio import read_hmm
 from .search import B200Searcher, parse_hmmsearch_parameters, write_step_outputs, write_tblout
 
@@ -78,10 +79,11 @@ def reads_from_ingest(ing):
 
 def hmmsearch_step(outdir: str, groups, mol_type: str = "prot", gencode: int = 1, no_reverse: bool = False,
                    codon: bool = False, hmmsearch_parameters=(), devices=(0,), raw_fasta: str | None = None,
-                   write_tbl: bool = True, ingest=None):
+                   write_tbl: bool = True, ingest=None, write_text: bool = False):
     """Batched replacement of ``for g in groups: hmmsearch g.hmm all.target.fasta; extract_reads(g)``.
 
-    Returns {g: number of hit_info rows}.  Raises on any failure (the reference returns (1, g) per
+    write_text additionally writes map/{g}.hmmsearch.txt, the HMMER3 text report of the reference's `-o`
+    (lib/aln.py:664), from the same hit records.  Returns {g: number of hit_info rows}.  Raises on any failure (the reference returns (1, g) per
     failed group, lib/aln.py:669-672; here the whole batch fails loudly -- there is no CPU fallback)."""
     groups = list(groups)
     opts = parse_hmmsearch_parameters(hmmsearch_parameters)
@@ -102,7 +104,7 @@ def hmmsearch_step(outdir: str, groups, mol_type: str = "prot", gencode: int = 1
     searcher = B200Searcher(hmms, devices=devices, options=opts)
     try:
         rep, nframes, translated = searcher.search_and_report(nt, off, ids, mol_type=mol_type, gencode=gencode,
-                                                              no_reverse=no_reverse, codon=codon)
+                                                              no_reverse=no_reverse, codon=codon, want_pp=write_text)
         stats = [c.stats() for c in searcher.ctxs]
     finally:
         searcher.close()
@@ -117,5 +119,9 @@ def hmmsearch_step(outdir: str, groups, mol_type: str = "prot", gencode: int = 1
         write_step_outputs(outdir, g, rows, ids, raw_seq, nframes, translated, log)
         if write_tbl:
             write_tblout(os.path.join(outdir, "map", g + ".hmmsearch.tbl"), g, rows)
+        if write_text:
+            with open(os.path.join(outdir, "map", g + ".hmmsearch.txt"), "w") as fh:
+                write_text_report(fh, hmms[hi], rows, searcher.last_Z, incE=opts.incE, incdomE=opts.incdomE,
+                                  header={"query HMM file": os.path.join("ref_hmm", g + ".hmm"), "target sequence database": "all.target.fasta"})
         counts[g] = len(rows)
     return counts

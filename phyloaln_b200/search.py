@@ -102,7 +102,7 @@ def frame_suffix(frame: int, nframes: int, translated: bool):
     return ("", "+", None) if frame == 0 else ("_rev", "rev", None)
 
 
-def report(hits: np.ndarray, model, aligned, target_names, Z: float, opts: SearchOptions, n_hmm: int):
+def report(hits: np.ndarray, model, aligned, target_names, Z: float, opts: SearchOptions, n_hmm: int, pp=None):
     """Apply reporting thresholds and HMMER's report order per profile.
 
     hits: structured array (capi.HIT_DTYPE) gathered from all shards, ``target`` already global.
@@ -152,7 +152,8 @@ def report(hits: np.ndarray, model, aligned, target_names, Z: float, opts: Searc
                              "dom_bits": float(hs["dom_bits"][g]), "dom_cevalue": math.exp(float(hs["dom_lnP"][g])) * domZ,
                              "dom_ievalue": math.exp(float(hs["dom_lnP"][g])) * Zeff,
                              "dom_bias": float(hs["dombias"][g]) / math.log(2.0), "ndom": int(hs["ndom_in_seq"][g]),
-                             "model": model[og], "aligned": aligned[og]})
+                             "oasc": float(hs["oasc"][g]), "domZ": domZ, "Z": Zeff,
+                             "model": model[og], "aligned": aligned[og], "pp": pp[og] if pp is not None else None})
         out[h] = rows
     return out
 
@@ -251,8 +252,9 @@ class B200Searcher:
         self.ctxs = []
 
     def search_reads(self, nt: np.ndarray, off: np.ndarray, mol_type: str = "prot", gencode: int = 1, no_reverse: bool = False,
-                     codon: bool = False, chunk_reads: int = 1 << 18):
-        """Search concatenated ASCII reads. Returns (hits, model, aligned, Z, nframes, translated).
+                     codon: bool = False, chunk_reads: int = 1 << 18, want_pp: bool = False):
+        """Search concatenated ASCII reads. Returns (hits, model, aligned, Z, nframes, translated); with want_pp the PP
+        annotation lines of the alignments are left in ``self.last_pp`` (same order as hits).
 
         ``mol_type`` follows PhyloAln's -m: 'dna*' searches nucleotide targets, everything else translates
         (lib/aln.py:241-258). Reads are cut into chunks; chunk c goes to GPU c mod n (contexts run in
@@ -283,9 +285,10 @@ class B200Searcher:
                     search_range(ctx, mid, b, out)
                     return
                 raise
+            pp = ctx.hit_pp(hits) if want_pp else [None] * len(hits)
             hits = hits.copy()
             hits["target"] += a * nf
-            out.append((hits, model, aligned))
+            out.append((hits, model, aligned, pp))
 
         def work(ci, ctx):
             try:
@@ -293,7 +296,7 @@ class B200Searcher:
                     parts = []
                     search_range(ctx, bounds[c], bounds[c + 1], parts)
                     results[c] = (np.concatenate([p[0] for p in parts]), [m for p in parts for m in p[1]],
-                                  [m for p in parts for m in p[2]])
+                                  [m for p in parts for m in p[2]], [m for p in parts for m in p[3]])
             except Exception as e:  # surfaced after join
                 errors.append(e)
 
@@ -309,14 +312,16 @@ class B200Searcher:
         hits = np.concatenate([r[0] for r in res]) if res else np.zeros(0, dtype=capi.HIT_DTYPE)
         model = [m for r in res for m in r[1]]
         aligned = [m for r in res for m in r[2]]
+        self.last_pp = [m for r in res for m in r[3]] if want_pp else None
         Z = nreads * nframes
         return hits, model, aligned, Z, nframes, translated
 
     def search_and_report(self, nt, off, ids, **kw):
         hits, model, aligned, Z, nframes, translated = self.search_reads(nt, off, **kw)
+        self.last_Z = Z
 
         def tname(t):
             read, frame = divmod(t, nframes)
             return ids[read] + frame_suffix(frame, nframes, translated)[0]
-        rep = report(hits, model, aligned, tname, Z, self.opts, len(self.hmms))
+        rep = report(hits, model, aligned, tname, Z, self.opts, len(self.hmms), pp=self.last_pp)
         return rep, nframes, translated

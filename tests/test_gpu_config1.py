@@ -23,8 +23,21 @@ def test_config1_dropin_outputs_identical_to_golden(tmp_path):
         shutil.copy(os.path.join(C1, "ref_hmm", g + ".hmm"), out / "ref_hmm" / (g + ".hmm"))
     with gzip.open(os.path.join(C1, "all.raw.fasta.gz"), "rb") as f, open(out / "all.raw.fasta", "wb") as g:
         shutil.copyfileobj(f, g)
-    counts = dropin.hmmsearch_step(str(out), GROUPS, mol_type="codon", gencode=1)
+    counts = dropin.hmmsearch_step(str(out), GROUPS, mol_type="codon", gencode=1, write_text=True)
     total = 0
+    import sys
+    shim = os.path.join(os.path.dirname(__file__), "bio_shim")
+    sys.path.insert(0, shim)
+    try:
+        from Bio import SearchIO
+        for g in GROUPS:   # the `-o` text report carries the same rows (what the unmodified extract_reads would parse)
+            want = [l.split("\t") for l in open(os.path.join(C1, "hit_info", g + ".hit_info.tsv")).read().splitlines()]
+            got = [f for q in SearchIO.parse(str(out / "map" / (g + ".hmmsearch.txt")), "hmmer3-text") for hit in q for hsp in hit for f in hsp]
+            assert [(str(f.query_start + 1), str(f.query_end), str(f.hit_start + 1), str(f.hit_end), str(f.query.seq).upper().replace(".", "-"),
+                     str(f.hit.seq).upper().replace(".", "-")) for f in got] == [tuple(w[2:6] + w[8:10]) for w in want], g
+            assert all(len(f.aln_annotation["PP"]) == len(str(f.hit.seq)) for f in got)
+    finally:
+        sys.path.remove(shim)
     for g in GROUPS:
         got = open(out / "map" / (g + ".hit_info.tsv")).read()
         want = open(os.path.join(C1, "hit_info", g + ".hit_info.tsv")).read()

@@ -10,7 +10,7 @@ INT_FIELDS = ["ndom_in_seq", "dom_idx", "ienv", "jenv", "iali", "jali", "hmmfrom
 FLOAT_FIELDS = ["envsc", "domcorrection", "oasc", "dombias", "dom_bits", "seq_bits", "pre_bits", "seqbias", "fwdsc", "nullsc"]
 
 
-def compare_hits(oracle, hmms, seqs, hits, model, aligned, opts=None):
+def compare_hits(oracle, hmms, seqs, hits, model, aligned, opts=None, pp=None):
     """Every oracle hit must be reproduced exactly: set, coordinates, strings; scores within 0.01 bit."""
     got = {}
     for i in range(len(hits)):
@@ -28,6 +28,8 @@ def compare_hits(oracle, hmms, seqs, hits, model, aligned, opts=None):
                 assert int(hits[f][g]) == oh[f], (key, f, int(hits[f][g]), oh[f])
             assert model[g] == oh["model"], key
             assert aligned[g] == oh["aligned"], key
+            if pp is not None:      # posterior-probability annotation of the alignment (HMMER's PP line)
+                assert pp[g] == oh["pp"], key
             for f in FLOAT_FIELDS:
                 assert abs(float(hits[f][g]) - oh[f]) <= 0.01 * 0.6931 + 1e-5 * abs(oh[f]), (key, f, float(hits[f][g]), oh[f])
             for f in ("dom_lnP", "seq_lnP"):
@@ -46,7 +48,7 @@ def test_search_matches_oracle_proteins(oracle, gpu_ctx_factory):
     ctx.commit()
     ctx.load_proteins(seqs)
     hits, model, aligned = ctx.search()
-    n = compare_hits(oracle, hmms, seqs, hits, model, aligned)
+    n = compare_hits(oracle, hmms, seqs, hits, model, aligned, pp=ctx.hit_pp(hits))
     assert n > 50
     ctx.close()
 
@@ -74,7 +76,7 @@ def test_search_matches_oracle_long_targets(oracle, gpu_ctx_factory):
     ctx.commit()
     ctx.load_proteins(seqs)
     hits, model, aligned = ctx.search()
-    n = compare_hits(oracle, hmms, seqs, hits, model, aligned)
+    n = compare_hits(oracle, hmms, seqs, hits, model, aligned, pp=ctx.hit_pp(hits))
     assert n > 40
     assert (hits["ndom_in_seq"] > 1).any()
     ctx.close()
@@ -97,7 +99,7 @@ def test_search_six_frame_reads(oracle, gpu_ctx_factory):
     ctx.commit()
     assert ctx.load_read_list(rl, moltype=0, gencode=1) == len(frames)
     hits, model, aligned = ctx.search()
-    n = compare_hits(oracle, hmms, frames, hits, model, aligned)
+    n = compare_hits(oracle, hmms, frames, hits, model, aligned, pp=ctx.hit_pp(hits))
     assert n > 30
     ctx.close()
 
@@ -148,12 +150,12 @@ def test_nucleotide_mode_dna_profiles(oracle, gpu_ctx_factory):
     assert ctx.load_read_list(reads, moltype=1) == len(targets)
     assert ctx.get_targets(len(targets), sum(map(len, targets))) == [t.upper() for t in targets]
     hits, model, aligned = ctx.search()
-    n = compare_hits(oracle, hmms, targets, hits, model, aligned)
+    n = compare_hits(oracle, hmms, targets, hits, model, aligned, pp=ctx.hit_pp(hits))
     assert n > 40
     # forward-only variant (-n / no_reverse)
     assert ctx.load_read_list(reads, moltype=1, no_reverse=True) == len(reads)
     hits, model, aligned = ctx.search()
-    assert compare_hits(oracle, hmms, reads, hits, model, aligned) > 20
+    assert compare_hits(oracle, hmms, reads, hits, model, aligned, pp=ctx.hit_pp(hits)) > 20
     ctx.close()
 
 
@@ -173,7 +175,7 @@ def test_codon_mode_first_frame_only(oracle, gpu_ctx_factory):
     ctx.commit()
     assert ctx.load_read_list(rl, moltype=0, gencode=11, no_reverse=True, codon_only=True) == len(frames)
     hits, model, aligned = ctx.search()
-    assert compare_hits(oracle, hmms, frames, hits, model, aligned) > 10
+    assert compare_hits(oracle, hmms, frames, hits, model, aligned, pp=ctx.hit_pp(hits)) > 10
     ctx.close()
 
 
@@ -201,7 +203,7 @@ def test_search_very_long_targets_and_profiles(oracle, gpu_ctx_factory):
     ctx.commit()
     ctx.load_proteins(seqs)
     hits, model, aligned = ctx.search()
-    assert compare_hits(oracle, hmms, seqs, hits, model, aligned) > 15
+    assert compare_hits(oracle, hmms, seqs, hits, model, aligned, pp=ctx.hit_pp(hits)) > 15
     ctx.close()
 
 
@@ -230,7 +232,7 @@ def test_multidomain_regions_are_resolved_by_trace_clustering(oracle, gpu_ctx_fa
     ctx.commit()
     ctx.load_proteins(seqs)
     hits, model, aligned = ctx.search()
-    n = compare_hits(oracle, hmms, seqs, hits, model, aligned)
+    n = compare_hits(oracle, hmms, seqs, hits, model, aligned, pp=ctx.hit_pp(hits))
     multi = hits[hits["multidomain_region"] == 1]
     assert len(multi) >= 40 and n >= 150
     # a flagged region really was split: several domains share it
@@ -251,7 +253,7 @@ def test_packed_profiles_boundaries(oracle, gpu_ctx_factory):
     ctx.commit()
     ctx.load_proteins(seqs)
     hits, model, aligned = ctx.search()
-    n = compare_hits(oracle, hmms, seqs, hits, model, aligned)
+    n = compare_hits(oracle, hmms, seqs, hits, model, aligned, pp=ctx.hit_pp(hits))
     assert n > 100
     assert len(set(int(x) for x in hits["hmm"])) >= 12   # hits spread over the packed profiles
     # the funnel counts agree with the oracle as well (every pair, candidate or not)
