@@ -326,7 +326,10 @@ def main():
             "roofline": {"bound": "int_dpx", "kernel": "msv_pack_kernel<2> + msv_tmem_kernel<17..32,2> (sticky-inf SSV: one fp16x2 HFMA2.RELU per two cells, no running maximum; packed profile tables in TMEM; inline exact MSV)",
                          "achieved": 4.0 * msv_cells_s / 1e12, "peak": 4.0 * peak_cells / 1e12,
                          "unit": "T 16-bit lane-op/s (algorithmic 4 per DP cell)",
-                         "frac": msv_cells_s / peak_cells, "traffic": None,
+                         "frac": msv_cells_s / peak_cells,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of msv_pack_kernel, one `ncu --set full` capture of this
+                         # command at the default 131,072 reads/step (profiles/r1d_ncu_full_kernels.md): 128.0 MB + 20.8 MB
+                         "traffic": 148.8e6 if args.reads_per_step == 131072 else None, "traffic_unit": "bytes per msv_pack_kernel launch",
                          "msv_gcups": msv_cells_s / 1e9,
                          "useful_cells_per_clk_per_sm": msv_cells_s / sm_clk / 148.0,
                          "padded_cells_per_clk_per_sm": padded_cells_per_step / (ms_msv * 1e-3) / sm_clk / 148.0,
@@ -337,8 +340,8 @@ def main():
                          "tmem_read_B_per_clk_per_sm": 2.0 * padded_cells_per_step / (ms_msv * 1e-3) / sm_clk / 148.0,
                          "binding_resource": "the half-rate HFMA2 pipe (16 HFMA2.RELU per 1,024-cell warp row = 32 pipe cycles) and warp "
                                              "instruction issue (profiles/r1d_ncu_full_kernels.md)",
-                         "traffic_note": "DRAM traffic is not the bound: ncu dram bytes of the MSV launches = 38.5 MB per 32,768-read step "
-                                         "(targets + tables); the emission tables live in TMEM",
+                         "traffic_note": "DRAM traffic is not the bound (149 MB per 547 ms launch = 0.27 GB/s): targets + tables in, candidate "
+                                         "records out; the emission tables live in TMEM",
                          "ginstr_per_s": dpx},
             "roofline_translate": tr_roof,
             "stage_ms": ms_stage,

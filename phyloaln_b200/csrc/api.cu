@@ -812,9 +812,9 @@ static cudaError_t launch_fwd_t(pa_ctx *ctx, FwdTArgs &a, cudaStream_t st) {
   const unsigned long long n = a.end - a.begin;
   if (n == 0) return cudaSuccess;
   // B <= 32: rows in registers, 4 warps per block. B > 32: 4 shared-memory rows per warp, as many warps as fit in ~96 KB
-  const size_t per_warp = B <= 32 ? 0 : (size_t)4 * B * 32 * 4;
+  constexpr size_t per_warp = B <= 32 ? 0 : (size_t)4 * B * 32 * 4;
   int wpb = 4;
-  if (per_warp) wpb = (int)std::max<size_t>(1, std::min<size_t>(4, (96 * 1024) / per_warp));
+  if constexpr (per_warp != 0) wpb = (int)std::max<size_t>(1, std::min<size_t>(4, (96 * 1024) / per_warp));
   const size_t smem = per_warp * wpb;
   if (smem) {
     cudaError_t e = cudaFuncSetAttribute(fwd_kernel_t<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -860,12 +860,6 @@ static int launch_thresholds(pa_ctx *ctx, int all_pass) {
   msv_threshold_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_hmms.p, nh, make_lentabs(ctx), ctx->d_thrJ.p, ctx->d_scJ.p, all_pass);
   ctx->stats.kernel_launches++;
   return 0;
-}
-
-static size_t warps_for_smem(pa_ctx *ctx, size_t per_warp) {
-  size_t budget = std::min<size_t>(ctx->smem_optin, 200 * 1024);
-  size_t w = budget / std::max<size_t>(per_warp, 1);
-  return std::max<size_t>(1, std::min<size_t>(8, w));
 }
 
 static int check_targets_ready(pa_ctx *ctx) {

@@ -264,3 +264,42 @@ def test_packed_profiles_boundaries(oracle, gpu_ctx_factory):
         past_msv += int((tr["stage"] >= 1).sum())
     assert st["n_past_msv"] == past_msv
     ctx.close()
+
+
+@pytest.mark.parametrize("F1", [0.02, 0.3, 1.0])
+def test_sticky_ssv_long_targets_in_packs_and_loose_thresholds(oracle, gpu_ctx_factory, F1):
+    """The sticky-inf SSV pass (no running maximum): targets longer than the 1,024-cell packed model (the +inf flag wraps
+    around the pack several times), many narrow members per pack, and MSV thresholds so loose that the candidate threshold
+    Cp collapses to 1 or below (scale +inf / every pair a candidate).  Hits and every funnel count must equal the oracle's."""
+    from phyloaln_b200 import hmmbuild_lite as hb, synth
+    rng = np.random.default_rng(31)
+    Ms = [18, 25, 40, 40, 55, 70, 90, 120, 160, 200, 260, 310]
+    hmms = [helpers.calibrated_hmm(f"st{i}", M, seed=900 + i, bg_mix=0.1, n=24) for i, M in enumerate(Ms)]
+    seqs = []
+    for i in range(90):
+        L = int(rng.integers(30, 120)) if i % 3 else int(rng.integers(900, 2600))
+        s = hb.random_sequences("amino", 1, L, rng)[0]
+        if i % 2 == 0:
+            h = hmms[int(rng.integers(len(hmms)))]
+            frag = synth.sample_protein(h, rng, 1, h.M)
+            if len(frag) < L:
+                pos = int(rng.integers(0, L - len(frag)))
+                s = s[:pos] + frag + s[pos + len(frag):]
+        seqs.append(s)
+    ctx = gpu_ctx_factory()
+    ctx.set_opts(F1=F1)
+    for h in hmms:
+        ctx.add_hmm(h)
+    ctx.commit()
+    ctx.load_proteins(seqs)
+    hits, model, aligned = ctx.search()
+    opts = oracle.default_opts(F1=F1)
+    assert compare_hits(oracle, hmms, seqs, hits, model, aligned, opts=opts, pp=ctx.hit_pp(hits)) >= 15
+    st = ctx.stats()
+    want = np.zeros(6, dtype=np.int64)
+    for h in hmms:
+        _, tr = oracle.Profile.from_hmm(h).search(seqs, opts=opts, nthreads=8)
+        want += np.bincount(tr["stage"], minlength=6)
+    assert (st["n_past_msv"], st["n_past_bias"], st["n_past_vit"], st["n_past_fwd"]) == (want[1:].sum(), want[2:].sum(), want[3:].sum(), want[4:].sum())
+    assert st["n_past_ssv"] >= st["n_past_msv"]
+    ctx.close()

@@ -7,6 +7,8 @@ measured totals: tools/run_config.py --config {2,3,4} [--fraction 1.0] [--out gp
             (M = 3 x the protein length distribution, clipped to this library's 2,047-column limit;
             PhyloAln's own --ref_split_len covers longer references)
   config 4  200 k transcripts of 0.5-5 kb (30 % carry one or two planted domains), six-frame, vs 3,000 protein HMMs
+  config 5  100 M x 150 bp reads, six-frame, vs 3,000 protein HMMs (the per-GPU share of the 1/2/4/8-GPU job: reads shard by
+            chunk, so one GPU at fraction f measures the per-read cost of the whole configuration)
 Reads are generated chunk by chunk (seeded), uploaded from host memory, searched, and the hit records
 pulled back: the timed region is the whole stream (generation excluded)."""
 import argparse
@@ -30,6 +32,8 @@ a = ap.parse_args()
 rng = np.random.default_rng(3000 + a.config)
 if a.config in (2, 3):
     n_units, n_hmm = int(10_000_000 * a.fraction), 1000
+elif a.config == 5:
+    n_units, n_hmm = int(100_000_000 * a.fraction), 3000
 else:
     n_units, n_hmm = int(200_000 * a.fraction), 3000
 abc = "dna" if a.config == 3 else "amino"
@@ -45,14 +49,14 @@ t0 = time.perf_counter()
 bench.calibrate_on_gpu(ctx, hmms, abc=abc)
 t_cal = time.perf_counter() - t0
 sumM = int(sum(h.M for h in hmms))
-chunk = a.chunk or (131072 if a.config in (2, 3) else 8192)
+chunk = a.chunk or (131072 if a.config in (2, 3, 5) else 8192)
 tot_s, tot_units, tot_hits, planted = 0.0, 0, 0, 0
 funnel = {k: 0 for k in ("n_pairs", "n_cells", "n_past_ssv", "n_past_msv", "n_past_bias", "n_past_vit", "n_past_fwd", "n_domains")}
 stage = {k: 0.0 for k in ("ms_translate", "ms_msv", "ms_bias", "ms_vit", "ms_fwd", "ms_domain", "ms_total")}
 done = 0
 while done < n_units:
     n = min(chunk, n_units - done)
-    if a.config in (2, 3):
+    if a.config in (2, 3, 5):
         reads = synth.random_reads(n, 150, rng)
         if abc == "amino":
             planted += len(synth.plant_reads(reads, hmms, 0.01, rng))
