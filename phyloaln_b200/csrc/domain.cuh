@@ -113,19 +113,18 @@ struct DomArgs {
 
 // One backward row. Mn/In: row i+1 (zeros for the last row); em: emission row of residue x(i+1).
 // last: row L (no next residue; sp preset by the caller). Arrays [j*32+lane].
-__device__ void bwd_row(const FwdTabs &T, const float *__restrict__ em, const float *__restrict__ Mn, const float *__restrict__ In,
-                        const XF &xf, const Specials &sn, Specials &sp, float *__restrict__ Mc, float *__restrict__ Ic,
-                        float *__restrict__ Dc, float *__restrict__ we, float *__restrict__ wP, int lane, bool last) {
+__device__ void bwd_row(const FwdTabs &T, const float *em, const float *Mn, const float *In, const XF &xf,
+                        const Specials &sn, Specials &sp, float *Mc, float *Ic, float *Dc, float *we, float *wP,
+                        int lane, bool last) {
   const int B = T.B;
   const int nv = min(B, max(0, T.M - lane * B));
   if (!last) {
     float s = 0.0f;
-#pragma unroll 4
     for (int j = 0; j < nv; j++) {
       const int c = j * 32 + lane;
-      const float w = __fmul_rn(Mn[c], __ldg(em + c));
+      const float w = __fmul_rn(Mn[c], em[c]);
       we[c] = w;
-      s = __fadd_rn(s, __fmul_rn(w, __ldg(&T.bwB[c].w)));
+      s = __fadd_rn(s, __fmul_rn(w, T.bwB[c].w));
     }
     sp.xB = lane_sum(s);
     sp.xJ = __fadd_rn(__fmul_rn(sp.xB, xf.tJB), __fmul_rn(sn.xJ, xf.tJJ));
@@ -139,10 +138,9 @@ __device__ void bwd_row(const FwdTabs &T, const float *__restrict__ em, const fl
   float weR = __shfl_down_sync(PA_FULL, we[lane], 1);
   if (lane == 31) weR = 0.0f;
   float LA = 0.0f, LP = 1.0f;
-#pragma unroll 4
   for (int j = nv - 1; j >= 0; j--) {
     const int c = j * 32 + lane;
-    const float4 B4 = __ldg(T.bwB + c);
+    const float4 B4 = T.bwB[c];
     const float wnext = (j + 1 < B) ? we[c + 32] : weR;
     const float cc = __fadd_rn(__fmul_rn(wnext, B4.y), xE);
     if (j == nv - 1) { LA = cc; LP = B4.z; }
@@ -157,17 +155,15 @@ __device__ void bwd_row(const FwdTabs &T, const float *__restrict__ em, const fl
   }
   float cin = __shfl_down_sync(PA_FULL, LA, 1);
   if (lane == 31) cin = 0.0f;
-#pragma unroll 4
   for (int j = 0; j < nv; j++) {
     const int c = j * 32 + lane;
     Dc[c] = __fadd_rn(Dc[c], __fmul_rn(wP[c], cin));
   }
   float dR = __shfl_down_sync(PA_FULL, Dc[lane], 1);
   if (lane == 31) dR = 0.0f;
-#pragma unroll 4
   for (int j = 0; j < nv; j++) {
     const int c = j * 32 + lane;
-    const float4 A4 = __ldg(T.bwA + c), B4 = __ldg(T.bwB + c);
+    const float4 A4 = T.bwA[c], B4 = T.bwB[c];
     const float wnext = (j + 1 < B) ? we[c + 32] : weR;
     const float dnext = (j + 1 < B) ? Dc[c + 32] : dR;
     float t = __fadd_rn(__fmul_rn(wnext, A4.x), __fmul_rn(In[c], A4.y));

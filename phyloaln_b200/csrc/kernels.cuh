@@ -819,8 +819,8 @@ __device__ __forceinline__ FwdTabs fwd_tabs(const DevHmm &hm, const float *pool)
 }
 
 // One forward row. Arrays are [j*32+lane]; cells beyond M stay 0. wP: scratch row. Returns xE.
-__device__ float fwd_row(const FwdTabs &T, int x, const float *__restrict__ Mp, const float *__restrict__ Ip, const float *__restrict__ Dp,
-                         float xBp, float *__restrict__ Mc, float *__restrict__ Ic, float *__restrict__ Dc, float *__restrict__ wP, int lane) {
+__device__ float fwd_row(const FwdTabs &T, int x, const float *Mp, const float *Ip, const float *Dp, float xBp,
+                         float *Mc, float *Ic, float *Dc, float *wP, int lane) {
   const int B = T.B;
   const float *em = T.em + (size_t)x * T.W;
   const int nv = min(B, max(0, T.M - lane * B));  // valid cells of this lane
@@ -828,26 +828,24 @@ __device__ float fwd_row(const FwdTabs &T, int x, const float *__restrict__ Mp, 
   float mL = __shfl_up_sync(PA_FULL, Mp[ilast], 1), iL = __shfl_up_sync(PA_FULL, Ip[ilast], 1),
         dL = __shfl_up_sync(PA_FULL, Dp[ilast], 1);
   if (lane == 0) mL = iL = dL = 0.0f;
-#pragma unroll 4
   for (int j = 0; j < nv; j++) {
     const int c = j * 32 + lane;
-    const float4 A = __ldg(T.trA + c), Bq = __ldg(T.trB + c);
+    const float4 A = T.trA[c], Bq = T.trB[c];
     const float pm = j ? Mp[c - 32] : mL, pi = j ? Ip[c - 32] : iL, pd = j ? Dp[c - 32] : dL;
     float t = __fmul_rn(xBp, A.x);
     t = __fadd_rn(t, __fmul_rn(pm, A.y));
     t = __fadd_rn(t, __fmul_rn(pi, A.z));
     t = __fadd_rn(t, __fmul_rn(pd, A.w));
-    Mc[c] = __fmul_rn(t, __ldg(em + c));
+    Mc[c] = __fmul_rn(t, em[c]);
     Ic[c] = __fadd_rn(__fmul_rn(Mp[c], Bq.z), __fmul_rn(Ip[c], Bq.w));
   }
   __syncwarp();
   float mcL = __shfl_up_sync(PA_FULL, Mc[ilast], 1);
   if (lane == 0) mcL = 0.0f;
   float LA = 0.0f, LP = 1.0f;
-#pragma unroll 4
   for (int j = 0; j < nv; j++) {
     const int c = j * 32 + lane;
-    const float4 Bq = __ldg(T.trB + c);
+    const float4 Bq = T.trB[c];
     const float a = __fmul_rn(j ? Mc[c - 32] : mcL, Bq.x);
     if (j == 0) { LA = a; LP = Bq.y; }
     else { LA = __fadd_rn(a, __fmul_rn(LA, Bq.y)); LP = __fmul_rn(LP, Bq.y); }
@@ -862,7 +860,6 @@ __device__ float fwd_row(const FwdTabs &T, int x, const float *__restrict__ Mp, 
   float cin = __shfl_up_sync(PA_FULL, LA, 1);
   if (lane == 0) cin = 0.0f;
   float s = 0.0f;
-#pragma unroll 4
   for (int j = 0; j < nv; j++) {
     const int c = j * 32 + lane;
     const float d = __fadd_rn(Dc[c], __fmul_rn(wP[c], cin));
