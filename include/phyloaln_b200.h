@@ -76,7 +76,7 @@ typedef struct {
   float ms_translate, ms_msv, ms_bias, ms_vit, ms_fwd, ms_domain; /* last call, CUDA events */
   float ms_h2d, ms_total;
   float ms_domain_kernel;                                  /* domain_kernel alone (ms_domain adds D2H + host scoring) */
-  float reserved0;
+  float vit_exact_pairs;                                   /* pairs the exact Viterbi kernel had to run after the 16-bit upper-bound pass */
 } pa_stats;
 
 /* per-hit column mapping result (pa_map_hits) */

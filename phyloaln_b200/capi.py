@@ -35,7 +35,7 @@ class PaStats(C.Structure):
                 ("n_past_fwd", C.c_uint64), ("n_domains", C.c_uint64), ("kernel_launches", C.c_uint64),
                 ("ms_translate", C.c_float), ("ms_msv", C.c_float), ("ms_bias", C.c_float), ("ms_vit", C.c_float),
                 ("ms_fwd", C.c_float), ("ms_domain", C.c_float), ("ms_h2d", C.c_float), ("ms_total", C.c_float),
-                ("ms_domain_kernel", C.c_float), ("reserved0", C.c_float)]
+                ("ms_domain_kernel", C.c_float), ("vit_exact_pairs", C.c_float)]
 
 
 class PaMapRec(C.Structure):

@@ -22,6 +22,7 @@
 #include "../../include/phyloaln_b200.h"
 #include "kernels.cuh"
 #include "msv_tmem.cuh"
+#include "vit16.cuh"
 #include "domain.cuh"
 #include "gencode.hpp"
 #include "ctx_access.hpp"
@@ -78,6 +79,10 @@ struct pa_ctx {
   DevBuf<uint32_t> d_msv, d_msvh;
   int msv_impl = 0;  // 0: TMEM kernel where the table fits (default), 1: shared-memory kernel everywhere (PA_MSV_IMPL=smem)
   DevBuf<int> d_vit;
+  DevBuf<uint32_t> d_v16;   // packed tables of vit16_kernel
+  DevBuf<uint8_t> d_need;   // per sorted Viterbi input: must the exact kernel run?
+  std::vector<std::pair<int, std::pair<int, int>>> v16_classes;  // (BH, (first rank, last rank + 1))
+  int use_vit16 = 1;        // PA_VIT16=0: exact kernel on every pair
   DevBuf<float> d_fwd;
   DevBuf<int> d_hmm_lists;
   std::map<int, std::pair<int, int>> q_groups;  // Q -> (offset, count) in d_hmm_lists (all profiles: score_all / single-profile runs)
@@ -175,6 +180,7 @@ extern "C" pa_ctx *pa_create(int device, char *err, int errlen) {
   ctx->num_sms = prop.multiProcessorCount;
   ctx->smem_optin = prop.sharedMemPerBlockOptin;
   if (const char *impl = getenv("PA_MSV_IMPL")) ctx->msv_impl = !strcmp(impl, "smem") ? 1 : 0;
+  if (const char *v = getenv("PA_VIT16")) ctx->use_vit16 = strcmp(v, "0") != 0;
   if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
     delete ctx;
     return fail("cudaStreamCreate", e);
@@ -185,7 +191,7 @@ extern "C" pa_ctx *pa_create(int device, char *err, int errlen) {
 extern "C" void pa_destroy(pa_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
-  ctx->d_hmms.release(); ctx->d_msv.release(); ctx->d_msvh.release(); ctx->d_vit.release(); ctx->d_fwd.release(); ctx->d_hmm_lists.release(); ctx->d_hmm_lists_rest.release(); ctx->d_packs.release(); ctx->d_packmem.release(); ctx->d_sort.release();
+  ctx->d_hmms.release(); ctx->d_msv.release(); ctx->d_msvh.release(); ctx->d_vit.release(); ctx->d_v16.release(); ctx->d_need.release(); ctx->d_fwd.release(); ctx->d_hmm_lists.release(); ctx->d_hmm_lists_rest.release(); ctx->d_packs.release(); ctx->d_packmem.release(); ctx->d_sort.release();
   ctx->d_nt.release(); ctx->d_ntoff.release(); ctx->d_dsq.release(); ctx->d_toff.release(); ctx->d_tlen.release();
   ctx->d_lidx.release(); ctx->d_codon.release(); ctx->d_flag.release();
   ctx->d_L.release(); ctx->d_nullsc.release(); ctx->d_biasA.release(); ctx->d_biasB.release(); ctx->d_tjb.release();
@@ -235,6 +241,14 @@ extern "C" int pa_set_evparam(pa_ctx *ctx, int h, const float *ev) {
 
 extern "C" int pa_num_hmms(pa_ctx *ctx) { return ctx ? (int)ctx->hmms.size() : -1; }
 
+static int v16_class(int B) {
+  static const int cls[] = {1, 2, 3, 4, 5, 6, 7, 8, 10, 12, 14, 16, 20, 24, 28, 32};
+  for (int c : cls)
+    if (B <= c) return c;
+  return 32;
+}
+static inline int clamp_v16(int v) { return v < PA_V16_FLOOR ? PA_V16_FLOOR : v; }
+
 static int vit_class(int B) {
   static const int cls[] = {1, 2, 3, 4, 6, 8, 10, 12, 14, 16, 20, 24, 28, 32, 40, 48, 56, 64};
   for (int c : cls)
@@ -271,6 +285,7 @@ extern "C" int pa_commit_hmms(pa_ctx *ctx) {
   if (nh == 0) { ctx->err = "no profiles"; return -2; }
   std::vector<uint32_t> msv, msvh;
   std::vector<int> vit;
+  std::vector<uint32_t> v16;
   std::vector<float> fwd;
   ctx->h_dev.assign(nh, DevHmm{});
   ctx->maxB = 1;
@@ -367,6 +382,46 @@ extern "C" int pa_commit_hmms(pa_ctx *ctx) {
         }
       }
     }
+    // ---- packed tables of the 16-bit upper-bound pass: half-lane hl = 2*lane + hf owns k = hl*BH + j + 1; every entry >= -16384
+    d.BH = v16_class((M + 63) / 64);
+    {
+      const int BH = d.BH, W16 = BH * 32;
+      while (v16.size() % 4) v16.push_back(0);
+      d.v16_off = v16.size();
+      v16.resize(v16.size() + (size_t)W16 * (9 + Kp), 0u);
+      uint32_t *wA = v16.data() + d.v16_off, *wI = wA + 4 * W16, *wD = wI + 2 * W16, *wps = wD + 2 * W16, *wem = wps + W16;
+      int guard = 0;
+      auto put = [](uint32_t *w, int hf, int v) { *w = hf ? ((*w & 0x0000ffffu) | ((uint32_t)(v & 0xffff) << 16)) : ((*w & 0xffff0000u) | (uint32_t)(v & 0xffff)); };
+      for (int c = 0; c < W16; c++)
+        for (int hf = 0; hf < 2; hf++) {
+          const int k = (2 * (c % 32) + hf) * BH + (c / 32) + 1;
+          int tA[4] = {PA_V16_FLOOR, PA_V16_FLOOR, PA_V16_FLOOR, PA_V16_FLOOR}, tI[2] = {PA_V16_FLOOR, PA_V16_FLOOR},
+              tD[2] = {PA_V16_FLOOR, PA_V16_FLOOR};
+          if (k <= M) {
+            const int16_t *tp = &hp.twv[(size_t)(k - 1) * 8], *tk = &hp.twv[(size_t)k * 8];
+            tA[0] = clamp_v16(tp[T_BM]); tA[1] = clamp_v16(tp[T_MM]); tA[2] = clamp_v16(tp[T_IM]); tA[3] = clamp_v16(tp[T_DM]);
+            tI[0] = clamp_v16(tk[T_MI]); tI[1] = clamp_v16(tk[T_II]);
+            tD[0] = clamp_v16(tp[T_MD]); tD[1] = clamp_v16(tp[T_DD]);
+          }
+          for (int z = 0; z < 4; z++) put(&wA[4 * c + z], hf, tA[z]);
+          for (int z = 0; z < 2; z++) { put(&wI[2 * c + z], hf, tI[z]); put(&wD[2 * c + z], hf, tD[z]); }
+          for (int x = 0; x < Kp; x++) {
+            const int e = k <= M ? clamp_v16(hp.rwv[(size_t)x * (M + 1) + k]) : PA_V16_FLOOR;
+            put(&wem[(size_t)x * W16 + c], hf, e);
+            guard = std::max(guard, e);
+          }
+        }
+      for (int lane = 0; lane < 32; lane++)
+        for (int hf = 0; hf < 2; hf++) {  // in-half-lane prefix sums of DD(k-1), floored
+          int sum = 0;
+          for (int j = 0; j < BH; j++) {
+            const int c = j * 32 + lane;
+            sum = clamp_v16(sum + (int)(short)(hf ? (wD[2 * c + 1] >> 16) : (wD[2 * c + 1] & 0xffff)));
+            put(&wps[c], hf, sum);
+          }
+        }
+      d.v16_guard = guard + std::abs((int)d.xw_E) + 8;
+    }
     // ---- float tables, lane-blocked [j][lane] with the canonical B = ceil(M/32): k = lane*B + j + 1
     const int B = d.B, W = B * 32;
     auto cellk = [&](int c) { return (c % 32) * B + (c / 32) + 1; };
@@ -393,12 +448,16 @@ extern "C" int pa_commit_hmms(pa_ctx *ctx) {
     std::stable_sort(ord.begin(), ord.end(), [&](int x, int y) { return ctx->h_dev[x].B < ctx->h_dev[y].B; });
     ctx->rank_B.assign(nh, 1);
     ctx->vit_classes.clear();
+    ctx->v16_classes.clear();
     for (int r = 0; r < nh; r++) {
       ctx->h_dev[ord[r]].rank = r;
       ctx->rank_B[r] = ctx->h_dev[ord[r]].B;
       const int bv = ctx->h_dev[ord[r]].Bv;
       if (ctx->vit_classes.empty() || ctx->vit_classes.back().first != bv) ctx->vit_classes.push_back({bv, {r, r + 1}});
       else ctx->vit_classes.back().second.second = r + 1;
+      const int bh = ctx->h_dev[ord[r]].BH;   // monotone in B as well
+      if (ctx->v16_classes.empty() || ctx->v16_classes.back().first != bh) ctx->v16_classes.push_back({bh, {r, r + 1}});
+      else ctx->v16_classes.back().second.second = r + 1;
     }
   }
   // ---- packs of narrow profiles for msv_pack_kernel (first-fit decreasing into 64 half-lanes of 16 cells)
@@ -485,6 +544,8 @@ extern "C" int pa_commit_hmms(pa_ctx *ctx) {
   CK(cudaMemcpy(ctx->d_msv.p, msv.data(), msv.size() * 4, cudaMemcpyHostToDevice));
   CK(ctx->d_msvh.ensure(msvh.size() + 1));
   if (!msvh.empty()) CK(cudaMemcpy(ctx->d_msvh.p, msvh.data(), msvh.size() * 4, cudaMemcpyHostToDevice));
+  CK(ctx->d_v16.ensure(v16.size() + 4));
+  CK(cudaMemcpy(ctx->d_v16.p, v16.data(), v16.size() * 4, cudaMemcpyHostToDevice));
   CK(ctx->d_vit.ensure(vit.size()));
   CK(cudaMemcpy(ctx->d_vit.p, vit.data(), vit.size() * 4, cudaMemcpyHostToDevice));
   CK(ctx->d_fwd.ensure(fwd.size()));
@@ -776,6 +837,24 @@ static cudaError_t launch_vit(pa_ctx *ctx, VitArgs &v, cudaStream_t st) {
   ctx->stats.kernel_launches++;
   return cudaGetLastError();
 }
+template <int BH>
+static cudaError_t launch_vit16(pa_ctx *ctx, Vit16Args &v, cudaStream_t st) {
+  const unsigned long long n = v.end - v.begin;
+  if (n == 0) return cudaSuccess;
+  const int grid = (int)std::min<unsigned long long>((n + 3) / 4, (unsigned long long)ctx->num_sms * 24);
+  vit16_kernel<BH><<<grid, 128, 0, st>>>(v);
+  ctx->stats.kernel_launches++;
+  return cudaGetLastError();
+}
+static cudaError_t dispatch_vit16(pa_ctx *ctx, int BH, Vit16Args &v, cudaStream_t st) {
+  switch (BH) {
+#define C_(b) case b: return launch_vit16<b>(ctx, v, st);
+    C_(1) C_(2) C_(3) C_(4) C_(5) C_(6) C_(7) C_(8) C_(10) C_(12) C_(14) C_(16) C_(20) C_(24) C_(28) C_(32)
+#undef C_
+  }
+  return cudaErrorInvalidValue;
+}
+
 static cudaError_t dispatch_vit(pa_ctx *ctx, int Bv, VitArgs &v, cudaStream_t st) {
   switch (Bv) {
 #define C_(b) case b: return launch_vit<b>(ctx, v, st);

@@ -37,6 +37,8 @@ struct DevHmm {
   unsigned long long msvh_off;  // uint32 words into the fp16x2 pool of the TMEM kernel ([x][q][lane])
   unsigned long long vit_off;   // ints into vit pool: trA(int4) | trB(int4) | ps | em[Kp]
   unsigned long long fwd_off;   // floats into fwd pool: trA | trB | bwA | bwB | em[Kp]
+  unsigned long long v16_off;   // uint32 words into the packed Viterbi pool of vit16_kernel (vit16.cuh)
+  int BH, v16_guard;            // words per lane of vit16_kernel (class-rounded ceil(M/64)); headroom its values need below 32767
   int tbm, tec, bias, base;
   int base_w, xw_E;
   float scale_b, scale_w;
@@ -708,6 +710,7 @@ struct VitArgs {
   unsigned long long out_cap;
   int all_pairs;           // score_all: run Viterbi on every input, write raw xC at the input index
   int *raw_out;
+  const uint8_t *need;     // from vit16_kernel: 0 = the upper bound already failed the filter, skip (nullptr: run all)
 };
 
 // register budget per class: keep several warps per scheduler for the common (M <= 512) profiles
@@ -715,6 +718,7 @@ template <int BT>
 __global__ void __launch_bounds__(128, (BT <= 8 ? 5 : BT <= 16 ? 4 : BT <= 24 ? 3 : BT <= 32 ? 2 : 1)) vit_kernel(VitArgs a) {
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   for (unsigned long long i = a.begin + (unsigned long long)blockIdx.x * wpb + wib; i < a.end; i += (unsigned long long)gridDim.x * wpb) {
+    if (a.need && !a.need[i]) continue;
     const Pass2 r = a.in[i];
     const DevHmm &hm = a.hmms[r.h];
     if (!(r.flags & 1) && !a.all_pairs) {  // P <= F2 already: Viterbi not needed
