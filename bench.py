@@ -345,7 +345,8 @@ def main():
                          "ginstr_per_s": dpx},
             "roofline_translate": tr_roof,
             "stage_ms": ms_stage,
-            "funnel": {k: int(last[k]) for k in ("n_pairs", "n_past_ssv", "n_past_msv", "n_past_bias", "n_past_vit", "n_past_fwd", "n_domains")}}
+            "funnel": dict({k: int(last[k]) for k in ("n_pairs", "n_past_ssv", "n_past_msv", "n_past_bias", "n_past_vit", "n_past_fwd", "n_domains")},
+                           n_vit_exact=int(last["vit_exact_pairs"]))}
     if rank == 0:
         if not args.no_cpu_baseline and world == 1:
             try:

@@ -54,6 +54,7 @@ tot_s, tot_units, tot_hits, planted = 0.0, 0, 0, 0
 funnel = {k: 0 for k in ("n_pairs", "n_cells", "n_past_ssv", "n_past_msv", "n_past_bias", "n_past_vit", "n_past_fwd", "n_domains")}
 stage = {k: 0.0 for k in ("ms_translate", "ms_msv", "ms_bias", "ms_vit", "ms_fwd", "ms_domain", "ms_total")}
 done = 0
+vit_exact = 0
 while done < n_units:
     n = min(chunk, n_units - done)
     if a.config in (2, 3, 5):
@@ -92,6 +93,7 @@ while done < n_units:
         funnel[k] += int(st[k])
     for k in stage:
         stage[k] += float(st[k])
+    vit_exact += int(st["vit_exact_pairs"])
     tot_hits += len(hits)
     tot_units += n
     done += n
@@ -100,7 +102,7 @@ res = {"config": a.config, "fraction": a.fraction, "units": tot_units, "unit": "
        "n_hmm": n_hmm, "sum_M": sumM, "alphabet": abc, "seconds": tot_s, "units_per_s": tot_units / tot_s,
        "gcups": funnel["n_cells"] / tot_s / 1e9, "msv_gcups": funnel["n_cells"] / (stage["ms_msv"] * 1e-3) / 1e9,
        "planted": planted, "domains_reported_to_host": tot_hits, "funnel": funnel, "stage_ms": stage,
-       "calibration_s": t_cal, "chunk": chunk}
+       "calibration_s": t_cal, "chunk": chunk, "vit_exact_pairs": vit_exact}
 print(json.dumps(res))
 if a.out:
     json.dump(res, open(a.out, "w"), indent=1)
