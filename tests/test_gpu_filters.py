@@ -41,11 +41,34 @@ def test_translation_matches_oracle(oracle, gpu_ctx_factory):
     ctx.close()
 
 
+@pytest.mark.parametrize("longest", [150, 1024, 1025, 3000])
+def test_translation_frame_sets_and_read_lengths(oracle, gpu_ctx_factory, longest):
+    """Six-frame, forward-only and codon-only modes on ragged chunks whose longest read sits below, at and above the
+    staging sizes of translate_kernel (shared-memory image for reads <= 1,024 nt, generic path beyond)."""
+    rng = np.random.default_rng(longest)
+    letters = np.frombuffer(b"ACGTACGTACGTACGTACGTACGTNRYacgt", dtype=np.uint8)
+    reads = [letters[rng.integers(0, len(letters), int(rng.integers(0, min(longest, 200) + 1)))].tobytes().decode() for _ in range(333)]
+    reads[17] = letters[rng.integers(0, len(letters), longest)].tobytes().decode()
+    reads[0], reads[1], reads[2] = "", "A", "AC"
+    ctx = gpu_ctx_factory()
+    for kw, frames in (({}, lambda r: [p for _, p in oracle.six_frames(r, 4)]),
+                       ({"no_reverse": True}, lambda r: [p for _, p in oracle.six_frames(r, 4)][:3]),
+                       ({"no_reverse": True, "codon_only": True}, lambda r: [oracle.translate(r, 4)])):
+        n = ctx.load_read_list(reads, moltype=0, gencode=4, **kw)
+        want = [p for r in reads for p in frames(r)]
+        assert n == len(want)
+        assert ctx.get_targets(n, 2 * sum(map(len, reads)) + 64) == want
+    ctx.close()
+
+
 def test_invalid_nucleotide_is_an_error(gpu_ctx_factory):
     from phyloaln_b200.capi import PaError
     ctx = gpu_ctx_factory()
     with pytest.raises(PaError):
         ctx.load_read_list(["ACGTACGTAC", "ACGTXACGT"], moltype=0)
+    with pytest.raises(PaError):   # next to a read that takes the generic long-read path
+        ctx.load_read_list(["ACGT" * 300, "ACGT!ACGT"], moltype=0)
+    assert ctx.load_read_list(["ACGTACGTAC", "AC"], moltype=0) == 12
     ctx.close()
 
 
