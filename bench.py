@@ -314,7 +314,7 @@ def main():
     sm_clk = (clocks["sm_mhz"] or 1965.0) * 1e6
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * tot / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u8 MSV semantics evaluated in fp16x2 (exact) / s16 Viterbi in s32 DPX / f32", "data": "synthetic", "config": config,
+            "dtype": "u8 MSV semantics evaluated in fp16x2 / s16 Viterbi: packed s16x2 upper bound + exact s32 DPX / f32", "data": "synthetic", "config": config,
             "gcups": gcups,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(chunks[0].nbytes + offs.nbytes),
                     "d2h_bytes_per_step": d2h},

@@ -191,3 +191,77 @@ def consensus_hits(ctx: capi.Context, rows, reads: dict, comps: dict, species, r
             comp[col] = one(0) if nucl else {1: one(0), 2: one(1), 3: one(2)}
         out[key] = {"qstart": lo, "qend": hi, "seq_comp": comp}
     return _records(rec, base, codon, unmap, frame), out
+
+
+def ref_score_tables(refseqs: dict, outgroup=(), ingroup=(), sep: str = ".", unknow: str = "N"):
+    """The two tables of the mapping kernel straight from the reference alignment: a restatement of get_ref_score()
+    (/root/reference/lib/assemble.py:678-764) that skips its per-column dictionaries.
+
+    refseqs: {seqid: aligned sequence} in file order (map/{g}.ref.fas).  Returns (comp, out_names, out_tab):
+    comp = composition_table(site_composition), out_tab = outgroup_table(outgroup_score) with out_names its row
+    labels (the outgroup sequences found, then 'PhyloAln_Alt').  Float results are produced with the reference's own
+    operation order (left-to-right Python sums), so they are bit-identical to the dictionaries' values."""
+    ids = list(refseqs)
+    if not ids:
+        raise ValueError("empty reference alignment")
+    ncols = len(refseqs[ids[0]])
+
+    def pick(species):
+        found = []
+        for sp in species:
+            for sid in ids:
+                if sid == sp or sid.startswith(sp + sep):
+                    found.append(sid)
+                    break
+        return found
+    out_ids = pick(outgroup) if outgroup else list(ids)
+    if ingroup:
+        in_ids = pick(ingroup)
+    elif len(out_ids) == len(ids):
+        in_ids = list(ids)
+    else:
+        in_ids = [sid for sid in ids if sid not in out_ids]
+    # valid ranges: runs of residues whose internal gaps are <= 5 long and that hold > 5 non-gap... exactly :706-723
+    valid = {}
+    for sid in ids:
+        s = refseqs[sid]
+        ok = np.zeros(ncols, dtype=bool)
+        gap = nogap = 0
+        i = -1
+        for i, ch in enumerate(s):
+            if ch == "-" or ch == unknow:
+                gap += 1
+                if gap > 5:
+                    if nogap > 5:
+                        ok[i - gap - nogap + 1:i - gap + 1] = True
+                    nogap = 0
+            else:
+                if nogap > 0 and 0 < gap <= 5:
+                    nogap += gap
+                nogap += 1
+                gap = 0
+        if nogap > 5:
+            ok[max(i - gap - nogap + 1, 0):i - gap + 1] = True
+        valid[sid] = ok
+    comp = np.zeros((ncols, 32), dtype=np.int32)
+    for sid in in_ids:
+        s, ok = refseqs[sid], valid[sid]
+        for i in np.nonzero(ok)[0]:
+            comp[i, comp_symbol(s[i])] += 1
+    # dictionary keys are the literal characters: two characters that share a table slot ('?' and '#', say) would be
+    # separate keys in the reference; alignments only hold letters, '-', '*' and the unknown symbol
+    totals = comp.sum(axis=1)
+    out_tab = np.full((len(out_ids) + 1, ncols), np.nan, dtype=np.float64)
+    means = []
+    for r, sid in enumerate(out_ids):
+        s, ok = refseqs[sid], valid[sid]
+        fr = []
+        for i in np.nonzero(ok)[0]:
+            cnt = int(comp[i, comp_symbol(s[i])])
+            out_tab[r, i] = float(cnt)
+            fr.append(cnt / int(totals[i]))      # ZeroDivisionError as in the reference when no ingroup residue is valid here
+        means.append(sum(fr) / len(fr))
+    aver = min(means)
+    for i in range(ncols):
+        out_tab[len(out_ids), i] = int(totals[i]) * aver
+    return comp, out_ids + ["PhyloAln_Alt"], out_tab

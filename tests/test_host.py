@@ -162,3 +162,65 @@ def test_composition_table():
     from phyloaln_b200 import mapping
     tab = mapping.composition_table({1: {"M": 3}, 2: {"K": 2, "-": 1}, 3: {"*": 1, "X": 2}})
     assert tab.shape == (3, 32) and tab[0, 12] == 3 and tab[1, 26] == 1 and tab[2, 27] == 1 and tab[2, 23] == 2
+
+
+def test_ref_score_tables_match_reference_get_ref_score():
+    """mapping.ref_score_tables == get_ref_score() (lib/assemble.py:678-764): against the committed vectors the reference
+    produced for the five config-1 alignments, and - when the reference tree is present - against the reference itself on
+    gappy random alignments (valid ranges, several outgroups, explicit ingroup, missing species)."""
+    import gzip, json, sys
+    from phyloaln_b200 import mapping
+    here = os.path.dirname(os.path.abspath(__file__))
+    gold = json.load(gzip.open(os.path.join(here, "golden", "mapping_ext_golden.json.gz"), "rt"))
+
+    def read_fasta(path):
+        seqs, name = {}, None
+        for line in open(path):
+            line = line.rstrip("\n")
+            if line.startswith(">"):
+                name = line[1:].split()[0]
+                seqs[name] = ""
+            elif name:
+                seqs[name] += line
+        return seqs
+    for g, G in gold["groups"].items():
+        ref = read_fasta(os.path.join(here, "golden", "config1", "ref", g + ".ref.fas"))
+        comp, names, tab = mapping.ref_score_tables(ref, outgroup=["SLEBA"], sep=".", unknow="X")
+        assert (comp == mapping.composition_table({int(k): v for k, v in G["site_composition"].items()})).all()
+        assert names == list(G["outgroup_score"].keys())
+        want = mapping.outgroup_table({s: {int(c): v for c, v in d.items()} for s, d in G["outgroup_score"].items()}, comp.shape[0])
+        assert np.array_equal(np.isnan(tab), np.isnan(want)) and np.array_equal(tab[~np.isnan(tab)], want[~np.isnan(want)])
+    if not os.path.isdir("/root/reference/lib"):
+        return
+    sys.path.insert(0, os.path.join(here, "bio_shim"))
+    sys.path.insert(0, "/root/reference/lib")
+    try:
+        import assemble as asm
+    finally:
+        sys.path.remove("/root/reference/lib")
+        sys.path.remove(os.path.join(here, "bio_shim"))
+    rng = np.random.default_rng(3)
+    n = 0
+    for t in range(30):
+        ncols, nseq = int(rng.integers(20, 120)), int(rng.integers(3, 9))
+        ref = {}
+        for s in range(nseq):
+            row = list("ACDEFGHIKLMNPQRSTVWY"[int(x)] for x in rng.integers(0, 20, ncols))
+            for _ in range(int(rng.integers(0, 6))):          # gap runs of assorted lengths, some X
+                a, ln = int(rng.integers(0, ncols)), int(rng.integers(1, 12))
+                row[a:a + ln] = ("-" if rng.random() < 0.8 else "X") * len(row[a:a + ln])
+            ref[f"SP{s}.{t}"] = "".join(row)
+        for kw in (dict(outgroup=["SP0"]), dict(outgroup=[]), dict(outgroup=["SP0", "SP1"], ingroup=["SP2", "SP3", "SPX"]),
+                   dict(outgroup=["NOPE", "SP1"])):
+            try:
+                sc, osc = asm.get_ref_score(dict(ref), sep=".", unknow="X", **kw)
+            except (ZeroDivisionError, ValueError):
+                with pytest.raises((ZeroDivisionError, ValueError)):
+                    mapping.ref_score_tables(ref, sep=".", unknow="X", **kw)
+                continue
+            comp, names, tab = mapping.ref_score_tables(ref, sep=".", unknow="X", **kw)
+            assert (comp == mapping.composition_table(sc)).all() and names == list(osc.keys())
+            want = mapping.outgroup_table(osc, ncols)
+            assert np.array_equal(np.isnan(tab), np.isnan(want)) and np.array_equal(tab[~np.isnan(tab)], want[~np.isnan(want)]), (t, kw)
+            n += 1
+    assert n > 60
