@@ -155,3 +155,16 @@ def test_hmmsearch_front_end_on_the_gpu(tmp_path, oracle):
     # unsupported option -> exit status 1 (the reference then reports "Error in hmmsearch command")
     rc = subprocess.run([sys.executable, exe, "--cut_ga", str(tmp_path / "g.hmm"), str(tmp_path / "t.fasta")], capture_output=True, text=True)
     assert rc.returncode == 1 and "cut" in rc.stderr
+
+
+def test_front_end_argument_errors_without_a_gpu(tmp_path, capsys):
+    """Usage and option errors are reported with exit status 1 before any device is touched (lib/aln.py:669-672 then logs
+    'Error in hmmsearch command'); a missing GPU is an error as well, never a CPU fallback."""
+    from phyloaln_b200 import frontend
+    assert frontend.hmmsearch_main([]) == 1
+    assert frontend.hmmsearch_main(["--cpu"]) == 1
+    assert frontend.hmmsearch_main(["--cut_ga", "a.hmm", "b.fa"]) == 1
+    assert frontend.hmmsearch_main(["--frobnicate", "a.hmm", "b.fa"]) == 1
+    assert frontend.hmmsearch_main(["-o", str(tmp_path / "o.txt"), str(tmp_path / "missing.hmm"), str(tmp_path / "missing.fa")]) == 1
+    err = capsys.readouterr().err
+    assert "Usage" in err and "cut" in err and not (tmp_path / "o.txt").exists()
