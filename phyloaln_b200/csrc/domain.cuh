@@ -19,7 +19,6 @@
 namespace pa {
 
 #define PA_MAXREG 64
-#define PA_DOM_SROW 4096  // floats of shared-memory row scratch per warp (16 KB): 8 rows of W <= 512 cells
 #define PA_NSAMPLES 200   // stochastic tracebacks per multi-domain region (HMMER: 200)
 #define PA_MAXSEG 8      // domain segments kept per sampled trace
 #define PA_MAXENV 8      // envelopes kept per multi-domain region
@@ -487,8 +486,7 @@ __global__ void __launch_bounds__(128) domain_kernel(DomArgs a) {
   float *slab = a.scratch + (size_t)gw * a.slab_floats;
   const int maxL1 = a.maxL + 1;
   const SlabLayout sl = slab_layout(a.maxL, a.maxW, a.maxM);
-  float *const grows = slab;                           // 8 * maxW row scratch in the slab (profiles too wide for shared memory)
-  extern __shared__ __align__(16) float s_rowscratch[];  // PA_DOM_SROW floats per warp: the 8 scratch rows of profiles with W <= PA_DOM_SROW / 8
+  float *rows = slab;                                  // 8 * maxW
   Specials *sf = reinterpret_cast<Specials *>(slab + sl.sf);
   Specials *sb = reinterpret_cast<Specials *>(slab + sl.sb);
   int *ef = reinterpret_cast<int *>(slab + sl.ef), *eb = reinterpret_cast<int *>(slab + sl.eb);
@@ -516,8 +514,6 @@ __global__ void __launch_bounds__(128) domain_kernel(DomArgs a) {
     const FwdTabs T = fwd_tabs(hm, a.tab);
     const int L = (int)a.tg.len[r.t], W = T.W, B = T.B, M = T.M;
     const uint8_t *p = a.tg.dsq + a.tg.off[r.t];
-    // the parser rows (previous / current M, I, D, carries) are re-read every row: shared memory when they fit
-    float *rows = (8 * W <= PA_DOM_SROW) ? s_rowscratch + (size_t)(threadIdx.x >> 5) * PA_DOM_SROW : grows;
     // ---- multihit parsers -> specials
     float mant;
     const int Ze0 = fwd_parser(T, p, L, L, 1, rows, lane, &mant, sf, ef);
