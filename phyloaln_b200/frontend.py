@@ -9,6 +9,7 @@ command" (lib/aln.py:669-672).
 """
 from __future__ import annotations
 
+import os
 import sys
 
 import numpy as np
@@ -105,5 +106,134 @@ def hmmsearch_main(argv, device: int = 0) -> int:
             write_tblout(tbl, hmm.name, rows)
     except (SearchParameterError, capi.PaError, OSError, ValueError, ImportError) as e:
         print(f"hmmsearch (phyloaln_b200): {e}", file=sys.stderr)
+        return 1
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# hmmbuild front-end (bin/hmmbuild): `hmmbuild -O STO -n NAME --cpu N [parameters] HMMFILE MSAFILE`, the command line of
+# /root/reference/lib/aln.py:66-77.  NOT a re-implementation of HMMER's model construction: the profile comes from
+# hmmbuild_lite (Henikoff position-based weights, symfrac match columns, entropy weighting to HMMER's default target, a
+# single-component Dirichlet prior instead of HMMER's mixtures), so its numbers differ from a real hmmbuild's; the
+# E-value parameters are calibrated with the GPU filters themselves.  It exists so that a machine without HMMER can run
+# the whole default pipeline; with HMMER installed, keep the real hmmbuild.
+# ---------------------------------------------------------------------------------------------------------------------
+def read_alignment(path: str):
+    """Aligned FASTA or single-/multi-block Stockholm -> ordered {id: row}."""
+    with open(path) as fh:
+        text = fh.read()
+    rows: dict[str, str] = {}
+    if text.lstrip().startswith("# STOCKHOLM"):
+        for line in text.splitlines():
+            if not line.strip() or line.startswith("#") or line.startswith("//"):
+                continue
+            name, seq = line.split()[:2]
+            rows[name] = rows.get(name, "") + seq
+    else:
+        name = None
+        for line in text.splitlines():
+            if line.startswith(">"):
+                name = line[1:].split()[0]
+                rows[name] = ""
+            elif name is not None:
+                rows[name] += line.strip()
+    if not rows:
+        raise ValueError(f"{path}: no sequences")
+    return rows
+
+
+def guess_alphabet(rows) -> str:
+    n = nt = 0
+    for s in rows.values():
+        for ch in s.upper():
+            if ch.isalpha():
+                n += 1
+                nt += ch in "ACGTUN"
+    return "dna" if n and nt / n >= 0.9 else "amino"
+
+
+def write_stockholm(path: str, name: str, rows: dict, mcols) -> None:
+    """hmmbuild -O: match columns upper case with '-' for deletions, insert columns lower case with '.', #=GC RF with an
+    'x' per match column -- what lib/aln.py:767-792 reads back (RF != '.' selects the reference columns)."""
+    alen = len(next(iter(rows.values())))
+    is_match = [False] * alen
+    for c in mcols:
+        is_match[c] = True
+    width = max(len(k) for k in rows) + 2
+    with open(path, "w") as fh:
+        fh.write(f"# STOCKHOLM 1.0\n#=GF ID {name}\n\n")
+        for sid, s in rows.items():
+            out = []
+            for c, ch in enumerate(s):
+                gap = not ch.isalpha() and ch != "*"
+                if is_match[c]:
+                    out.append("-" if gap else ch.upper())
+                else:
+                    out.append("." if gap else ch.lower())
+            fh.write(f"{sid:<{width}s}{''.join(out)}\n")
+        fh.write(f"{'#=GC RF':<{width}s}{''.join('x' if m else '.' for m in is_match)}\n//\n")
+
+
+def gpu_score_fn(device: int = 0):
+    """(msv, vit, fwd) raw scores of a profile for a list of sequences, from the filter kernels (E-value calibration)."""
+    def score(hmm, seqs):
+        ctx = capi.Context(device)
+        try:
+            ctx.add_hmm(hmm, require_stats=False)
+            ctx.commit()
+            n = ctx.load_proteins(seqs, abc=0 if hmm.abc == "amino" else 1)
+            r = ctx.score_all(0, n, want=("msv", "vit", "fwd"))
+            return r["msv"].astype(np.float64), r["vit"].astype(np.float64), r["fwd"].astype(np.float64)
+        finally:
+            ctx.close()
+    return score
+
+
+def hmmbuild_main(argv, score_fn=None) -> int:
+    from . import hmmbuild_lite as hb
+    from .hmmio import write_hmm
+    with_arg = {"-O", "-n", "-o", "--cpu", "--symfrac", "--informat", "--seed", "--fragthresh", "--wid", "--eset", "--ere", "--esigma",
+                "--eid", "--EmL", "--EmN", "--EvL", "--EvN", "--EfL", "--EfN", "--Eft", "--w_beta", "--w_length", "--maxinsertlen"}
+    opt, pos, i = {}, [], 0
+    while i < len(argv):
+        a = argv[i]
+        if a in with_arg:
+            if i + 1 >= len(argv):
+                print(f"hmmbuild: option {a} needs an argument", file=sys.stderr)
+                return 1
+            opt[a] = argv[i + 1]
+            i += 2
+        elif a.startswith("-") and len(a) > 1:
+            opt[a] = True
+            i += 1
+        else:
+            pos.append(a)
+            i += 1
+    if len(pos) != 2:
+        print("Usage: hmmbuild [-options] <hmmfile_out> <msafile>", file=sys.stderr)
+        return 1
+    unsupported = [k for k in opt if k in ("--hand", "--fast") and k == "--hand"]
+    if unsupported:
+        print("hmmbuild (phyloaln_b200): --hand (RF-defined architecture) is not supported", file=sys.stderr)
+        return 1
+    try:
+        rows = read_alignment(pos[1])
+        abc = "amino" if "--amino" in opt else "dna" if ("--dna" in opt or "--rna" in opt) else guess_alphabet(rows)
+        name = opt.get("-n") or os.path.splitext(os.path.basename(pos[1]))[0]
+        hmm, mcols = hb.build_from_alignment(name, rows, abc=abc, symfrac=float(opt.get("--symfrac", 0.5)))
+        hb.calibrate(hmm, score_fn or gpu_score_fn())
+        write_hmm(hmm, pos[0])
+        if "-O" in opt:
+            write_stockholm(opt["-O"], name, rows, mcols)
+        summary = (f"# hmmbuild (phyloaln_b200 hmmbuild-lite; not HMMER's model construction)\n"
+                   f"# idx name                  nseq  alen  mlen eff_nseq\n"
+                   f"  1   {name:<20s} {len(rows):5d} {len(next(iter(rows.values()))):5d} {hmm.M:5d} {hmm.effn:8.2f}\n")
+        if "-o" in opt:
+            with open(opt["-o"], "w") as fh:
+                fh.write(summary)
+        else:
+            sys.stdout.write(summary)
+    except (capi.PaError, OSError, ValueError, ImportError) as e:
+        print(f"hmmbuild (phyloaln_b200): {e}", file=sys.stderr)
         return 1
     return 0

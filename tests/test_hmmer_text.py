@@ -168,3 +168,69 @@ def test_front_end_argument_errors_without_a_gpu(tmp_path, capsys):
     assert frontend.hmmsearch_main(["-o", str(tmp_path / "o.txt"), str(tmp_path / "missing.hmm"), str(tmp_path / "missing.fa")]) == 1
     err = capsys.readouterr().err
     assert "Usage" in err and "cut" in err and not (tmp_path / "o.txt").exists()
+
+
+def _gappy_alignment(path):
+    ref = [l for l in open(os.path.join(HERE, "golden", "config1", "ref", "OG0003709.ref.fas")).read().split(">") if l]
+    rows = {}
+    with open(path, "w") as fh:
+        for r in ref:
+            n, s = r.split("\n", 1)
+            s = s.replace("\n", "")
+            s = s[:20] + ("--" if n.startswith("D") else "QW") + s[20:]     # an insert column pair (one sequence only)
+            rows[n] = s
+            fh.write(f">{n}\n{s}\n")
+    return rows
+
+
+def test_hmmbuild_front_end_files(tmp_path, oracle):
+    """bin/hmmbuild's outputs as the reference consumes them: the .hmm loads, and the -O Stockholm file's RF line selects the
+    match columns the way lib/aln.py:767-782 does (RF != '.', upper case, '.'/'~' -> '-')."""
+    from phyloaln_b200 import frontend, hmmio
+    rows = _gappy_alignment(tmp_path / "a.fas")
+    rc = frontend.hmmbuild_main(["-O", str(tmp_path / "a.sto"), "-n", "OGx", "--cpu", "2", "-o", str(tmp_path / "a.log"),
+                                 str(tmp_path / "a.hmm"), str(tmp_path / "a.fas")],
+                                score_fn=lambda hmm, seqs: oracle.Profile.from_hmm(hmm).score_all(seqs))
+    assert rc == 0
+    hmm = hmmio.read_hmm(str(tmp_path / "a.hmm"))
+    assert hmm.name == "OGx" and hmm.M == 128 and set(hmm.stats) == {"MSV", "VITERBI", "FORWARD"}
+    sto = frontend.read_alignment(str(tmp_path / "a.sto"))
+    rf = [l.split()[2] for l in open(tmp_path / "a.sto") if l.startswith("#=GC RF")][0]
+    assert rf.count("x") == hmm.M and len(rf) == 130 and rf[20:22] == ".."
+    for sid, s in rows.items():
+        picked = "".join(ch for ch, m in zip(sto[sid], rf) if m != ".").upper().replace(".", "-").replace("~", "-")
+        assert picked == s[:20] + s[22:]                      # = the original reference columns
+        assert sto[sid][20:22] == ("qw" if not sid.startswith("D") else "..")
+    assert frontend.hmmbuild_main(["only_one_arg"]) == 1 and frontend.guess_alphabet({"a": "ACGTNACGT-"}) == "dna"
+
+
+@pytest.mark.gpu
+def test_hmmbuild_then_hmmsearch_front_ends_on_the_gpu(tmp_path):
+    """The two executables chained as the unmodified PhyloAln would spawn them: profile from an alignment, then a search of
+    translated reads; reads derived from the alignment must be found."""
+    import subprocess
+    from oracle import oracle as O
+    from phyloaln_b200 import synth
+    rows = _gappy_alignment(tmp_path / "a.fas")
+    bindir = os.path.join(os.path.dirname(HERE), "phyloaln_b200", "bin")
+    rc = subprocess.run([sys.executable, os.path.join(bindir, "hmmbuild"), "-O", str(tmp_path / "a.sto"), "-n", "OGx", "--cpu", "1",
+                         str(tmp_path / "a.hmm"), str(tmp_path / "a.fas")], capture_output=True, text=True)
+    assert rc.returncode == 0, rc.stderr
+    prot = next(iter(rows.values())).replace("-", "")
+    rng = np.random.default_rng(2)
+    with open(tmp_path / "t.fasta", "w") as fh:
+        for i in range(40):
+            a = int(rng.integers(0, len(prot) - 45))
+            nt = synth.back_translate(prot[a:a + 45])
+            for suffix, p in O.six_frames(nt, 1):
+                fh.write(f">r{i}_PhAlTag_S_fastx1{suffix}\n{p}\n")
+    rc = subprocess.run([sys.executable, os.path.join(bindir, "hmmsearch"), "-o", str(tmp_path / "o.txt"), "--tblout", str(tmp_path / "o.tbl"),
+                         "--cpu", "1", "-E", "1e-3", str(tmp_path / "a.hmm"), str(tmp_path / "t.fasta")], capture_output=True, text=True)
+    assert rc.returncode == 0, rc.stderr
+    sys.path.insert(0, SHIM)
+    try:
+        from Bio import SearchIO
+        hits = [f.hit_id for q in SearchIO.parse(str(tmp_path / "o.txt"), "hmmer3-text") for hit in q for hsp in hit for f in hsp]
+    finally:
+        sys.path.remove(SHIM)
+    assert len(hits) >= 35 and all(h.endswith("_pos1") for h in hits)
