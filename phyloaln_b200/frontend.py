@@ -17,7 +17,7 @@ import numpy as np
 from . import capi
 from .hmmer_text import write_text_report
 from .hmmio import read_hmm
-from .search import SearchParameterError, parse_hmmsearch_parameters, report, write_tblout
+from .search import SearchParameterError, parse_hmmsearch_parameters, report, write_domtblout, write_tblout
 
 _WITH_ARG = {"-o", "--tblout", "--domtblout", "--pfamtblout", "-A", "--cpu", "--seed", "--textw", "--tformat", "-E", "--domE", "-T",
              "--domT", "--incE", "--incdomE", "-Z", "--domZ", "--F1", "--F2", "--F3"}
@@ -40,7 +40,7 @@ def read_fasta(path: str):
 
 
 def hmmsearch_main(argv, device: int = 0) -> int:
-    opts_toks, pos, out, tbl, textw = [], [], None, None, 120
+    opts_toks, pos, out, tbl, domtbl, textw = [], [], None, None, None, 120
     i = 0
     while i < len(argv):
         a = argv[i]
@@ -55,6 +55,8 @@ def hmmsearch_main(argv, device: int = 0) -> int:
                 out = argv[i + 1]
             elif a == "--tblout":
                 tbl = argv[i + 1]
+            elif a == "--domtblout":
+                domtbl = argv[i + 1]
             elif a == "--textw":
                 textw = int(argv[i + 1])
             opts_toks += [a, argv[i + 1]]
@@ -104,6 +106,8 @@ def hmmsearch_main(argv, device: int = 0) -> int:
                 fh.close()
         if tbl:
             write_tblout(tbl, hmm.name, rows)
+        if domtbl:
+            write_domtblout(domtbl, hmm.name, hmm.M, rows, target_lengths=lambda t: len(seqs[t]))
     except (SearchParameterError, capi.PaError, OSError, ValueError, ImportError) as e:
         print(f"hmmsearch (phyloaln_b200): {e}", file=sys.stderr)
         return 1

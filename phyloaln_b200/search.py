@@ -207,6 +207,28 @@ def write_tblout(path: str, query: str, rows):
                      f"{r['ndom']:3d} {r['ndom']:3d} {len(doms):3d} {len(doms):3d} -\n")
 
 
+def write_domtblout(path: str, query: str, qlen: int, rows, target_lengths=None):
+    """HMMER --domtblout table: one line per reported domain, 22 columns + description."""
+    with open(path, "w") as fh:
+        fh.write("#                                                                            --- full sequence --- -------------- this domain -------------   hmm coord   ali coord   env coord\n")
+        fh.write("# target name        accession   tlen query name           accession   qlen   E-value  score  bias   #  of  c-Evalue  i-Evalue  score  bias  from    to  from    to  from    to  acc description of target\n")
+        fh.write("#------------------- ---------- ----- -------------------- ---------- ----- --------- ------ ----- --- --- --------- --------- ------ ----- ----- ----- ----- ----- ----- ----- ---- ---------------------\n")
+        seqs = []
+        for r in rows:
+            if seqs and seqs[-1][0]["target"] == r["target"]:
+                seqs[-1].append(r)
+            else:
+                seqs.append([r])
+        for doms in seqs:
+            for n, d in enumerate(doms, 1):
+                tlen = target_lengths(d["target"]) if target_lengths else 0
+                acc = d.get("oasc", 0.0) / (1.0 + abs(d["envto"] - d["envfrom"]))
+                fh.write(f"{d['name']:<20s} -          {tlen:5d} {query:<20s} -          {qlen:5d} {d['seq_evalue']:9.2g} {d['seq_bits']:6.1f} "
+                         f"{d['seq_bias']:5.1f} {n:3d} {len(doms):3d} {d['dom_cevalue']:9.2g} {d['dom_ievalue']:9.2g} {d['dom_bits']:6.1f} "
+                         f"{d['dom_bias']:5.1f} {d['hmmfrom']:5d} {d['hmmto']:5d} {d['alifrom']:5d} {d['alito']:5d} {d['envfrom']:5d} "
+                         f"{d['envto']:5d} {acc:4.2f} -\n")
+
+
 def shard_bounds(nreads: int, world: int, rank: int):
     """Contiguous read range of one rank (reads shard by chunk; profiles are replicated)."""
     per = (nreads + world - 1) // world

@@ -128,3 +128,24 @@ def test_mapping_kernel_matches_reference_python(gpu_ctx_factory):
         n_trim += bool(c["start_trim"] or c["end_trim"])
         n_unmap += bool(c["unmap"])
     assert n_trim > 20 and n_unmap > 20
+
+
+def test_two_gpu_searcher_gives_the_one_gpu_report():
+    """Reads shard by chunk over the GPUs of one box (one context per GPU, host-side gather, no collective): the report
+    must not depend on the number of devices.  Skipped on a single-GPU box."""
+    from phyloaln_b200 import capi, dropin, hmmio, search
+    try:
+        probe = capi.Context(1)
+        probe.close()
+    except capi.PaError:
+        pytest.skip("needs two GPUs")
+    ids, nt, off = dropin.read_raw_fasta(os.path.join(C1, "all.raw.fasta.gz"))
+    hmms = [hmmio.read_hmm(os.path.join(C1, "ref_hmm", g + ".hmm")) for g in GROUPS]
+    reports = []
+    for devices in ((0,), (0, 1)):
+        s = search.B200Searcher(hmms, devices=devices)
+        rep, nframes, translated = s.search_and_report(nt, off, ids, mol_type="codon", chunk_reads=1500)
+        s.close()
+        reports.append([[(r["name"], r["dom_idx"], r["hmmfrom"], r["hmmto"], r["alifrom"], r["alito"], r["model"], r["aligned"],
+                          round(r["seq_bits"], 3)) for r in rep[hi]] for hi in range(len(GROUPS))])
+    assert reports[0] == reports[1] and sum(map(len, reports[0])) == 777

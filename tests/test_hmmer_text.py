@@ -83,6 +83,18 @@ def test_text_report_round_trips_through_a_searchio_parse(oracle, textw):
             assert (c == m) if (m != "." and a != "-" and m.upper() == a.upper()) else c in "+ "
 
 
+def test_domtblout_columns(oracle, tmp_path):
+    from phyloaln_b200 import search
+    hmm, seqs, names, rows = _report_inputs(oracle)
+    search.write_domtblout(str(tmp_path / "d.tbl"), hmm.name, hmm.M, rows, target_lengths=lambda t: len(seqs[t]))
+    lines = [l.split() for l in open(tmp_path / "d.tbl") if not l.startswith("#")]
+    assert len(lines) == len(rows) and all(len(l) == 23 for l in lines)
+    for l, r in zip(lines, rows):
+        assert (l[0], l[3], int(l[5]), int(l[15]), int(l[16]), int(l[17]), int(l[18]), int(l[19]), int(l[20])) == (
+            r["name"], hmm.name, hmm.M, r["hmmfrom"], r["hmmto"], r["alifrom"], r["alito"], r["envfrom"], r["envto"])
+        assert int(l[2]) == len(seqs[r["target"]]) and 0.0 <= float(l[21]) <= 1.0
+
+
 def test_empty_report(oracle):
     from phyloaln_b200 import hmmer_text
     hmm, _, _, _ = _report_inputs(oracle)
