@@ -214,6 +214,16 @@ int pa_ingest_write(pa_ingest *ing, const char *raw_fasta, const char *total_cou
 /* sequences [first, first+count) concatenated + offsets (count+1), ready for pa_load_reads */
 int64_t pa_ingest_pack(pa_ingest *ing, uint64_t first, uint64_t count, char *nt_out, uint64_t cap, uint64_t *off_out);
 
+/* ---- all.raw.fasta loader (host only): what dropin.hmmsearch_step needs from the file prepare_target() wrote --
+ * ids, concatenated nucleotides and offsets ready for pa_load_reads -- with the dictionary semantics of the reference's
+ * read_fastx(..., 'fasta') (lib/library.py:186-198): id = header up to the first blank, a repeated id keeps its first
+ * position and its last sequence. gz or plain. Views are borrowed until pa_fasta_close. ---- */
+typedef struct pa_fasta pa_fasta;
+pa_fasta *pa_fasta_open(const char *path, char *err, int errlen);
+int64_t pa_fasta_num_records(pa_fasta *f);
+int pa_fasta_views(pa_fasta *f, const char **ids, const uint64_t **id_off /* n+1 */, const char **nt, const uint64_t **off /* n+1 */);
+void pa_fasta_close(pa_fasta *f);
+
 #ifdef __cplusplus
 }
 #endif

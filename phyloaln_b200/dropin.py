@@ -97,7 +97,8 @@ def hmmsearch_step(outdir: str, groups, mol_type: str = "prot", gencode: int = 1
         ids, nt, off = reads_from_ingest(ingest)
     else:
         raw_fasta = raw_fasta or os.path.join(outdir, "all.raw.fasta")
-        ids, nt, off = read_raw_fasta(raw_fasta)
+        from .ingest import load_raw_fasta     # native loader; read_raw_fasta below is its plain-Python statement
+        ids, nt, off = load_raw_fasta(raw_fasta)
     # '--codon' forces no_reverse in the reference (lib/main.py:196-198)
     if codon:
         no_reverse = True

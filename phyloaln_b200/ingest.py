@@ -33,8 +33,56 @@ def _lib():
         L.pa_ingest_write.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_char_p]
         L.pa_ingest_pack.restype = i64
         L.pa_ingest_pack.argtypes = [vp, u64, u64, vp, u64, vp]
+        L.pa_fasta_open.restype = vp
+        L.pa_fasta_open.argtypes = [C.c_char_p, C.c_char_p, i32]
+        L.pa_fasta_num_records.restype = i64
+        L.pa_fasta_num_records.argtypes = [vp]
+        L.pa_fasta_views.argtypes = [vp] + [vp] * 4
+        L.pa_fasta_close.argtypes = [vp]
         L._ingest_ready = True
     return L
+
+
+class LazyIds:
+    """Sequence of record ids decoded on demand from one byte blob (10 M ids are never all needed: only reads with hits)."""
+
+    def __init__(self, blob: bytes, off: np.ndarray):
+        self._blob, self._off = blob, off
+
+    def __len__(self):
+        return len(self._off) - 1
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[k] for k in range(*i.indices(len(self)))]
+        if i < 0:
+            i += len(self)
+        return self._blob[int(self._off[i]):int(self._off[i + 1])].decode()
+
+    def __iter__(self):
+        return (self[k] for k in range(len(self)))
+
+
+def load_raw_fasta(path: str):
+    """Native all.raw.fasta loader (pa_fasta_*): (ids, nt uint8 array, offsets uint64[n+1]) with the dictionary semantics of
+    the reference's read_fastx (lib/library.py:186-198); ids is a lazily decoding sequence."""
+    L = _lib()
+    err = C.create_string_buffer(512)
+    h = L.pa_fasta_open(path.encode(), err, 512)
+    if not h:
+        raise OSError(err.value.decode() or f"cannot read {path}")
+    try:
+        n = L.pa_fasta_num_records(h)
+        p_ids, p_idoff, p_nt, p_off = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+        L.pa_fasta_views(h, C.byref(p_ids), C.byref(p_idoff), C.byref(p_nt), C.byref(p_off))
+        id_off = np.ctypeslib.as_array(C.cast(p_idoff, C.POINTER(C.c_uint64)), shape=(n + 1,)).copy()
+        off = np.ctypeslib.as_array(C.cast(p_off, C.POINTER(C.c_uint64)), shape=(n + 1,)).copy()
+        blob = C.string_at(p_ids, int(id_off[-1])) if n else b""
+        total = int(off[-1])
+        nt = np.ctypeslib.as_array(C.cast(p_nt, C.POINTER(C.c_uint8)), shape=(max(total, 1),)).copy() if total else np.zeros(1, np.uint8)
+    finally:
+        L.pa_fasta_close(h)
+    return LazyIds(blob, id_off), nt[:total] if total else nt[:0], off
 
 
 class Ingest:

@@ -81,3 +81,37 @@ def test_bad_inputs_are_errors(tmp_path):
         ingest.Ingest({"SP": [str(tmp_path / "missing.fq.gz")]})
     with pytest.raises(PaError):
         ingest.Ingest({"SP": [__file__]}, file_format="sam")
+
+
+def test_native_raw_fasta_loader_equals_python_statement(tmp_path):
+    """pa_fasta_* == dropin.read_raw_fasta (the plain-Python statement of read_fastx's dictionary semantics,
+    lib/library.py:186-198): repeated ids (first position, last sequence), multi-line records, CRLF, blank lines, text
+    before the first header, header descriptions, gz input, an empty file, and the committed config-1 all.raw.fasta."""
+    import gzip
+    from phyloaln_b200 import dropin
+    from phyloaln_b200.ingest import load_raw_fasta
+    text = ("junk before\n>r1 desc here\nACGT\n>r2\nAC\nGT\r\n\nTT\n>r1\nGGGG\n>r3\n>r4_PhAlTag_SP_fastx1\nacgtn\n>r2\nC\n>\nAAA\n"
+            ">last")
+    p = tmp_path / "a.fasta"
+    p.write_bytes(text.encode())
+    with gzip.open(tmp_path / "a.fasta.gz", "wb") as f:
+        f.write(text.encode())
+    (tmp_path / "empty.fasta").write_bytes(b"")
+    gold = os.path.join(os.path.dirname(__file__), "golden", "config1", "all.raw.fasta.gz")
+    for path in (str(p), str(tmp_path / "a.fasta.gz"), str(tmp_path / "empty.fasta"), gold):
+        ids0, nt0, off0 = dropin.read_raw_fasta(path)
+        ids1, nt1, off1 = load_raw_fasta(path)
+        assert list(ids1) == ids0 and len(ids1) == len(ids0)
+        assert np.array_equal(off1, off0) and nt1.tobytes() == nt0.tobytes()
+    ids, nt, off = load_raw_fasta(str(p))
+    assert list(ids) == ["r1", "r2", "r3", "r4_PhAlTag_SP_fastx1", "", "last"]
+    assert [nt.tobytes()[int(off[i]):int(off[i + 1])].decode() for i in range(len(ids))] == ["GGGG", "C", "", "acgtn", "AAA", ""]
+    assert ids[-1] == "last" and ids[1:3] == ["r2", "r3"]
+    with pytest.raises(OSError):
+        load_raw_fasta(str(tmp_path / "missing.fasta"))
+    # many tiny records (the id table grows several times) with every 7th id repeated later
+    names = [f"s{i}" for i in range(6000)] + [f"s{i}" for i in range(0, 6000, 7)]
+    (tmp_path / "tiny.fasta").write_text("".join(f">{nm}\n{'ACGT'[k % 4]}\n" for k, nm in enumerate(names)))
+    ids0, nt0, off0 = dropin.read_raw_fasta(str(tmp_path / "tiny.fasta"))
+    ids1, nt1, off1 = load_raw_fasta(str(tmp_path / "tiny.fasta"))
+    assert list(ids1) == ids0 and len(ids0) == 6000 and nt1.tobytes() == nt0.tobytes() and np.array_equal(off1, off0)
