@@ -92,7 +92,12 @@ def hmmsearch_step(outdir: str, groups, mol_type: str = "prot", gencode: int = 1
     counts = {}
     if not todo:
         return counts
+    import time
+    tm = {}
+    t0 = time.perf_counter()
     hmms = [read_hmm(os.path.join(outdir, "ref_hmm", g + ".hmm")) for g in todo]
+    tm["read_hmms_s"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
     if ingest is not None:
         ids, nt, off = reads_from_ingest(ingest)
     else:
@@ -102,13 +107,19 @@ def hmmsearch_step(outdir: str, groups, mol_type: str = "prot", gencode: int = 1
     # '--codon' forces no_reverse in the reference (lib/main.py:196-198)
     if codon:
         no_reverse = True
+    tm["load_reads_s"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
     searcher = B200Searcher(hmms, devices=devices, options=opts)
+    tm["upload_profiles_s"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
     try:
         rep, nframes, translated = searcher.search_and_report(nt, off, ids, mol_type=mol_type, gencode=gencode,
                                                               no_reverse=no_reverse, codon=codon, want_pp=write_text)
         stats = [c.stats() for c in searcher.ctxs]
     finally:
         searcher.close()
+    tm["search_and_report_s"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
     raw = nt.tobytes()
 
     def raw_seq(read):
@@ -125,4 +136,6 @@ def hmmsearch_step(outdir: str, groups, mol_type: str = "prot", gencode: int = 1
                 write_text_report(fh, hmms[hi], rows, searcher.last_Z, incE=opts.incE, incdomE=opts.incdomE,
                                   header={"query HMM file": os.path.join("ref_hmm", g + ".hmm"), "target sequence database": "all.target.fasta"})
         counts[g] = len(rows)
+    tm["write_outputs_s"] = time.perf_counter() - t0
+    hmmsearch_step.last_timing = tm
     return counts
