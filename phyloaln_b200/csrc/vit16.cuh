@@ -138,8 +138,11 @@ __global__ void __launch_bounds__(128, (BH <= 4 ? 6 : BH <= 8 ? 4 : BH <= 16 ? 3
       // cover the float rounding of the exact kernel's own evaluation
       const float need_sc = (float)((double)hm.thrF2v * PA_LN2) + r.filtersc + 3.0f;
       const float tf = need_sc * hm.scale_w + (float)hm.base_w - (float)xw_move;
-      const int Tint = (int)floorf(tf) - 2;
-      if (Tint + hm.v16_guard < 32767 && Tint > PA_V16_FLOOR + 1) need = vit16_pair<BH>(hm, a.tab, a.tg.dsq + a.tg.off[r.t], L, xw_move, Tint, lane);
+      // thresholds outside the 16-bit working range (F2 >= 1 gives -inf, absurdly strict ones exceed 32767 - guard): exact kernel
+      if (tf > (float)(PA_V16_FLOOR + 8) && tf < 32000.0f) {
+        const int Tint = (int)floorf(tf) - 2;
+        if (Tint + hm.v16_guard < 32767) need = vit16_pair<BH>(hm, a.tab, a.tg.dsq + a.tg.off[r.t], L, xw_move, Tint, lane);
+      }
     }
     if (lane == 0) a.need[i] = need ? 1 : 0;
     nneed += need ? 1 : 0;

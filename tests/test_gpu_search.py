@@ -303,3 +303,29 @@ def test_sticky_ssv_long_targets_in_packs_and_loose_thresholds(oracle, gpu_ctx_f
     assert (st["n_past_msv"], st["n_past_bias"], st["n_past_vit"], st["n_past_fwd"]) == (want[1:].sum(), want[2:].sum(), want[3:].sum(), want[4:].sum())
     assert st["n_past_ssv"] >= st["n_past_msv"]
     ctx.close()
+
+
+@pytest.mark.parametrize("F2", [1.0, 0.2, 1e-9])
+def test_viterbi_threshold_extremes(oracle, gpu_ctx_factory, F2):
+    """The 16-bit Viterbi upper-bound pass only drops pairs whose bound fails the pair's own threshold: F2 = 1 (threshold
+    -inf: every pair goes to the exact kernel), a loose and a very strict F2 must all give the oracle's cascade and hits."""
+    rng = np.random.default_rng(41)
+    hmms = [helpers.calibrated_hmm(f"v{i}", M, seed=300 + i, bg_mix=0.1, n=30) for i, M in enumerate([35, 64, 129, 300, 520])]
+    seqs = helpers.protein_targets(hmms, 1500, rng, Lmin=20, Lmax=90, plant_every=5)
+    ctx = gpu_ctx_factory()
+    ctx.set_opts(F2=F2)
+    for h in hmms:
+        ctx.add_hmm(h)
+    ctx.commit()
+    ctx.load_proteins(seqs)
+    hits, model, aligned = ctx.search()
+    opts = oracle.default_opts(F2=F2)
+    assert compare_hits(oracle, hmms, seqs, hits, model, aligned, opts=opts) > 30
+    st = ctx.stats()
+    want = np.zeros(6, dtype=np.int64)
+    for h in hmms:
+        _, tr = oracle.Profile.from_hmm(h).search(seqs, opts=opts, nthreads=8)
+        want += np.bincount(tr["stage"], minlength=6)
+    assert (st["n_past_bias"], st["n_past_vit"], st["n_past_fwd"]) == (want[2:].sum(), want[3:].sum(), want[4:].sum())
+    assert st["vit_exact_pairs"] <= st["n_past_bias"]
+    ctx.close()
