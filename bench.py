@@ -12,9 +12,9 @@ value      reads/s with the read chunk already resident in HBM (translate + all 
            stage + host-side domain scoring), max over ranks, whole job.
 e2e        same metric through the public C ABI with HOST buffers: H2D of the reads, translation,
            search, D2H of the hit records, every step.
-roofline   dominant kernel = msv_kernel (SSV/MSV filter): algorithmic 4 integer lane-ops per DP
-           cell x cells per launch / CUDA-event time, against the 16-bit lane-op peak
-           microbenchmarked in this run (VIADDMNMX.S16x2 issue rate x 2 lanes).
+roofline   dominant kernel = msv_pack_kernel (sticky-inf SSV + exact MSV re-run): algorithmic 4 integer lane-ops per DP
+           cell x cells per launch / CUDA-event time, against the issue rate of the kernel's only per-cell
+           instruction (HFMA2.RELU, two cells each), microbenchmarked in this run.
 cpu_baseline  the CPU oracle (scalar C restatement of the hmmsearch pipeline, OpenMP over all host
            cores) on a bounded sample of the same workload; kind "port" (no hmmsearch binary exists
            in this image).
