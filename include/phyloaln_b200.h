@@ -214,6 +214,13 @@ int pa_ingest_write(pa_ingest *ing, const char *raw_fasta, const char *total_cou
 /* sequences [first, first+count) concatenated + offsets (count+1), ready for pa_load_reads */
 int64_t pa_ingest_pack(pa_ingest *ing, uint64_t first, uint64_t count, char *nt_out, uint64_t cap, uint64_t *off_out);
 
+/* ---- HMMER3/[a-f] ASCII reader (host only): the numbers of ref_hmm/{g}.hmm (first model of the file), ready for pa_add_hmm.
+ * Call once with mat == NULL for M / abc / name / stats, then with arrays: mat, ins (M+1)*K, t (M+1)*7 (-ln p, +inf for '*'),
+ * compo K (NaN when absent), cons / rf M+1 bytes (empty string when absent), map M ints (map[0] = -1 when absent),
+ * stats {MSV mu, lambda, VITERBI mu, lambda, FORWARD tau, lambda} (NaN when absent). 0 ok, <0 malformed / unreadable. ---- */
+int pa_hmm_file_parse(const char *path, int32_t *M, int32_t *abc, char *name, int namecap, double *mat, double *ins, double *t,
+                      double *compo, char *cons, char *rf, int32_t *map, float *stats, int32_t *nseq, double *effn);
+
 /* ---- all.raw.fasta loader (host only): what dropin.hmmsearch_step needs from the file prepare_target() wrote --
  * ids, concatenated nucleotides and offsets ready for pa_load_reads -- with the dictionary semantics of the reference's
  * read_fastx(..., 'fasta') (lib/library.py:186-198): id = header up to the first blank, a repeated id keeps its first

@@ -272,3 +272,179 @@ float flogsum(float a, float b) {
 }
 
 }  // namespace pa
+
+// ---------------------------------------------------------------------------------------------------------------------
+// HMMER3/[a-f] ASCII reader (first model of a file): the numbers of `ref_hmm/{g}.hmm` as written by hmmbuild
+// (/root/reference/lib/aln.py:66-76), SURVEY.md A.2.  Mirrors phyloaln_b200/hmmio.py::read_hmm_py field for field; the
+// Python layer falls back to that statement for the descriptive error when this returns non-zero.
+// ---------------------------------------------------------------------------------------------------------------------
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+namespace {
+struct Tok {  // whitespace tokenizer over one line
+  const char *p, *e;
+  bool next(const char *&b, size_t &n) {
+    while (p < e && (*p == ' ' || *p == '\t' || *p == '\r')) p++;
+    if (p >= e) return false;
+    b = p;
+    while (p < e && *p != ' ' && *p != '\t' && *p != '\r') p++;
+    n = (size_t)(p - b);
+    return true;
+  }
+};
+inline bool num(const char *b, size_t n, double *v) {
+  if (n == 1 && *b == '*') { *v = INFINITY; return true; }
+  {  // plain decimals (what hmmbuild writes): integer mantissa / exact power of ten is correctly rounded, i.e. == strtod
+    static const double p10[] = {1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11, 1e12, 1e13, 1e14, 1e15};
+    size_t z = 0;
+    const bool neg = b[0] == '-';
+    if (neg || b[0] == '+') z = 1;
+    unsigned long long mant = 0;
+    int digits = 0, frac = -1;
+    bool ok = z < n;
+    for (; z < n && ok; z++) {
+      const char c = b[z];
+      if (c >= '0' && c <= '9') { mant = mant * 10 + (unsigned)(c - '0'); digits++; if (frac >= 0) frac++; }
+      else if (c == '.' && frac < 0) frac = 0;
+      else ok = false;
+    }
+    if (ok && digits > 0 && digits <= 15 && frac <= 15) {
+      const double x = (double)mant / p10[frac < 0 ? 0 : frac];
+      *v = neg ? -x : x;
+      return true;
+    }
+  }
+  char buf[64];
+  if (n >= sizeof(buf)) return false;
+  memcpy(buf, b, n);
+  buf[n] = 0;
+  char *end = nullptr;
+  *v = strtod(buf, &end);
+  return end == buf + n;
+}
+}  // namespace
+
+extern "C" int pa_hmm_file_parse(const char *path, int32_t *M_out, int32_t *abc_out, char *name, int namecap, double *mat,
+                                 double *ins, double *t, double *compo, char *cons, char *rf, int32_t *map, float *stats,
+                                 int32_t *nseq, double *effn) {
+  FILE *fp = fopen(path, "rb");
+  if (!fp) return -1;
+  std::string text;
+  {
+    char buf[1 << 16];
+    size_t got;
+    while ((got = fread(buf, 1, sizeof(buf), fp)) > 0) text.append(buf, got);
+  }
+  fclose(fp);
+  std::vector<std::pair<const char *, const char *>> lines;
+  for (const char *p = text.data(), *e = p + text.size(); p < e;) {
+    const char *nl = (const char *)memchr(p, '\n', (size_t)(e - p));
+    const char *le = nl ? nl : e;
+    lines.emplace_back(p, le);
+    p = nl ? nl + 1 : e;
+  }
+  if (lines.empty() || (size_t)(lines[0].second - lines[0].first) < 7 || memcmp(lines[0].first, "HMMER3/", 7) != 0) return -2;
+  int M = -1, abc = -1, K = 0;
+  bool has_cons = false, has_rf = false, has_map = false;
+  float st[6];
+  for (auto &x : st) x = NAN;
+  if (name && namecap > 0) snprintf(name, (size_t)namecap, "unnamed");
+  int32_t ns = 1;
+  double ef = 1.0;
+  size_t i = 1;
+  for (; i < lines.size(); i++) {
+    const char *b = lines[i].first, *e = lines[i].second;
+    if (e - b >= 4 && memcmp(b, "HMM ", 4) == 0) break;
+    Tok tk{b, e};
+    const char *k0, *v0;
+    size_t kn, vn;
+    if (!tk.next(k0, kn) || !tk.next(v0, vn)) continue;
+    const std::string key(k0, kn), val(v0, vn);
+    if (key == "STATS") {
+      const char *w[3];
+      size_t wn[3];
+      if (tk.next(w[0], wn[0]) && tk.next(w[1], wn[1]) && tk.next(w[2], wn[2])) {
+        const std::string which(w[0], wn[0]);
+        double a, c;
+        if (num(w[1], wn[1], &a) && num(w[2], wn[2], &c)) {
+          const int o = which == "MSV" ? 0 : which == "VITERBI" ? 2 : which == "FORWARD" ? 4 : -1;
+          if (o >= 0) { st[o] = (float)a; st[o + 1] = (float)c; }
+        } else return -3;
+      }
+    } else if (key == "LENG") M = atoi(val.c_str());
+    else if (key == "ALPH") {
+      std::string a = val;
+      for (auto &c : a) c = (char)tolower((unsigned char)c);
+      abc = a == "amino" ? 0 : (a == "dna" || a == "rna") ? 1 : -2;
+    } else if (key == "NAME") { if (name && namecap > 0) snprintf(name, (size_t)namecap, "%s", val.c_str()); }
+    else if (key == "CONS") has_cons = val == "yes" || val == "YES" || val == "Yes";
+    else if (key == "RF") has_rf = val == "yes" || val == "YES" || val == "Yes";
+    else if (key == "MAP") has_map = val == "yes" || val == "YES" || val == "Yes";
+    else if (key == "NSEQ") ns = atoi(val.c_str());
+    else if (key == "EFFN") ef = atof(val.c_str());
+  }
+  if (i >= lines.size() || M < 1 || abc < 0) return -3;
+  K = abc == 0 ? 20 : 4;
+  if (M_out) *M_out = M;
+  if (abc_out) *abc_out = abc;
+  if (nseq) *nseq = ns;
+  if (effn) *effn = ef;
+  if (stats) memcpy(stats, st, sizeof(st));
+  if (!mat) return 0;   // size query
+  i += 2;               // HMM line + transition-label line
+  if (i >= lines.size()) return -3;
+  auto numbers = [&](size_t li, int skip, int n, double *out) -> bool {
+    if (li >= lines.size()) return false;
+    Tok tk{lines[li].first, lines[li].second};
+    const char *b;
+    size_t bn;
+    for (int s = 0; s < skip; s++)
+      if (!tk.next(b, bn)) return false;
+    for (int z = 0; z < n; z++)
+      if (!tk.next(b, bn) || !num(b, bn, out + z)) return false;
+    return true;
+  };
+  for (int z = 0; z < (M + 1) * K; z++) { mat[z] = INFINITY; ins[z] = INFINITY; }
+  for (int z = 0; z < (M + 1) * 7; z++) t[z] = INFINITY;
+  for (int z = 0; z < K; z++) compo[z] = NAN;
+  {
+    Tok tk{lines[i].first, lines[i].second};
+    const char *b;
+    size_t bn;
+    if (tk.next(b, bn) && bn == 5 && memcmp(b, "COMPO", 5) == 0) {
+      if (!numbers(i, 1, K, compo)) return -3;
+      i++;
+    }
+  }
+  if (!numbers(i, 0, K, ins) || !numbers(i + 1, 0, 7, t)) return -3;
+  i += 2;
+  cons[0] = rf[0] = 0;
+  int ncons = 0, nrf = 0, nmap = 0;
+  for (int k = 1; k <= M; k++, i += 3) {
+    if (i + 2 >= lines.size()) return -3;
+    Tok tk{lines[i].first, lines[i].second};
+    const char *b;
+    size_t bn;
+    if (!tk.next(b, bn)) return -3;
+    char kb[16];
+    const int kl = snprintf(kb, sizeof(kb), "%d", k);
+    if ((size_t)kl != bn || memcmp(kb, b, bn) != 0) return -3;
+    for (int z = 0; z < K; z++)
+      if (!tk.next(b, bn) || !num(b, bn, &mat[(size_t)k * K + z])) return -3;
+    if (tk.next(b, bn)) {                       // MAP
+      if (has_map) { map[nmap++] = (bn == 1 && *b == '-') ? 0 : atoi(std::string(b, bn).c_str()); }
+      if (tk.next(b, bn)) {                     // CONS
+        if (has_cons) { cons[ncons++] = *b; }
+        if (tk.next(b, bn) && has_rf) rf[nrf++] = *b;
+      }
+    }
+    if (!numbers(i + 1, 0, K, ins + (size_t)k * K) || !numbers(i + 2, 0, 7, t + (size_t)k * 7)) return -3;
+  }
+  cons[ncons == M ? M : 0] = 0;
+  rf[nrf == M ? M : 0] = 0;
+  if (nmap != M) map[0] = -1;   // absent
+  return 0;
+}

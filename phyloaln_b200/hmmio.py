@@ -77,7 +77,39 @@ def _val(tok: str) -> float:
 
 
 def read_hmm(path: str) -> HMM:
-    """Parse one HMMER3/[a-f] ASCII profile (first model of the file)."""
+    """One HMMER3/[a-f] ASCII profile (first model of the file) through the native reader (pa_hmm_file_parse, ~0.3 ms per
+    profile instead of ~4 ms); a file it rejects is re-read by the Python statement below for the descriptive error."""
+    import ctypes as C
+    from . import capi
+    L = capi.load_library()
+    if not getattr(L, "_hmm_ready", False):
+        L.pa_hmm_file_parse.argtypes = [C.c_char_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_char_p, C.c_int] + [C.c_void_p] * 8 + [
+            C.POINTER(C.c_int32), C.POINTER(C.c_double)]
+        L._hmm_ready = True
+    M, abc, nseq, effn = C.c_int32(), C.c_int32(), C.c_int32(), C.c_double()
+    name = C.create_string_buffer(512)
+    stats = np.zeros(6, np.float32)
+    if L.pa_hmm_file_parse(path.encode(), C.byref(M), C.byref(abc), name, 512, None, None, None, None, None, None, None,
+                           stats.ctypes.data, C.byref(nseq), C.byref(effn)) != 0:
+        return read_hmm_py(path)
+    m, K = M.value, 20 if abc.value == 0 else 4
+    mat, ins, t = np.empty((m + 1, K)), np.empty((m + 1, K)), np.empty((m + 1, 7))
+    compo, mp = np.empty(K), np.zeros(max(m, 1), np.int32)
+    cons, rf = C.create_string_buffer(m + 2), C.create_string_buffer(m + 2)
+    if L.pa_hmm_file_parse(path.encode(), C.byref(M), C.byref(abc), name, 512, mat.ctypes.data, ins.ctypes.data, t.ctypes.data,
+                           compo.ctypes.data, cons, rf, mp.ctypes.data, stats.ctypes.data, C.byref(nseq), C.byref(effn)) != 0:
+        return read_hmm_py(path)
+    st = {}
+    for k, tag in enumerate(("MSV", "VITERBI", "FORWARD")):
+        if not math.isnan(float(stats[2 * k])):
+            st[tag] = (float(stats[2 * k]), float(stats[2 * k + 1]))
+    return HMM(name=name.value.decode(), abc="amino" if abc.value == 0 else "dna", mat=mat, ins=ins, t=t,
+               compo=None if np.isnan(compo).any() else compo, cons=cons.value.decode() or None, stats=st, nseq=nseq.value,
+               effn=effn.value, rf=rf.value.decode() or None, map=None if mp[0] < 0 else [int(x) for x in mp[:m]])
+
+
+def read_hmm_py(path: str) -> HMM:
+    """Parse one HMMER3/[a-f] ASCII profile (first model of the file): the plain-Python statement of the format."""
     with open(path) as fh:
         lines = fh.read().splitlines()
     if not lines or not lines[0].startswith("HMMER3/"):

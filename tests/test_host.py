@@ -224,3 +224,37 @@ def test_ref_score_tables_match_reference_get_ref_score():
             assert np.array_equal(np.isnan(tab), np.isnan(want)) and np.array_equal(tab[~np.isnan(tab)], want[~np.isnan(want)]), (t, kw)
             n += 1
     assert n > 60
+
+
+def test_native_hmm_reader_equals_python_statement(tmp_path):
+    """pa_hmm_file_parse (hmmio.read_hmm) against hmmio.read_hmm_py: config-1 profiles, a written DNA profile without
+    STATS, numbers in exponent notation, and malformed files (same exception from both)."""
+    import glob
+    from phyloaln_b200 import hmmio, synth
+    here = os.path.dirname(os.path.abspath(__file__))
+    files = sorted(glob.glob(os.path.join(here, "golden", "config1", "ref_hmm", "*.hmm")))
+    dna = synth.random_hmm("dnaprof", 77, np.random.default_rng(4), abc="dna")
+    dna.stats = {}
+    hmmio.write_hmm(dna, str(tmp_path / "dna.hmm"))
+    files.append(str(tmp_path / "dna.hmm"))
+    src = open(files[0]).read()
+    tokv = [l for l in src.splitlines() if l.split() and l.split()[0] == "1"][0].split()[1]   # first match emission of node 1
+    assert src.count(tokv) >= 1
+    (tmp_path / "exp.hmm").write_text(src.replace(tokv, tokv + "e+00"))
+    files.append(str(tmp_path / "exp.hmm"))
+    for f in files:
+        a, b = hmmio.read_hmm(f), hmmio.read_hmm_py(f)
+        assert (a.name, a.abc, a.M, a.cons, a.rf, a.map, a.nseq, a.effn) == (b.name, b.abc, b.M, b.cons, b.rf, b.map, b.nseq, b.effn), f
+        assert np.array_equal(a.mat, b.mat) and np.array_equal(a.ins, b.ins) and np.array_equal(a.t, b.t), f
+        assert (a.compo is None) == (b.compo is None) and (a.compo is None or np.array_equal(a.compo, b.compo))
+        assert set(a.stats) == set(b.stats)
+        for k in a.stats:
+            assert a.stats[k] == pytest.approx(b.stats[k], rel=1e-6)
+    good = open(files[0]).read().splitlines()
+    for name, lines in (("trunc", good[:len(good) // 2]), ("nohdr", good[1:]), ("badnum", [l.replace(tokv, tokv[:2] + "x" + tokv[3:]) for l in good]),
+                        ("noleng", [l for l in good if not l.startswith("LENG")])):
+        (tmp_path / (name + ".hmm")).write_text("\n".join(lines) + "\n")
+        with pytest.raises((hmmio.HMMFormatError, ValueError, IndexError)) as e1:
+            hmmio.read_hmm_py(str(tmp_path / (name + ".hmm")))
+        with pytest.raises(type(e1.value)):
+            hmmio.read_hmm(str(tmp_path / (name + ".hmm")))
