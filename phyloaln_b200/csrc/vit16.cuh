@@ -124,7 +124,7 @@ __device__ __forceinline__ bool vit16_pair(const DevHmm &hm, const uint32_t *tab
 }
 
 template <int BH>
-__global__ void __launch_bounds__(128, (BH <= 4 ? 6 : BH <= 8 ? 4 : BH <= 16 ? 3 : 2)) vit16_kernel(Vit16Args a) {
+__global__ void __launch_bounds__(128, (BH <= 4 ? 6 : BH <= 8 ? 4 : 3)) vit16_kernel(Vit16Args a) {
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   unsigned long long nneed = 0;
   for (unsigned long long i = a.begin + (unsigned long long)blockIdx.x * wpb + wib; i < a.end; i += (unsigned long long)gridDim.x * wpb) {
