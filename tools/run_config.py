@@ -49,7 +49,7 @@ t0 = time.perf_counter()
 bench.calibrate_on_gpu(ctx, hmms, abc=abc)
 t_cal = time.perf_counter() - t0
 sumM = int(sum(h.M for h in hmms))
-chunk = a.chunk or (131072 if a.config in (2, 3, 5) else 8192)
+chunk = a.chunk or (131072 if a.config in (2, 3, 5) else 65536)
 tot_s, tot_units, tot_hits, planted = 0.0, 0, 0, 0
 funnel = {k: 0 for k in ("n_pairs", "n_cells", "n_past_ssv", "n_past_msv", "n_past_bias", "n_past_vit", "n_past_fwd", "n_domains")}
 stage = {k: 0.0 for k in ("ms_translate", "ms_msv", "ms_bias", "ms_vit", "ms_fwd", "ms_domain", "ms_total")}
