@@ -170,7 +170,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--hmms", type=int, default=1000)
-    ap.add_argument("--reads-per-step", type=int, default=131072)
+    ap.add_argument("--reads-per-step", type=int, default=524288)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-region", action="store_true", help="cudaProfilerStart/Stop around the timed resident steps (ncu --profile-from-start off)")
     args = ap.parse_args()
@@ -181,8 +181,9 @@ def main():
     config = {"workload": "config2: 150bp synthetic reads (1% planted homologs, 0.1% N) x BUSCO-size protein HMMs, six-frame",
               "n_hmm": args.hmms, "reads_per_step_per_gpu": args.reads_per_step, "read_len": 150,
               "frames": 6, "full_config_reads": 10_000_000,
-              "l2": "inputs larger than L2: every step streams ~190 MB of per-profile score tables (1000 profiles) "
-                    "plus a fresh, different read chunk; no explicit flush"}
+              "l2": "inputs larger than L2: every step streams ~190 MB of per-profile score tables (1000 profiles) per L2-sized "
+                    "super-tile of targets plus a fresh, different read chunk (164 MB of translated targets at 524,288 reads); "
+                    "no explicit flush"}
     hmms = build_profiles(args.hmms, seed=2002)
 
     if args.impl == "reference":
@@ -327,9 +328,10 @@ def main():
                          "achieved": 4.0 * msv_cells_s / 1e12, "peak": 4.0 * peak_cells / 1e12,
                          "unit": "T 16-bit lane-op/s (algorithmic 4 per DP cell)",
                          "frac": msv_cells_s / peak_cells,
-                         # dram__bytes_read.sum + dram__bytes_write.sum of msv_pack_kernel, one `ncu --set full` capture of this
-                         # command at the default 131,072 reads/step (profiles/r1d_ncu_full_kernels.md): 128.0 MB + 20.8 MB
-                         "traffic": 148.8e6 if args.reads_per_step == 131072 else None, "traffic_unit": "bytes per msv_pack_kernel launch",
+                         # dram__bytes_read.sum + dram__bytes_write.sum of msv_pack_kernel from ncu captures of this command
+                         # (profiles/r1d_ncu_full_kernels.md): 131,072 reads/step 128.0 MB + 20.8 MB (--set full); 524,288 reads/step
+                         # 1,426.3 MB + 83.9 MB with the L2 super-tile work order (metrics-only pass; 87.9 GB before it)
+                         "traffic": {131072: 148.8e6, 524288: 1510.2e6}.get(args.reads_per_step), "traffic_unit": "bytes per msv_pack_kernel launch",
                          "msv_gcups": msv_cells_s / 1e9,
                          "useful_cells_per_clk_per_sm": msv_cells_s / sm_clk / 148.0,
                          "padded_cells_per_clk_per_sm": padded_cells_per_step / (ms_msv * 1e-3) / sm_clk / 148.0,
@@ -340,8 +342,8 @@ def main():
                          "tmem_read_B_per_clk_per_sm": 2.0 * padded_cells_per_step / (ms_msv * 1e-3) / sm_clk / 148.0,
                          "binding_resource": "the half-rate HFMA2 pipe (16 HFMA2.RELU per 1,024-cell warp row = 32 pipe cycles) and warp "
                                              "instruction issue (profiles/r1d_ncu_full_kernels.md)",
-                         "traffic_note": "DRAM traffic is not the bound (149 MB per 547 ms launch = 0.27 GB/s): targets + tables in, candidate "
-                                         "records out; the emission tables live in TMEM",
+                         "traffic_note": "DRAM traffic is not the bound (1.5 GB per 2.19 s launch at 524,288 reads/step, 149 MB per 0.55 s at 131,072): "
+                                         "targets (one L2-sized super-tile at a time) + tables in, candidate records out; emission tables live in TMEM",
                          "ginstr_per_s": dpx},
             "roofline_translate": tr_roof,
             "stage_ms": ms_stage,

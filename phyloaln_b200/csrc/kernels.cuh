@@ -388,6 +388,7 @@ struct MsvArgs {
   const uint16_t *scJ;     // [hmm*nL + li] fp16 bits of the sticky-SSV scale 32*ceil(2048/Cp) (Cp = 1: +inf; Cp <= 0: 0xffff)
   int nL;
   uint32_t tile;           // targets per work item
+  uint32_t super_tiles;    // tiles per L2-sized super-tile: all profiles run over one super-tile of targets before the next
   unsigned long long *work;  // msv_tmem_kernel: next work item (dynamic distribution over CTAs), zeroed per launch
   Pass1 *out;
   unsigned long long *out_count;
@@ -396,6 +397,24 @@ struct MsvArgs {
   int all_pairs;           // 1: emit every pair with its exact MSV result (score_all)
   uint32_t zero;           // always 0; a run-time value so ptxas cannot re-materialise {0,0} per use
 };
+
+// Work item -> (profile slot, target tile).  Items are profile-major INSIDE a super-tile of `T` target tiles (neighbouring items
+// share the profile, so its table is reloaded rarely) and super-tile-major overall, so that a chunk whose targets exceed the L2 is
+// streamed from DRAM once per super-tile instead of once per profile.  T >= ntiles gives the plain profile-major order.
+__device__ __forceinline__ void msv_item_decode(unsigned long long item, uint32_t nlist, uint32_t ntiles, uint32_t T, uint32_t &slot,
+                                                uint32_t &tile) {
+  const uint32_t full = ntiles / T;
+  const unsigned long long per = (unsigned long long)nlist * T, items_full = per * full;
+  if (item < items_full) {
+    const uint32_t s = (uint32_t)(item / per), r = (uint32_t)(item % per);
+    slot = r / T;
+    tile = s * T + r % T;
+  } else {
+    const uint32_t r = (uint32_t)(item - items_full), Ts = ntiles - full * T;
+    slot = r / Ts;
+    tile = full * T + r % Ts;
+  }
+}
 
 template <int Q>
 __global__ void __launch_bounds__(256, 2) msv_kernel(MsvArgs a) {
@@ -411,8 +430,9 @@ __global__ void __launch_bounds__(256, 2) msv_kernel(MsvArgs a) {
   const int lanem1 = (lane + 31) & 31;
   const uint32_t zero = a.zero;
   for (unsigned long long item = blockIdx.x; item < nitems; item += gridDim.x) {
-    const int h = a.hmm_list[item / ntiles];
-    const uint32_t tile = (uint32_t)(item % ntiles);
+    uint32_t slot, tile;
+    msv_item_decode(item, (uint32_t)a.nlist, ntiles, a.super_tiles, slot, tile);
+    const int h = a.hmm_list[slot];
     const DevHmm &hm = a.hmms[h];
     if (h != cur_h) {
       __syncthreads();

@@ -224,8 +224,9 @@ __global__ void __launch_bounds__(MsvTmemCfg<Q>::THREADS, MsvTmemCfg<Q>::MINB) m
     __syncthreads();
     const unsigned long long item = s_item;
     if (item >= nitems) break;
-    const int h = a.hmm_list[item / ntiles];
-    const uint32_t tile = (uint32_t)(item % ntiles);
+    uint32_t slot, tile;
+    msv_item_decode(item, (uint32_t)a.nlist, ntiles, a.super_tiles, slot, tile);
+    const int h = a.hmm_list[slot];
     const DevHmm &hm = a.hmms[h];
     const int nrows = hm.nrows;
     if (h != cur_h) {
@@ -395,8 +396,9 @@ __global__ void __launch_bounds__(1024, 1) msv_pack_kernel(MsvPackArgs pa_, int 
     __syncthreads();
     const unsigned long long item = s_item;
     if (item >= nitems) break;
-    const int pk = (int)(item / ntiles);
-    const uint32_t tile = (uint32_t)(item % ntiles);
+    uint32_t slot, tile;
+    msv_item_decode(item, (uint32_t)pa_.npacks, ntiles, a.super_tiles, slot, tile);
+    const int pk = (int)slot;
     const DevPack pack = pa_.packs[pk];
     const int nrows = pack.nrows;
     const int *mem = pa_.packmem + pack.mem_off;
