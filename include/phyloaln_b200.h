@@ -163,6 +163,11 @@ int pa_score_all(pa_ctx *ctx, int hmm, float *msv, int32_t *msv_raw, float *vit,
  * VIMNMX3.S16x2 per 16 cells). Result in giga thread-instructions per second over the whole GPU. */
 int pa_microbench_dpx(pa_ctx *ctx, int mode, double *ginstr_per_s);
 
+/* The order in which the MSV kernels walk their work items (no reference equivalent): item -> (profile slot, target tile),
+ * profile-major inside an L2-sized super-tile of `super_tiles` target tiles, super-tile-major overall. Host evaluation of the
+ * device function, for tests. 0 ok, -2 bad argument. */
+int pa_msv_item_decode(uint64_t item, uint32_t nlist, uint32_t ntiles, uint32_t super_tiles, uint32_t *slot, uint32_t *tile);
+
 /* cudaProfilerStart / cudaProfilerStop (on != 0 / on == 0): lets `ncu --profile-from-start off` capture
  * only the timed region of bench.py. No reference equivalent. */
 int pa_profiler_range(int on);

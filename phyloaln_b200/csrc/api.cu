@@ -950,6 +950,13 @@ static int check_targets_ready(pa_ctx *ctx) {
 
 #include "search_impl.inc"
 
+// host-side view of the MSV work-item order (same function the kernels run); used by the CPU test-suite
+extern "C" int pa_msv_item_decode(uint64_t item, uint32_t nlist, uint32_t ntiles, uint32_t super_tiles, uint32_t *slot, uint32_t *tile) {
+  if (!slot || !tile || nlist == 0 || ntiles == 0 || super_tiles == 0 || item >= (uint64_t)nlist * ntiles) return -2;
+  msv_item_decode(item, nlist, ntiles, super_tiles, *slot, *tile);
+  return 0;
+}
+
 // accessors for the other translation units (ctx_access.hpp)
 cudaStream_t pa_ctx_stream(pa_ctx *ctx) { return ctx->stream; }
 int pa_ctx_device(pa_ctx *ctx) { return ctx->device; }

@@ -401,7 +401,7 @@ struct MsvArgs {
 // Work item -> (profile slot, target tile).  Items are profile-major INSIDE a super-tile of `T` target tiles (neighbouring items
 // share the profile, so its table is reloaded rarely) and super-tile-major overall, so that a chunk whose targets exceed the L2 is
 // streamed from DRAM once per super-tile instead of once per profile.  T >= ntiles gives the plain profile-major order.
-__device__ __forceinline__ void msv_item_decode(unsigned long long item, uint32_t nlist, uint32_t ntiles, uint32_t T, uint32_t &slot,
+__host__ __device__ __forceinline__ void msv_item_decode(unsigned long long item, uint32_t nlist, uint32_t ntiles, uint32_t T, uint32_t &slot,
                                                 uint32_t &tile) {
   const uint32_t full = ntiles / T;
   const unsigned long long per = (unsigned long long)nlist * T, items_full = per * full;

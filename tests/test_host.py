@@ -258,3 +258,30 @@ def test_native_hmm_reader_equals_python_statement(tmp_path):
             hmmio.read_hmm_py(str(tmp_path / (name + ".hmm")))
         with pytest.raises(type(e1.value)):
             hmmio.read_hmm(str(tmp_path / (name + ".hmm")))
+
+
+def test_msv_work_item_order_is_a_bijection_with_l2_super_tiles():
+    """pa_msv_item_decode (the function the MSV kernels run): every (profile slot, target tile) pair exactly once, tiles of a
+    super-tile contiguous in item order, profile-major inside a super-tile, plain profile-major order when one super-tile
+    covers the chunk."""
+    import ctypes as C
+    from phyloaln_b200 import capi
+    L = capi.load_library()
+    L.pa_msv_item_decode.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+    slot, tile = C.c_uint32(), C.c_uint32()
+    for nlist, ntiles, T in ((7, 10, 3), (1, 1, 1), (5, 9, 9), (5, 9, 100), (3, 12, 4), (466, 37, 5), (2, 1536, 461)):
+        seen, order = set(), []
+        for item in range(nlist * ntiles):
+            assert L.pa_msv_item_decode(item, nlist, ntiles, T, C.byref(slot), C.byref(tile)) == 0
+            assert slot.value < nlist and tile.value < ntiles
+            seen.add((slot.value, tile.value))
+            order.append((slot.value, tile.value))
+        assert len(seen) == nlist * ntiles
+        supers = [t // T for _, t in order]
+        assert supers == sorted(supers)                               # super-tile-major
+        for s in set(supers):                                         # profile-major inside a super-tile
+            sub = [o for o, sp in zip(order, supers) if sp == s]
+            assert sub == sorted(sub)
+        if T >= ntiles:
+            assert order == [(p, t) for p in range(nlist) for t in range(ntiles)]
+    assert L.pa_msv_item_decode(70, 7, 10, 3, C.byref(slot), C.byref(tile)) == -2
