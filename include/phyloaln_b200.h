@@ -24,6 +24,11 @@
  *                                trimming; lib/assemble.py:767-873), read_hit.__init__'s column walk and
  *                                --extend_pos extension (:13-306) and read_hit.consensus()'s per-column
  *                                accumulation (:309-633).
+ *   pa_get_hit_pp                the PP annotation lines of the same report (Bio.SearchIO aln_annotation).
+ *   pa_hmm_file_parse            hmmsearch's reader of ref_hmm/{g}.hmm (HMMER3/f ASCII, written by hmmbuild,
+ *                                lib/aln.py:66-76).
+ *   pa_fasta_*                   lib.read_fastx(..., 'fasta') on all.raw.fasta (lib/library.py:186-198).
+ *   pa_ingest_*                  prepare_target()'s read / tag / split / merge pass (lib/aln.py:274-433).
  *   pa_score_all                 (no reference equivalent) raw filter scores for every
  *                                (profile, target) pair: E-value calibration and parity tests.
  */
