@@ -23,6 +23,8 @@
 #include "kernels.cuh"
 #include "msv_tmem.cuh"
 #include "vit16.cuh"
+#include "wide.cuh"
+#include "launch.hpp"
 #include "domain.cuh"
 #include "gencode.hpp"
 #include "ctx_access.hpp"
@@ -81,18 +83,25 @@ struct pa_ctx {
   DevBuf<int> d_vit;
   DevBuf<uint32_t> d_v16;   // packed tables of vit16_kernel
   DevBuf<uint8_t> d_need;   // per sorted Viterbi input: must the exact kernel run?
-  std::vector<std::pair<int, std::pair<int, int>>> v16_classes;  // (BH, (first rank, last rank + 1))
+  struct VClass { int B, NW, r0, r1; };   // block size (class-rounded), warps per pair (1: single-warp kernels), rank range [r0, r1)
+  std::vector<VClass> v16_classes;
   int use_vit16 = 1;        // PA_VIT16=0: exact kernel on every pair
   DevBuf<float> d_fwd;
   DevBuf<int> d_hmm_lists;
   std::map<int, std::pair<int, int>> q_groups;  // Q -> (offset, count) in d_hmm_lists (all profiles: score_all / single-profile runs)
   std::map<int, std::pair<int, int>> q_groups_rest;  // same, profiles that are not in a pack (d_hmm_lists_rest)
   DevBuf<int> d_hmm_lists_rest;
+  std::map<int, std::pair<int, int>> w_groups;  // wide profiles (M > 2047): tile width QW -> (offset, count) in d_hmm_lists_w
+  DevBuf<int> d_hmm_lists_w;
+  int maxQ_wide = 0;         // widest striped state (words per lane) of msv_exact_wide_kernel
+  DevBuf<uint16_t> d_bnd;    // tile-boundary scratch of msv_wide_kernel
+  DevBuf<Pass1> d_wcand;     // its candidate list
+  DevBuf<float> d_fwdw;      // row scratch of fwd_wide_kernel
   std::vector<DevPack> h_packs;   // packed narrow profiles (msv_pack_kernel)
   DevBuf<DevPack> d_packs;
   DevBuf<int> d_packmem;
   int maxB = 1, maxM = 1;
-  std::vector<std::pair<int, std::pair<int, int>>> vit_classes;  // (Bv, (first rank, last rank + 1))
+  std::vector<VClass> vit_classes;
   std::vector<int> rank_B;  // canonical Forward block size B of the profile at each rank (ranks are sorted by B)
   DevBuf<unsigned int> d_sort;  // cnt | start | cursor, each nh + 1
 
@@ -191,7 +200,7 @@ extern "C" pa_ctx *pa_create(int device, char *err, int errlen) {
 extern "C" void pa_destroy(pa_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
-  ctx->d_hmms.release(); ctx->d_msv.release(); ctx->d_msvh.release(); ctx->d_vit.release(); ctx->d_v16.release(); ctx->d_need.release(); ctx->d_fwd.release(); ctx->d_hmm_lists.release(); ctx->d_hmm_lists_rest.release(); ctx->d_packs.release(); ctx->d_packmem.release(); ctx->d_sort.release();
+  ctx->d_hmms.release(); ctx->d_msv.release(); ctx->d_msvh.release(); ctx->d_vit.release(); ctx->d_v16.release(); ctx->d_need.release(); ctx->d_fwd.release(); ctx->d_hmm_lists.release(); ctx->d_hmm_lists_rest.release(); ctx->d_hmm_lists_w.release(); ctx->d_bnd.release(); ctx->d_wcand.release(); ctx->d_fwdw.release(); ctx->d_packs.release(); ctx->d_packmem.release(); ctx->d_sort.release();
   ctx->d_nt.release(); ctx->d_ntoff.release(); ctx->d_dsq.release(); ctx->d_toff.release(); ctx->d_tlen.release();
   ctx->d_lidx.release(); ctx->d_codon.release(); ctx->d_flag.release();
   ctx->d_L.release(); ctx->d_nullsc.release(); ctx->d_biasA.release(); ctx->d_biasB.release(); ctx->d_tjb.release();
@@ -219,7 +228,7 @@ extern "C" int pa_set_opts(pa_ctx *ctx, const pa_opts *o) {
 extern "C" int pa_add_hmm(pa_ctx *ctx, const char *name, int abc, int M, const double *mat, const double *ins,
                           const double *t, const double *compo, const char *cons, const float *evparam) {
   if (!ctx) return -1;
-  if (M < 1 || M > 2047) { ctx->err = "profile length must be 1..2047"; return -2; }
+  if (M < 1 || M > PA_MAX_M) { ctx->err = "profile length must be 1.." + std::to_string(PA_MAX_M); return -2; }
   if (abc != PA_AMINO && abc != PA_DNA) { ctx->err = "unknown alphabet"; return -2; }
   if (!ctx->hmms.empty() && ctx->hmms[0].abc != abc) { ctx->err = "all profiles of a context must share one alphabet"; return -2; }
   if (ctx->hmms.size() >= 65535) { ctx->err = "too many profiles (max 65535)"; return -2; }
@@ -290,7 +299,8 @@ extern "C" int pa_commit_hmms(pa_ctx *ctx) {
   ctx->h_dev.assign(nh, DevHmm{});
   ctx->maxB = 1;
   ctx->maxM = 1;
-  std::map<int, std::vector<int>> byQ;
+  std::map<int, std::vector<int>> byQ, byW;
+  ctx->maxQ_wide = 0;
   const bool maxmode = ctx->opts.do_max != 0;
   for (int h = 0; h < nh; h++) {
     const HostProfile &hp = ctx->hmms[h];
@@ -302,9 +312,15 @@ extern "C" int pa_commit_hmms(pa_ctx *ctx) {
     d.nrows = Kp;
     d.Q = M / 64 + 1;  // the last striped cell must be padding (see msv_kernel)
     d.B = (M + 31) / 32;
+    const bool wide = d.Q > 32;  // wide.cuh: model-tiled MSV, multi-warp Viterbi, run-time-B Forward
+    d.nT = wide ? (d.Q + 31) / 32 : 0;
+    const int QW = wide ? (d.Q + d.nT - 1) / d.nT : 0;  // words per lane of one MSV tile, 17..32
+    d.NWv = wide ? (M <= 4096 ? 4 : 8) : 1;
+    d.NW16 = wide ? (M <= 4096 ? 2 : 4) : 1;
     ctx->maxB = std::max(ctx->maxB, d.B);
     ctx->maxM = std::max(ctx->maxM, M);
-    byQ[d.Q].push_back(h);
+    if (wide) { byW[QW].push_back(h); ctx->maxQ_wide = std::max(ctx->maxQ_wide, d.Q); }
+    else byQ[d.Q].push_back(h);
     d.tbm = hp.tbm_b; d.tec = hp.tec_b; d.bias = hp.bias_b; d.base = hp.base_b;
     d.base_w = hp.base_w; d.xw_E = hp.xw_E; d.scale_b = hp.scale_b; d.scale_w = hp.scale_w;
     const double F1 = maxmode ? 1.0 : ctx->opts.F1, F2 = maxmode ? 1.0 : ctx->opts.F2, F3 = maxmode ? 1.0 : ctx->opts.F3;
@@ -318,7 +334,7 @@ extern "C" int pa_commit_hmms(pa_ctx *ctx) {
     memcpy(d.eo1, hp.eo1, sizeof(d.eo1));
     memcpy(d.ev, hp.ev, sizeof(d.ev));
 
-    // ---- MSV striped s16x2 table: delta = bias - rbv, dead padding beyond M
+    // ---- MSV striped s16x2 table: delta = bias - rbv, dead padding beyond M (wide profiles: plain [x][q][lane] rows)
     const int Q = d.Q, roww = Q * 32;
     while (msv.size() % 4) msv.push_back(0);
     d.msv_off = msv.size();
@@ -331,13 +347,34 @@ extern "C" int pa_commit_hmms(pa_ctx *ctx) {
             const int cell = (2 * lane + hf) * Q + q, k = cell + 1;
             half[hf] = k <= M ? (int16_t)((int)hp.bias_b - (int)hp.rbv[(size_t)x * (M + 1) + k]) : (int16_t)PA_MSV_DEAD;
           }
-          msv[d.msv_off + (size_t)x * roww + msv_word_pos(Q, q, lane)] = (uint32_t)(uint16_t)half[0] | ((uint32_t)(uint16_t)half[1] << 16);
+          msv[d.msv_off + (size_t)x * roww + (wide ? q * 32 + lane : msv_word_pos(Q, q, lane))] = (uint32_t)(uint16_t)half[0] | ((uint32_t)(uint16_t)half[1] << 16);
         }
 
     // ---- the same deltas as fp16x2 for the tensor-memory kernel (msv_tmem.cuh): words q < QT as
     // [x][q][lane] (TMEM part), words q >= QT striped like the s16 table (shared-memory part, Q > 16)
     d.msvh_off = msvh.size();
-    if (msv_use_tmem(ctx, Q, Kp)) {
+    if (wide) {
+      // nT tiles of 64*QW cells, each laid out like a profile with Q = QW: tile m holds model cells m*64*QW + (2*lane + hf)*QW + q
+      if (msv_tmem_cols_needed(QW, Kp) > 512) { ctx->err = "alphabet too large for the tiled MSV kernel"; return -2; }
+      const int QT = 16, QS = QW - QT;
+      const size_t tilew = (size_t)Kp * QW * 32;
+      msvh.resize(msvh.size() + tilew * d.nT, 0);
+      for (int m = 0; m < d.nT; m++) {
+        uint32_t *tpart = msvh.data() + d.msvh_off + tilew * m, *spart = tpart + (size_t)Kp * QT * 32;
+        for (int x = 0; x < Kp; x++)
+          for (int q = 0; q < QW; q++)
+            for (int lane = 0; lane < 32; lane++) {
+              uint16_t half[2];
+              for (int hf = 0; hf < 2; hf++) {
+                const int cell = m * 64 * QW + (2 * lane + hf) * QW + q, k = cell + 1;
+                half[hf] = h16_exact(k <= M ? (int)hp.bias_b - (int)hp.rbv[(size_t)x * (M + 1) + k] : PA_MSV_DEAD);
+              }
+              const uint32_t word = (uint32_t)half[0] | ((uint32_t)half[1] << 16);
+              if (q < QT) tpart[((size_t)x * QT + q) * 32 + lane] = word;
+              else spart[(size_t)x * QS * 32 + msv_word_pos(QS, q - QT, lane)] = word;
+            }
+      }
+    } else if (msv_use_tmem(ctx, Q, Kp)) {
       const int QT = msv_tmem_qt(Q), QS = Q - QT;
       msvh.resize(msvh.size() + (size_t)Kp * roww, 0);
       uint32_t *tpart = msvh.data() + d.msvh_off, *spart = tpart + (size_t)Kp * QT * 32;
@@ -355,16 +392,18 @@ extern "C" int pa_commit_hmms(pa_ctx *ctx) {
           }
     }
 
-    // ---- Viterbi tables, lane-blocked [j][lane] with the class-rounded block size Bv: k = lane*Bv + j + 1
-    d.Bv = vit_class(d.B);
+    // ---- Viterbi tables, thread-blocked [j][tid] with the class-rounded block size Bv: k = tid*Bv + j + 1
+    // (tid < NT: one warp, or the NWv warps of a CTA for wide profiles)
     {
-      const int Bv = d.Bv, Wv = Bv * 32;
+      const int NT = 32 * d.NWv;
+      d.Bv = vit_class((M + NT - 1) / NT);
+      const int Bv = d.Bv, Wv = Bv * NT;
       while (vit.size() % 4) vit.push_back(0);
       d.vit_off = vit.size();
       vit.resize(vit.size() + (size_t)Wv * (9 + Kp), PA_NEG16);
       int *vA = vit.data() + d.vit_off, *vI = vA + 4 * Wv, *vD = vI + 2 * Wv, *vps = vD + 2 * Wv, *vem = vps + Wv;
       for (int c = 0; c < Wv; c++) {
-        const int k = (c % 32) * Bv + (c / 32) + 1;
+        const int k = (c % NT) * Bv + (c / NT) + 1;
         if (k <= M) {
           const int16_t *tp = &hp.twv[(size_t)(k - 1) * 8], *tk = &hp.twv[(size_t)k * 8];
           vA[4 * c + 0] = tp[T_BM]; vA[4 * c + 1] = tp[T_MM]; vA[4 * c + 2] = tp[T_IM]; vA[4 * c + 3] = tp[T_DM];
@@ -373,19 +412,20 @@ extern "C" int pa_commit_hmms(pa_ctx *ctx) {
           for (int x = 0; x < Kp; x++) vem[(size_t)x * Wv + c] = hp.rwv[(size_t)x * (M + 1) + k];
         }
       }
-      for (int lane = 0; lane < 32; lane++) {  // in-lane prefix sums of DD(k-1)
+      for (int tid = 0; tid < NT; tid++) {  // in-thread prefix sums of DD(k-1)
         int sum = 0;
         for (int j = 0; j < Bv; j++) {
-          const int c = j * 32 + lane;
+          const int c = j * NT + tid;
           sum += vD[2 * c + 1];
           vps[c] = sum;
         }
       }
     }
-    // ---- packed tables of the 16-bit upper-bound pass: half-lane hl = 2*lane + hf owns k = hl*BH + j + 1; every entry >= -16384
-    d.BH = v16_class((M + 63) / 64);
+    // ---- packed tables of the 16-bit upper-bound pass: half-lane hl = 2*tid + hf owns k = hl*BH + j + 1; every entry >= -16384
     {
-      const int BH = d.BH, W16 = BH * 32;
+      const int NT = 32 * d.NW16;
+      d.BH = v16_class((M + 2 * NT - 1) / (2 * NT));
+      const int BH = d.BH, W16 = BH * NT;
       while (v16.size() % 4) v16.push_back(0);
       d.v16_off = v16.size();
       v16.resize(v16.size() + (size_t)W16 * (9 + Kp), 0u);
@@ -394,7 +434,7 @@ extern "C" int pa_commit_hmms(pa_ctx *ctx) {
       auto put = [](uint32_t *w, int hf, int v) { *w = hf ? ((*w & 0x0000ffffu) | ((uint32_t)(v & 0xffff) << 16)) : ((*w & 0xffff0000u) | (uint32_t)(v & 0xffff)); };
       for (int c = 0; c < W16; c++)
         for (int hf = 0; hf < 2; hf++) {
-          const int k = (2 * (c % 32) + hf) * BH + (c / 32) + 1;
+          const int k = (2 * (c % NT) + hf) * BH + (c / NT) + 1;
           int tA[4] = {PA_V16_FLOOR, PA_V16_FLOOR, PA_V16_FLOOR, PA_V16_FLOOR}, tI[2] = {PA_V16_FLOOR, PA_V16_FLOOR},
               tD[2] = {PA_V16_FLOOR, PA_V16_FLOOR};
           if (k <= M) {
@@ -411,11 +451,11 @@ extern "C" int pa_commit_hmms(pa_ctx *ctx) {
             guard = std::max(guard, e);
           }
         }
-      for (int lane = 0; lane < 32; lane++)
+      for (int tid = 0; tid < NT; tid++)
         for (int hf = 0; hf < 2; hf++) {  // in-half-lane prefix sums of DD(k-1), floored
           int sum = 0;
           for (int j = 0; j < BH; j++) {
-            const int c = j * 32 + lane;
+            const int c = j * NT + tid;
             sum = clamp_v16(sum + (int)(short)(hf ? (wD[2 * c + 1] >> 16) : (wD[2 * c + 1] & 0xffff)));
             put(&wps[c], hf, sum);
           }
@@ -441,23 +481,22 @@ extern "C" int pa_commit_hmms(pa_ctx *ctx) {
       }
     }
   }
-  {  // profile rank in (Bv, index) order: the sorted survivor list is then contiguous per Viterbi class
+  {  // profile rank in (M, index) order: the sorted survivor list is then contiguous per Viterbi class and per Forward block size
     std::vector<int> ord(nh);
     for (int h = 0; h < nh; h++) ord[h] = h;
-    // by B: the Viterbi classes (Bv = class of B, monotone in B) stay contiguous, and so do the exact-B groups of fwd_kernel_t
-    std::stable_sort(ord.begin(), ord.end(), [&](int x, int y) { return ctx->h_dev[x].B < ctx->h_dev[y].B; });
+    // by M: B = ceil(M/32), the Viterbi classes (block size and warps per pair) and the vit16 classes are all monotone in M
+    std::stable_sort(ord.begin(), ord.end(), [&](int x, int y) { return ctx->h_dev[x].M < ctx->h_dev[y].M; });
     ctx->rank_B.assign(nh, 1);
     ctx->vit_classes.clear();
     ctx->v16_classes.clear();
     for (int r = 0; r < nh; r++) {
-      ctx->h_dev[ord[r]].rank = r;
-      ctx->rank_B[r] = ctx->h_dev[ord[r]].B;
-      const int bv = ctx->h_dev[ord[r]].Bv;
-      if (ctx->vit_classes.empty() || ctx->vit_classes.back().first != bv) ctx->vit_classes.push_back({bv, {r, r + 1}});
-      else ctx->vit_classes.back().second.second = r + 1;
-      const int bh = ctx->h_dev[ord[r]].BH;   // monotone in B as well
-      if (ctx->v16_classes.empty() || ctx->v16_classes.back().first != bh) ctx->v16_classes.push_back({bh, {r, r + 1}});
-      else ctx->v16_classes.back().second.second = r + 1;
+      DevHmm &d = ctx->h_dev[ord[r]];
+      d.rank = r;
+      ctx->rank_B[r] = d.B;
+      if (ctx->vit_classes.empty() || ctx->vit_classes.back().B != d.Bv || ctx->vit_classes.back().NW != d.NWv) ctx->vit_classes.push_back({d.Bv, d.NWv, r, r + 1});
+      else ctx->vit_classes.back().r1 = r + 1;
+      if (ctx->v16_classes.empty() || ctx->v16_classes.back().B != d.BH || ctx->v16_classes.back().NW != d.NW16) ctx->v16_classes.push_back({d.BH, d.NW16, r, r + 1});
+      else ctx->v16_classes.back().r1 = r + 1;
     }
   }
   // ---- packs of narrow profiles for msv_pack_kernel (first-fit decreasing into 64 half-lanes of 16 cells)
@@ -527,7 +566,7 @@ extern "C" int pa_commit_hmms(pa_ctx *ctx) {
   {  // per-Q lists of the profiles that stay on the per-profile kernels
     std::map<int, std::vector<int>> rest;
     for (int h = 0; h < nh; h++)
-      if (!packed[h]) rest[ctx->h_dev[h].Q].push_back(h);
+      if (!packed[h] && ctx->h_dev[h].nT == 0) rest[ctx->h_dev[h].Q].push_back(h);
     std::vector<int> lists;
     ctx->q_groups_rest.clear();
     for (auto &kv : rest) {
@@ -556,8 +595,18 @@ extern "C" int pa_commit_hmms(pa_ctx *ctx) {
     ctx->q_groups[kv.first] = {(int)lists.size(), (int)kv.second.size()};
     lists.insert(lists.end(), kv.second.begin(), kv.second.end());
   }
-  CK(ctx->d_hmm_lists.ensure(lists.size()));
-  CK(cudaMemcpy(ctx->d_hmm_lists.p, lists.data(), lists.size() * 4, cudaMemcpyHostToDevice));
+  CK(ctx->d_hmm_lists.ensure(lists.size() + 1));
+  if (!lists.empty()) CK(cudaMemcpy(ctx->d_hmm_lists.p, lists.data(), lists.size() * 4, cudaMemcpyHostToDevice));
+  {
+    std::vector<int> wl;
+    ctx->w_groups.clear();
+    for (auto &kv : byW) {
+      ctx->w_groups[kv.first] = {(int)wl.size(), (int)kv.second.size()};
+      wl.insert(wl.end(), kv.second.begin(), kv.second.end());
+    }
+    CK(ctx->d_hmm_lists_w.ensure(wl.size() + 1));
+    if (!wl.empty()) CK(cudaMemcpy(ctx->d_hmm_lists_w.p, wl.data(), wl.size() * 4, cudaMemcpyHostToDevice));
+  }
   CK(ctx->d_counters.ensure(16));
   ctx->committed = true;
   return 0;
@@ -768,100 +817,20 @@ extern "C" int64_t pa_get_targets(pa_ctx *ctx, char *out, uint64_t cap, uint64_t
 // ---------------------------------------------------------------------------------------------
 // search
 // ---------------------------------------------------------------------------------------------
-template <int Q>
-static cudaError_t launch_msv(pa_ctx *ctx, MsvArgs &a, int nrows_max) {
-  const size_t smem = (size_t)nrows_max * Q * 32 * 4;
-  cudaError_t e = cudaFuncSetAttribute(msv_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  int bps = 1;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, msv_kernel<Q>, 256, smem);
-  bps = std::max(1, bps);
-  const uint32_t ntiles = (a.tg.n + a.tile - 1) / a.tile;
-  const unsigned long long nitems = (unsigned long long)a.nlist * ntiles;
-  const int grid = (int)std::min<unsigned long long>(nitems, (unsigned long long)ctx->num_sms * bps);
-  if (grid > 0) msv_kernel<Q><<<grid, 256, smem, ctx->stream>>>(a);
-  ctx->stats.kernel_launches++;
-  return cudaGetLastError();
-}
-
-template <int Q>
-static cudaError_t launch_msv_tmem(pa_ctx *ctx, MsvArgs &a, int nrows) {
-  constexpr int G = 2;
-  const int need = msv_tmem_cols_needed(Q, nrows);
-  int ncols = 32;
-  while (ncols < need) ncols *= 2;
-  // resident CTAs per SM: fixed by the kernel's __launch_bounds__ (register cap) and by TMEM -- every
-  // resident CTA must own its columns, or it would spin in tcgen05.alloc until a neighbour exits
-  const int bps = std::max(1, std::min(MsvTmemCfg<Q>::MINB, 512 / ncols));
-  const size_t smem = (size_t)(nrows + 1) * MsvTmemCfg<Q>::QS * 32 * 4;  // hybrid (Q > 16) only
-  if (smem) {
-    cudaError_t e = cudaFuncSetAttribute(msv_tmem_kernel<Q, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-  }
-  const uint32_t ntiles = (a.tg.n + a.tile - 1) / a.tile;
-  const unsigned long long nitems = (unsigned long long)a.nlist * ntiles;
-  const int grid = (int)std::min<unsigned long long>(nitems, (unsigned long long)ctx->num_sms * bps);
-  a.tab = ctx->d_msvh.p;
-  if (grid > 0) msv_tmem_kernel<Q, G><<<grid, MsvTmemCfg<Q>::THREADS, smem, ctx->stream>>>(a, ncols);
-  ctx->stats.kernel_launches++;
-  return cudaGetLastError();
-}
-
 static cudaError_t dispatch_msv(pa_ctx *ctx, int Q, MsvArgs &a, int nrows) {
-  if (msv_use_tmem(ctx, Q, nrows)) {
-    switch (Q) {
-#define C_(q) case q: return launch_msv_tmem<q>(ctx, a, nrows);
-      C_(1) C_(2) C_(3) C_(4) C_(5) C_(6) C_(7) C_(8) C_(9) C_(10) C_(11) C_(12) C_(13) C_(14) C_(15) C_(16)
-      C_(17) C_(18) C_(19) C_(20) C_(21) C_(22) C_(23) C_(24) C_(25) C_(26) C_(27) C_(28) C_(29) C_(30) C_(31) C_(32)
-#undef C_
-    }
-  }
-  switch (Q) {
-#define C_(q) case q: return launch_msv<q>(ctx, a, nrows);
-    C_(1) C_(2) C_(3) C_(4) C_(5) C_(6) C_(7) C_(8) C_(9) C_(10) C_(11) C_(12) C_(13) C_(14) C_(15) C_(16)
-    C_(17) C_(18) C_(19) C_(20) C_(21) C_(22) C_(23) C_(24) C_(25) C_(26) C_(27) C_(28) C_(29) C_(30) C_(31) C_(32)
-#undef C_
-  }
-  return cudaErrorInvalidValue;
+  const bool tmem = msv_use_tmem(ctx, Q, nrows);
+  if (tmem) a.tab = ctx->d_msvh.p;
+  return launch_msv_q(Q, tmem, a, nrows, ctx->num_sms, ctx->stream, &ctx->stats.kernel_launches);
 }
 
 static cudaError_t side_fork(pa_ctx *ctx);
 static cudaError_t side_join(pa_ctx *ctx);
 
-template <int BT>
-static cudaError_t launch_vit(pa_ctx *ctx, VitArgs &v, cudaStream_t st) {
-  const unsigned long long n = v.end - v.begin;
-  if (n == 0) return cudaSuccess;
-  const int grid = (int)std::min<unsigned long long>((n + 3) / 4, (unsigned long long)ctx->num_sms * 16);
-  vit_kernel<BT><<<grid, 128, 0, st>>>(v);
-  ctx->stats.kernel_launches++;
-  return cudaGetLastError();
+static cudaError_t dispatch_vit16(pa_ctx *ctx, int BH, int NW, Vit16Args &v, cudaStream_t st) {
+  return launch_vit16_class(BH, NW, v, ctx->num_sms, st, &ctx->stats.kernel_launches);
 }
-template <int BH>
-static cudaError_t launch_vit16(pa_ctx *ctx, Vit16Args &v, cudaStream_t st) {
-  const unsigned long long n = v.end - v.begin;
-  if (n == 0) return cudaSuccess;
-  const int grid = (int)std::min<unsigned long long>((n + 3) / 4, (unsigned long long)ctx->num_sms * 24);
-  vit16_kernel<BH><<<grid, 128, 0, st>>>(v);
-  ctx->stats.kernel_launches++;
-  return cudaGetLastError();
-}
-static cudaError_t dispatch_vit16(pa_ctx *ctx, int BH, Vit16Args &v, cudaStream_t st) {
-  switch (BH) {
-#define C_(b) case b: return launch_vit16<b>(ctx, v, st);
-    C_(1) C_(2) C_(3) C_(4) C_(5) C_(6) C_(7) C_(8) C_(10) C_(12) C_(14) C_(16) C_(20) C_(24) C_(28) C_(32)
-#undef C_
-  }
-  return cudaErrorInvalidValue;
-}
-
-static cudaError_t dispatch_vit(pa_ctx *ctx, int Bv, VitArgs &v, cudaStream_t st) {
-  switch (Bv) {
-#define C_(b) case b: return launch_vit<b>(ctx, v, st);
-    C_(1) C_(2) C_(3) C_(4) C_(6) C_(8) C_(10) C_(12) C_(14) C_(16) C_(20) C_(24) C_(28) C_(32) C_(40) C_(48) C_(56) C_(64)
-#undef C_
-  }
-  return cudaErrorInvalidValue;
+static cudaError_t dispatch_vit(pa_ctx *ctx, int Bv, int NW, VitArgs &v, cudaStream_t st) {
+  return launch_vit_class(Bv, NW, v, ctx->num_sms, st, &ctx->stats.kernel_launches);
 }
 
 // Fork: side streams wait for everything queued on the main stream; join: the main stream waits for them.
@@ -886,34 +855,14 @@ static cudaError_t side_join(pa_ctx *ctx) {
   return cudaSuccess;
 }
 
-template <int B>
-static cudaError_t launch_fwd_t(pa_ctx *ctx, FwdTArgs &a, cudaStream_t st) {
-  const unsigned long long n = a.end - a.begin;
-  if (n == 0) return cudaSuccess;
-  // B <= 32: rows in registers, 4 warps per block. B > 32: 4 shared-memory rows per warp, as many warps as fit in ~96 KB
-  constexpr size_t per_warp = B <= 32 ? 0 : (size_t)4 * B * 32 * 4;
-  int wpb = 4;
-  if constexpr (per_warp != 0) wpb = (int)std::max<size_t>(1, std::min<size_t>(4, (96 * 1024) / per_warp));
-  const size_t smem = per_warp * wpb;
-  if (smem) {
-    cudaError_t e = cudaFuncSetAttribute(fwd_kernel_t<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-  }
-  const int grid = (int)std::min<unsigned long long>((n + wpb - 1) / wpb, (unsigned long long)ctx->num_sms * 32);
-  fwd_kernel_t<B><<<grid, wpb * 32, smem, st>>>(a);
-  ctx->stats.kernel_launches++;
-  return cudaGetLastError();
-}
 static cudaError_t dispatch_fwd_t(pa_ctx *ctx, int B, FwdTArgs &a, cudaStream_t st) {
-  switch (B) {
-#define C_(b) case b: return launch_fwd_t<b>(ctx, a, st);
-    C_(1) C_(2) C_(3) C_(4) C_(5) C_(6) C_(7) C_(8) C_(9) C_(10) C_(11) C_(12) C_(13) C_(14) C_(15) C_(16)
-    C_(17) C_(18) C_(19) C_(20) C_(21) C_(22) C_(23) C_(24) C_(25) C_(26) C_(27) C_(28) C_(29) C_(30) C_(31) C_(32)
-    C_(33) C_(34) C_(35) C_(36) C_(37) C_(38) C_(39) C_(40) C_(41) C_(42) C_(43) C_(44) C_(45) C_(46) C_(47) C_(48)
-    C_(49) C_(50) C_(51) C_(52) C_(53) C_(54) C_(55) C_(56) C_(57) C_(58) C_(59) C_(60) C_(61) C_(62) C_(63) C_(64)
-#undef C_
+  float *scratch = nullptr;
+  if (B > 64 && a.end > a.begin) {  // fwd_wide_kernel: rows in a per-warp global scratch sized for the widest profile
+    cudaError_t e = ctx->d_fwdw.ensure(fwd_wide_per_warp(ctx->maxB) * 4 * (size_t)fwd_wide_grid(a.end - a.begin, ctx->num_sms));
+    if (e != cudaSuccess) return e;
+    scratch = ctx->d_fwdw.p;
   }
-  return cudaErrorInvalidValue;
+  return launch_fwd_b(B, a, ctx->num_sms, scratch, ctx->maxB, st, &ctx->stats.kernel_launches);
 }
 
 // counting sort of n Pass2 records by profile rank: in -> out; start[] (host copy) gets nh + 1 offsets

@@ -2,4 +2,4 @@
 # Builds phyloaln_b200/libphyloaln_b200.so for sm_100a (B200); see Makefile. Extra nvcc flags: EXTRA="...".
 set -e
 cd "$(dirname "$0")"
-make -j4 -s "$@"
+make -j8 -s "$@"

@@ -480,7 +480,7 @@ __device__ int resolve_multidomain(const FwdTabs &T, const uint8_t *sub, int Lr,
   return nenv;
 }
 
-__global__ void __launch_bounds__(128) domain_kernel(DomArgs a) {
+static __global__ void __launch_bounds__(128) domain_kernel(DomArgs a) {
   const int lane = threadIdx.x & 31;
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   float *slab = a.scratch + (size_t)gw * a.slab_floats;

@@ -39,6 +39,8 @@ struct DevHmm {
   unsigned long long fwd_off;   // floats into fwd pool: trA | trB | bwA | bwB | em[Kp]
   unsigned long long v16_off;   // uint32 words into the packed Viterbi pool of vit16_kernel (vit16.cuh)
   int BH, v16_guard;            // words per lane of vit16_kernel (class-rounded ceil(M/64)); headroom its values need below 32767
+  int nT;                       // wide profiles (M > 2047, wide.cuh): model tiles of msv_wide_kernel (0: not wide); msvh_off -> nT tile tables,
+  int NWv, NW16;                // msv_off -> plain [x][q][lane] table; warps per pair of vit_wide_kernel / vit16_wide_kernel (1: not wide)
   int tbm, tec, bias, base;
   int base_w, xw_E;
   float scale_b, scale_w;
@@ -135,7 +137,7 @@ __device__ __forceinline__ uint32_t target_base(unsigned long long ntoff, uint32
 // needs straight from global memory.  Used for nucleotide targets and for reads longer than the
 // staging buffer of translate_kernel.
 #define PA_TR_MAXL 1024
-__device__ void translate_read_generic(const char *__restrict__ nt, unsigned long long o, int L, uint32_t r, int moltype, int nfwd,
+static __device__ void translate_read_generic(const char *__restrict__ nt, unsigned long long o, int L, uint32_t r, int moltype, int nfwd,
                                        int nrev, const uint8_t *tab64, uint8_t *__restrict__ out, uint32_t *__restrict__ tgt_off,
                                        uint32_t *__restrict__ tgt_len, int *__restrict__ err, int lane) {
   const int nframes = nfwd + nrev;
@@ -178,7 +180,7 @@ __device__ void translate_read_generic(const char *__restrict__ nt, unsigned lon
   }
 }
 
-__global__ void __launch_bounds__(256) translate_generic_kernel(const char *__restrict__ nt, const unsigned long long *__restrict__ off,
+static __global__ void __launch_bounds__(256) translate_generic_kernel(const char *__restrict__ nt, const unsigned long long *__restrict__ off,
                                                                 uint32_t nreads, int moltype, int nfwd, int nrev,
                                                                 const uint8_t *__restrict__ tab64, uint8_t *__restrict__ out,
                                                                 uint32_t *__restrict__ tgt_off, uint32_t *__restrict__ tgt_len,
@@ -195,7 +197,7 @@ __global__ void __launch_bounds__(256) translate_generic_kernel(const char *__re
 
 // Exact IUPAC path for one triplet (Biopython rules): forward residue and the residue of the reverse
 // complement.  Kept out of line: it runs for the ~0.3 % of triplets that contain a non-ACGTU letter.
-__device__ __noinline__ int translate_ambiguous(int m0, int m1, int m2, const uint8_t *tab64) {
+static __device__ __noinline__ int translate_ambiguous(int m0, int m1, int m2, const uint8_t *tab64) {
   auto one = [&](int a0, int a1, int a2) -> int {
     uint32_t seen = 0;
     int nstop = 0, ntot = 0;
@@ -232,7 +234,7 @@ __device__ __noinline__ int translate_ambiguous(int m0, int m1, int m2, const ui
 //      is then copied out with coalesced 32-bit stores.
 // HBM traffic per read: L bytes in, six 4-byte-padded frames out (446 B algorithmic for 150 bp).
 template <int NFWD, int NREV>
-__global__ void __launch_bounds__(256) translate_kernel(const char *__restrict__ nt, const unsigned long long *__restrict__ off,
+static __global__ void __launch_bounds__(256) translate_kernel(const char *__restrict__ nt, const unsigned long long *__restrict__ off,
                                                         uint32_t nreads, const uint8_t *__restrict__ tab64,
                                                         uint8_t *__restrict__ out, uint32_t *__restrict__ tgt_off,
                                                         uint32_t *__restrict__ tgt_len, int *__restrict__ err) {
@@ -323,13 +325,13 @@ __global__ void __launch_bounds__(256) translate_kernel(const char *__restrict__
   }
 }
 
-__global__ void lidx_kernel(const uint32_t *__restrict__ len, const uint16_t *__restrict__ L2li, uint16_t *__restrict__ lidx, uint32_t n) {
+static __global__ void lidx_kernel(const uint32_t *__restrict__ len, const uint16_t *__restrict__ L2li, uint16_t *__restrict__ lidx, uint32_t n) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) lidx[i] = L2li[len[i]];
 }
 
 // protein / pre-digitised targets: ASCII -> digital codes
-__global__ void digitize_kernel(const char *__restrict__ in, const unsigned long long *__restrict__ in_off,
+static __global__ void digitize_kernel(const char *__restrict__ in, const unsigned long long *__restrict__ in_off,
                                 const uint32_t *__restrict__ tgt_off, uint32_t n, int abc, uint8_t *__restrict__ out) {
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   for (uint32_t s = blockIdx.x * wpb + wib; s < n; s += gridDim.x * wpb) {
@@ -417,7 +419,7 @@ __host__ __device__ __forceinline__ void msv_item_decode(unsigned long long item
 }
 
 template <int Q>
-__global__ void __launch_bounds__(256, 2) msv_kernel(MsvArgs a) {
+static __global__ void __launch_bounds__(256, 2) msv_kernel(MsvArgs a) {
   extern __shared__ __align__(16) uint32_t s_tab[];  // nrows * Q*32 words
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   const uint32_t ntiles = (a.tg.n + a.tile - 1) / a.tile;
@@ -535,7 +537,7 @@ __global__ void __launch_bounds__(256, 2) msv_kernel(MsvArgs a) {
 }
 
 // per (profile, length) minimal passing MSV xJ byte
-__global__ void msv_threshold_kernel(const DevHmm *hmms, int nh, LenTabs lt, int16_t *thrJ, uint16_t *scJ, int all_pass) {
+static __global__ void msv_threshold_kernel(const DevHmm *hmms, int nh, LenTabs lt, int16_t *thrJ, uint16_t *scJ, int all_pass) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= nh * lt.n) return;
   int h = idx / lt.n, li = idx % lt.n;
@@ -575,7 +577,7 @@ __device__ __forceinline__ float msv_score_from_xJ(const DevHmm &hm, int xJ, int
 // ---------------------------------------------------------------------------------------------
 // bias filter: one thread per MSV survivor
 // ---------------------------------------------------------------------------------------------
-__device__ float bias_filtersc(const DevHmm &hm, const uint8_t *p, int L, float lenA, float lenB) {
+static __device__ float bias_filtersc(const DevHmm &hm, const uint8_t *p, int L, float lenA, float lenB) {
   float d0 = 0.999f, d1 = 0.001f * hm.eo1[p[0]];
   int sexp = 0;
   for (int i = 1;; i++) {
@@ -608,7 +610,7 @@ struct BiasArgs {
   float *bias_out;  // optional (score_all): filtersc per input record
 };
 
-__global__ void bias_kernel(BiasArgs a) {
+static __global__ void bias_kernel(BiasArgs a) {
   unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
   if (i >= a.n_in) return;
   Pass1 r = a.in[i];
@@ -735,7 +737,7 @@ struct VitArgs {
 
 // register budget per class: keep several warps per scheduler for the common (M <= 512) profiles
 template <int BT>
-__global__ void __launch_bounds__(128, (BT <= 8 ? 5 : BT <= 16 ? 4 : BT <= 24 ? 3 : BT <= 32 ? 2 : 1)) vit_kernel(VitArgs a) {
+static __global__ void __launch_bounds__(128, (BT <= 8 ? 5 : BT <= 16 ? 4 : BT <= 24 ? 3 : BT <= 32 ? 2 : 1)) vit_kernel(VitArgs a) {
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   for (unsigned long long i = a.begin + (unsigned long long)blockIdx.x * wpb + wib; i < a.end; i += (unsigned long long)gridDim.x * wpb) {
     if (a.need && !a.need[i]) continue;
@@ -763,12 +765,12 @@ __global__ void __launch_bounds__(128, (BT <= 8 ? 5 : BT <= 16 ? 4 : BT <= 24 ? 
 }
 
 // ---- counting sort of a Pass2 list by profile rank (groups pairs of one profile together) ----
-__global__ void hist_kernel(const Pass2 *in, unsigned long long n, const DevHmm *hmms, unsigned int *cnt) {
+static __global__ void hist_kernel(const Pass2 *in, unsigned long long n, const DevHmm *hmms, unsigned int *cnt) {
   unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
   if (i < n) atomicAdd(&cnt[hmms[in[i].h].rank], 1u);
 }
 // single block: exclusive scan of cnt[0..nh) into start[] (also copied to cursor[]); start[nh] = total
-__global__ void scan_kernel(const unsigned int *cnt, int nh, unsigned int *start, unsigned int *cursor) {
+static __global__ void scan_kernel(const unsigned int *cnt, int nh, unsigned int *start, unsigned int *cursor) {
   __shared__ unsigned int carry;
   __shared__ unsigned int buf[1024];
   if (threadIdx.x == 0) carry = 0;
@@ -791,7 +793,7 @@ __global__ void scan_kernel(const unsigned int *cnt, int nh, unsigned int *start
   }
   if (threadIdx.x == 0) start[nh] = carry;
 }
-__global__ void scatter_kernel(const Pass2 *in, unsigned long long n, const DevHmm *hmms, unsigned int *cursor, Pass2 *out) {
+static __global__ void scatter_kernel(const Pass2 *in, unsigned long long n, const DevHmm *hmms, unsigned int *cursor, Pass2 *out) {
   unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
   if (i < n) {
     const Pass2 r = in[i];
@@ -843,7 +845,7 @@ __device__ __forceinline__ FwdTabs fwd_tabs(const DevHmm &hm, const float *pool)
 }
 
 // One forward row. Arrays are [j*32+lane]; cells beyond M stay 0. wP: scratch row. Returns xE.
-__device__ float fwd_row(const FwdTabs &T, int x, const float *Mp, const float *Ip, const float *Dp, float xBp,
+static __device__ float fwd_row(const FwdTabs &T, int x, const float *Mp, const float *Ip, const float *Dp, float xBp,
                          float *Mc, float *Ic, float *Dc, float *wP, int lane) {
   const int B = T.B;
   const float *em = T.em + (size_t)x * T.W;
@@ -903,7 +905,7 @@ __device__ __forceinline__ void scale_row(float *Mc, float *Ic, float *Dc, int B
 
 // Forward parser over p[0..L-1]; sm: 7 rows of W floats (zero-initialised here). Optionally stores
 // per-row specials/exponents (sp/sexp index 0..L). Returns exponent, *mant = xC*tCT.
-__device__ int fwd_parser(const FwdTabs &T, const uint8_t *p, int L, int Lcfg, int multihit, float *sm, int lane,
+static __device__ int fwd_parser(const FwdTabs &T, const uint8_t *p, int L, int Lcfg, int multihit, float *sm, int lane,
                           float *mant, Specials *sp, int *sexp) {
   const int W = T.W;
   float *Mp = sm, *Ip = sm + W, *Dp = sm + 2 * W, *Mc = sm + 3 * W, *Ic = sm + 4 * W, *Dc = sm + 5 * W, *wP = sm + 6 * W;
@@ -1062,7 +1064,7 @@ struct FwdTArgs {
 };
 
 template <int B>
-__global__ void __launch_bounds__(128) fwd_kernel_t(FwdTArgs a) {
+static __global__ void __launch_bounds__(128) fwd_kernel_t(FwdTArgs a) {
   extern __shared__ __align__(16) float s_fwdt[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   float *rows = s_fwdt + (size_t)wib * 4 * B * 32;  // used only when B > 32
@@ -1097,7 +1099,7 @@ __global__ void __launch_bounds__(128) fwd_kernel_t(FwdTArgs a) {
 // ---------------------------------------------------------------------------------------------
 namespace pa {
 template <int MODE>
-__global__ void __launch_bounds__(256) dpx_microbench_kernel(uint32_t *out, int iters, uint32_t seed) {
+static __global__ void __launch_bounds__(256) dpx_microbench_kernel(uint32_t *out, int iters, uint32_t seed) {
   uint32_t v[8], d = seed ^ threadIdx.x, m = 0;
 #pragma unroll
   for (int i = 0; i < 8; i++) v[i] = (threadIdx.x * 2654435761u + i) & 0x00ff00ffu;

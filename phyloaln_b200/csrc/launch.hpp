@@ -1,0 +1,33 @@
+// launch.hpp -- launch wrappers of the templated kernel families, one translation unit per family
+// (msv_launch.cu, vit_launch.cu, fwd_launch.cu) so that the ~250 instantiations build in parallel.
+// Every function launches at most one kernel on `st` and returns cudaGetLastError(); *launched is
+// incremented when a kernel was launched (the caller's gpu_launches counter).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "kernels.cuh"
+#include "msv_tmem.cuh"
+#include "vit16.cuh"
+#include "wide.cuh"
+
+namespace pa {
+
+// msv_kernel<Q> (shared-memory DPX kernel) or msv_tmem_kernel<Q,2> (table in tensor memory; a.tab must point at the fp16 pool)
+cudaError_t launch_msv_q(int Q, bool tmem, MsvArgs &a, int nrows, int num_sms, cudaStream_t st, uint64_t *launched);
+cudaError_t launch_msv_pack(MsvPackArgs &pk, int ncols, int grid, cudaStream_t st, uint64_t *launched);
+cudaError_t launch_msv_wide(int QW, MsvWideArgs &wa, int ncols, int grid, size_t smem, cudaStream_t st, uint64_t *launched);
+cudaError_t launch_msv_exact_wide(MsvExactWideArgs &ex, int num_sms, cudaStream_t st, uint64_t *launched);
+
+// NW == 1: vit16_kernel<BH> / vit_kernel<Bv>; NW > 1: the multi-warp kernels of wide.cuh
+cudaError_t launch_vit16_class(int BH, int NW, Vit16Args &v, int num_sms, cudaStream_t st, uint64_t *launched);
+cudaError_t launch_vit_class(int Bv, int NW, VitArgs &v, int num_sms, cudaStream_t st, uint64_t *launched);
+
+// B <= 64: fwd_kernel_t<B>.  B > 64: fwd_wide_kernel over `scratch` (fwd_wide_grid(n) * 4 warps * fwd_wide_per_warp(maxB) floats)
+cudaError_t launch_fwd_b(int B, FwdTArgs &a, int num_sms, float *scratch, int maxB, cudaStream_t st, uint64_t *launched);
+inline size_t fwd_wide_per_warp(int maxB) { return (size_t)7 * maxB * 32; }
+inline int fwd_wide_grid(unsigned long long n, int num_sms) {
+  const unsigned long long g = (n + 3) / 4, cap = (unsigned long long)num_sms * 4;
+  return (int)(g < cap ? g : cap);
+}
+
+}  // namespace pa

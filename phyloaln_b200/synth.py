@@ -93,3 +93,67 @@ def plant_reads(reads: np.ndarray, hmms: list[HMM], frac: float, rng: np.random.
             b = bytearray(bytes(b).translate(comp)[::-1])
         reads[r] = np.frombuffer(bytes(b), dtype=np.uint8)
     return idx
+
+
+# ---------------------------------------------------------------------------------------------
+# The BASELINE.json workloads, shared by tools/run_config.py, the per-config
+# parity checks (tests/config_parity.py) and the file-to-file benchmark (tools/dropin_bench.py)
+# ---------------------------------------------------------------------------------------------
+CONFIG_SHAPES = {
+    2: dict(units=10_000_000, n_hmm=1000, abc="amino", unit="reads", chunk=131072,
+            what="10 M x 150 bp reads, six-frame, vs 1,000 BUSCO-size protein HMMs"),
+    3: dict(units=10_000_000, n_hmm=1000, abc="dna", unit="reads", chunk=131072,
+            what="10 M x 150 bp reads (+ reverse complement) vs 1,000 DNA HMMs, M = 3 x the protein widths (300..6,000)"),
+    4: dict(units=200_000, n_hmm=3000, abc="amino", unit="transcripts", chunk=65536,
+            what="200 k transcripts of 0.5-5 kb (30 % carry one or two planted domains), six-frame, vs 3,000 protein HMMs"),
+    5: dict(units=100_000_000, n_hmm=3000, abc="amino", unit="reads", chunk=131072,
+            what="100 M x 150 bp reads, six-frame, vs 3,000 protein HMMs"),
+}
+
+
+def config_rng(config: int) -> np.random.Generator:
+    return np.random.default_rng(3000 + config)
+
+
+def config_profiles(config: int, rng: np.random.Generator, n_hmm: int | None = None) -> list[HMM]:
+    """The profile set of one BASELINE.json config (uncalibrated; consumes `rng` exactly as tools/run_config.py does)."""
+    shape = CONFIG_SHAPES[config]
+    n_hmm = n_hmm or shape["n_hmm"]
+    Ms = busco_lengths(n_hmm, rng)
+    if config == 3:
+        Ms = 3 * Ms   # nucleotide models of the same genes: 300..6,000 columns
+    return [random_hmm(f"c{config}_{i:04d}", int(Ms[i]), rng, abc=shape["abc"]) for i in range(n_hmm)]
+
+
+def config_chunk(config: int, n: int, rng: np.random.Generator, hmms: list[HMM]):
+    """One chunk of n reads / transcripts of the config: (nt uint8, off uint64[n+1], number planted)."""
+    abc = CONFIG_SHAPES[config]["abc"]
+    n_hmm = len(hmms)
+    planted = 0
+    if config in (2, 3, 5):
+        reads = random_reads(n, 150, rng)
+        if abc == "amino":
+            planted = len(plant_reads(reads, hmms, 0.01, rng))
+        else:  # fragments sampled from the DNA profiles themselves
+            for r in rng.choice(n, size=n // 100, replace=False):
+                h = hmms[int(rng.integers(n_hmm))]
+                s = int(rng.integers(1, h.M - 150 + 1)) if h.M > 151 else 1
+                frag = sample_protein(h, rng, s, min(h.M, s + 149)).encode()
+                reads[r, :len(frag)] = np.frombuffer(frag, dtype=np.uint8)
+                planted += 1
+        return reads.reshape(-1), np.arange(n + 1, dtype=np.uint64) * 150, planted
+    lens = rng.integers(500, 5001, n)
+    off = np.zeros(n + 1, dtype=np.uint64)
+    off[1:] = np.cumsum(lens)
+    nt = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, int(off[-1]))].copy()
+    for r in np.nonzero(rng.random(n) < 0.3)[0]:
+        for _ in range(int(rng.integers(1, 3))):
+            h = hmms[int(rng.integers(n_hmm))]
+            x = int(rng.integers(1, max(2, h.M // 2)))
+            y = int(rng.integers(min(h.M, x + 30), h.M + 1))
+            frag = np.frombuffer(back_translate(sample_protein(h, rng, x, y)).encode(), dtype=np.uint8)
+            if len(frag) < lens[r]:
+                p = int(off[r]) + int(rng.integers(0, lens[r] - len(frag)))
+                nt[p:p + len(frag)] = frag
+                planted += 1
+    return nt, off, planted
