@@ -48,7 +48,7 @@ def compare_with_oracle(O, hmms, targets, hits, model, aligned, pp, nthreads):
     nwant, max_bits, max_lnp = 0, 0.0, 0.0
     funnel = np.zeros(6, dtype=np.int64)
     for hi, h in enumerate(hmms):
-        ohits, tr = O.Profile.from_hmm(h).search(targets, nthreads=nthreads, want_trace=False)
+        ohits, tr = O.Profile.from_hmm(h).search(targets, nthreads=nthreads)
         funnel += np.bincount(tr["stage"], minlength=6)
         for oh in ohits:
             nwant += 1
@@ -163,7 +163,8 @@ def verify_config(config: int, n_units: int | None = None, n_sel: int = 32, devi
     ka = np.lexsort((a["dom_idx"], a["target"], a["hmm"]))
     kb = np.lexsort((b["dom_idx"], b["target"], b["hmm"]))
     assert len(a) == len(b), ("full profile set vs selected profiles", len(a), len(b))
-    assert a[ka].tobytes() == b[kb].tobytes(), "hit records differ between the full profile set and the selected profiles"
+    for f in a.dtype.names:
+        assert np.array_equal(a[f][ka], b[f][kb], equal_nan=(a[f].dtype.kind == "f")), ("full profile set vs selected profiles", f)
     for x, y in zip(ka, kb):
         i = keep[int(x)]
         assert modelA2[i] == modelB[int(y)] and alignedA2[i] == alignedB[int(y)] and ppA2[i] == ppB[int(y)]
@@ -204,13 +205,18 @@ def verify_msv_impl(n_reads: int = 524288, device: int = 0, log=lambda *a: None)
         st = ctx.stats()
         ctx.close()
         k = np.lexsort((hits["dom_idx"], hits["target"], hits["hmm"]))
-        h2 = hits[k].copy()
-        h2["ali_off"] = 0
-        out[impl] = (h2.tobytes(), [model[i] for i in k], [aligned[i] for i in k],
+        out[impl] = (hits[k], [model[i] for i in k], [aligned[i] for i in k],
                      {f: int(st[f]) for f in ("n_pairs", "n_past_msv", "n_past_bias", "n_past_vit", "n_past_fwd", "n_domains")}, float(st["ms_msv"]))
         log(f"  {impl}: funnel {out[impl][3]}, msv stage {out[impl][4]:.0f} ms")
     assert out["tmem"][3] == out["smem"][3], (out["tmem"][3], out["smem"][3])
-    assert out["tmem"][0] == out["smem"][0] and out["tmem"][1] == out["smem"][1] and out["tmem"][2] == out["smem"][2]
+    ha, hb_ = out["tmem"][0], out["smem"][0]
+    assert len(ha) == len(hb_)
+    for f in ha.dtype.names:
+        if f == "ali_off":   # position in the string pool: depends on the order the survivors were appended
+            continue
+        bad = np.flatnonzero(~((ha[f] == hb_[f]) | ((ha[f] != ha[f]) & (hb_[f] != hb_[f]))))
+        assert len(bad) == 0, (f, len(bad), ha[bad[:3]], hb_[bad[:3]])
+    assert out["tmem"][1] == out["smem"][1] and out["tmem"][2] == out["smem"][2]
     return {"check": "config 2, one bench-size step: TMEM path (packs, super-tiles) vs shared-memory DPX kernel", "reads": n_reads,
             "n_profiles": len(hmms), "funnel": out["tmem"][3], "identical_pass1_sets_and_hits": True,
             "ms_msv_tmem": out["tmem"][4], "ms_msv_smem": out["smem"][4], "ok": True}
