@@ -8,8 +8,8 @@
  *
  * What each entry point replaces in the reference (/root/reference):
  *   pa_add_hmm / pa_commit_hmms  the `ref_hmm/{g}.hmm` argument of the hmmsearch command line
- *                                (lib/aln.py:664-666); parsing of the ASCII file stays in the
- *                                Python host (phyloaln_b200/hmmio.py), arrays cross the ABI.
+ *                                (lib/aln.py:664-666); the ASCII file is read by pa_hmm_file_parse (below),
+ *                                its arrays cross the ABI here.  Profiles of 1..8192 columns.
  *   pa_load_reads                raw2target(): six-frame / codon translation or reverse
  *                                complement of a chunk of reads (lib/aln.py:233-259) fused with
  *                                HMMER's digitisation of all.target.fasta.
@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define PA_ABI_VERSION 2
+#define PA_ABI_VERSION 3
 #define PA_AMINO 0
 #define PA_DNA 1
 
@@ -139,7 +139,8 @@ int pa_num_hmms(pa_ctx *ctx);
 /* Targets. nt: concatenated ASCII nucleotides, off[nreads+1] byte offsets (HOST memory).
  * Produces nreads*nframes targets: TRANSLATE: frames pos1..3 (+ rev_pos1..3 unless no_reverse;
  * only pos1 if codon_only); NUCLEOTIDE: read (+ reverse complement). Returns #targets or <0.
- * -2: invalid nucleotide character (Biopython would raise TranslationError). */
+ * -2: invalid nucleotide character (Biopython would raise TranslationError) or unsupported genetic code;
+ * -3: capacity (2*nt + 32*reads >= 4 GiB, or more than 65,535 distinct target lengths): split the chunk and retry. */
 int64_t pa_load_reads(pa_ctx *ctx, const char *nt, const uint64_t *off, uint32_t nreads, int moltype,
                       int gencode, int no_reverse, int codon_only);
 int64_t pa_load_proteins(pa_ctx *ctx, const char *aa, const uint64_t *off, uint32_t nseq, int abc);
@@ -213,15 +214,36 @@ void pa_ingest_destroy(pa_ingest *ing);
 const char *pa_ingest_last_error(pa_ingest *ing);
 /* files in the order of the reference's loops: for species, for file j (file_index = j + 1); format guess|fastq|fasta */
 int pa_ingest_add_file(pa_ingest *ing, const char *path, const char *species, int file_index, const char *format);
-int pa_ingest_run(pa_ingest *ing);
+int pa_ingest_run(pa_ingest *ing);            /* = pa_ingest_start + pa_ingest_wait */
 int64_t pa_ingest_num_records(pa_ingest *ing);
+/* Streaming: pa_ingest_start returns at once; inflate/parse threads and the single order-dependent pass run in the
+ * background (at most nthreads files are inflated ahead of the pass).  Records become visible in EMISSION order
+ * (= the order of all.raw.fasta unless the reference's >1000-chunk fold happened, see pa_ingest_final_order) as soon as
+ * they are final, so the GPU search of the first records overlaps the decoding of the rest.  pa_ingest_emitted: records
+ * visible so far (monotone; any thread); pa_ingest_done: 1 once the pass has ended; pa_ingest_wait: join, 0 or the error. */
+int pa_ingest_start(pa_ingest *ing);
+int pa_ingest_wait(pa_ingest *ing);
+int pa_ingest_done(pa_ingest *ing);
+int64_t pa_ingest_emitted(pa_ingest *ing);
+/* like pa_ingest_pack, for emitted records [first, first+count) while the ingest may still be running */
+int64_t pa_ingest_pack_emitted(pa_ingest *ing, uint64_t first, uint64_t count, char *nt_out, uint64_t cap, uint64_t *off_out);
+int64_t pa_ingest_emitted_bytes(pa_ingest *ing, uint64_t first, uint64_t count);      /* sum of their sequence lengths */
+/* ids of the records idx[0..n) (emission indices), concatenated into out (may be NULL: sizes only); out_off[n+1] */
+int64_t pa_ingest_emitted_ids(pa_ingest *ing, const uint64_t *idx, uint64_t n, char *out, uint64_t cap, uint64_t *out_off);
+int64_t pa_ingest_emitted_seqs(pa_ingest *ing, const uint64_t *idx, uint64_t n, char *out, uint64_t cap, uint64_t *out_off); /* same, sequences */
+/* after the end: number of records whose id repeats an earlier record's id (the reference's read_fastx dictionary,
+ * lib/library.py:186-198, keeps one entry per id: first position, last sequence; 0 = every record is its own target) */
+int64_t pa_ingest_repeated_ids(pa_ingest *ing);
+/* after the end: 0 = all.raw.fasta order is the emission order; 1 = the chunk fold of check_file_num (lib/aln.py:262-271)
+ * permuted it and emitted_index[final position] (num_records entries, may be NULL) is filled */
+int pa_ingest_final_order(pa_ingest *ing, uint64_t *emitted_index);
 /* borrowed views, valid until pa_ingest_destroy: the all.raw.fasta text, its record table (offsets/lengths of ids and
  * sequences), the total_counts.tsv and merged_redundance.txt texts. Any pointer may be NULL. */
 int pa_ingest_views(pa_ingest *ing, const char **raw, uint64_t *raw_len, const uint64_t **id_off, const uint64_t **id_len,
                     const uint64_t **seq_off, const uint64_t **seq_len, const char **counts, uint64_t *counts_len,
                     const char **merged, uint64_t *merged_len);
 int pa_ingest_write(pa_ingest *ing, const char *raw_fasta, const char *total_counts, const char *merged_redundance);
-/* sequences [first, first+count) concatenated + offsets (count+1), ready for pa_load_reads */
+/* sequences [first, first+count) of the final (all.raw.fasta) order concatenated + offsets (count+1), ready for pa_load_reads */
 int64_t pa_ingest_pack(pa_ingest *ing, uint64_t first, uint64_t count, char *nt_out, uint64_t cap, uint64_t *off_out);
 
 /* ---- HMMER3/[a-f] ASCII reader (host only): the numbers of ref_hmm/{g}.hmm (first model of the file), ready for pa_add_hmm.

@@ -61,7 +61,11 @@ MAPREC_DTYPE = np.dtype(PaMapRec)
 EXPORTS = ["pa_abi_version", "pa_create", "pa_destroy", "pa_last_error", "pa_set_opts", "pa_add_hmm", "pa_set_evparam",
            "pa_commit_hmms", "pa_num_hmms", "pa_load_reads", "pa_load_proteins", "pa_num_frames", "pa_get_targets",
            "pa_search", "pa_get_hits", "pa_get_hit_pp", "pa_hit_pool_bytes", "pa_get_stats", "pa_score_all", "pa_map_hits", "pa_map_hits_ex", "pa_microbench_dpx",
-           "pa_profiler_range"]
+           "pa_profiler_range", "pa_msv_item_decode", "pa_hmm_file_parse",
+           "pa_ingest_create", "pa_ingest_destroy", "pa_ingest_last_error", "pa_ingest_add_file", "pa_ingest_run", "pa_ingest_start",
+           "pa_ingest_wait", "pa_ingest_done", "pa_ingest_emitted", "pa_ingest_num_records", "pa_ingest_views", "pa_ingest_write",
+           "pa_ingest_pack", "pa_ingest_pack_emitted", "pa_ingest_emitted_bytes", "pa_ingest_emitted_ids", "pa_ingest_emitted_seqs", "pa_ingest_repeated_ids",
+           "pa_ingest_final_order", "pa_fasta_open", "pa_fasta_num_records", "pa_fasta_views", "pa_fasta_close"]
 
 _lib = None
 

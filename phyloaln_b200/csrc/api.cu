@@ -630,7 +630,7 @@ static int build_length_tables(pa_ctx *ctx) {
   ctx->h_L.clear();
   for (int L = 0; L <= maxL; L++)
     if (present[L]) {
-      if (ctx->h_L.size() >= 65535) { ctx->err = "more than 65535 distinct target lengths in one chunk"; return -2; }
+      if (ctx->h_L.size() >= 65535) { ctx->err = "more than 65535 distinct target lengths in one chunk: split the chunk"; return -3; }
       L2li[L] = (uint16_t)ctx->h_L.size();
       ctx->h_L.push_back(L);
     }
@@ -670,7 +670,8 @@ extern "C" int64_t pa_load_reads(pa_ctx *ctx, const char *nt, const uint64_t *of
   if (!ctx) return -1;
   cudaSetDevice(ctx->device);
   const uint64_t total = off[nreads];
-  if (2 * total + 32ull * nreads + 64 >= (1ull << 32)) { ctx->err = "chunk too large (2*nt + 32*reads must stay below 4 GiB)"; return -2; }
+  // capacity limits are -3 ("split the chunk and retry", as for the survivor lists of pa_search); -2 is for bad input
+  if (2 * total + 32ull * nreads + 64 >= (1ull << 32)) { ctx->err = "chunk too large (2*nt + 32*reads must stay below 4 GiB): split the chunk"; return -3; }
   int nfwd, nrev;
   if (moltype == PA_TRANSLATE) {
     nfwd = codon_only ? 1 : 3;
@@ -683,7 +684,7 @@ extern "C" int64_t pa_load_reads(pa_ctx *ctx, const char *nt, const uint64_t *of
   }
   const int nframes = nfwd + nrev;
   const uint64_t ntargets64 = (uint64_t)nreads * nframes;
-  if (ntargets64 >= (1ull << 32)) { ctx->err = "too many targets in one chunk"; return -2; }
+  if (ntargets64 >= (1ull << 32)) { ctx->err = "too many targets in one chunk: split the chunk"; return -3; }
   uint8_t tab64[64];
   memset(tab64, 26, 64);
   if (moltype == PA_TRANSLATE && !codon_table(gencode, tab64)) { ctx->err = "unsupported genetic code table"; return -2; }
@@ -747,7 +748,7 @@ extern "C" int64_t pa_load_reads(pa_ctx *ctx, const char *nt, const uint64_t *of
   if (flag) { ctx->err = "invalid nucleotide character in reads (Biopython would raise TranslationError)"; return -2; }
   ctx->ntargets = (uint32_t)ntargets64;
   ctx->nframes = nframes;
-  if (build_length_tables(ctx) != 0) return -1;
+  { const int lrc = build_length_tables(ctx); if (lrc != 0) return lrc; }
   return (int64_t)ntargets64;
 }
 
@@ -755,7 +756,7 @@ extern "C" int64_t pa_load_proteins(pa_ctx *ctx, const char *aa, const uint64_t 
   if (!ctx) return -1;
   cudaSetDevice(ctx->device);
   const uint64_t total = off[nseq];
-  if (total + 4ull * nseq + 64 >= (1ull << 32)) { ctx->err = "chunk too large"; return -2; }
+  if (total + 4ull * nseq + 64 >= (1ull << 32)) { ctx->err = "chunk too large: split the chunk"; return -3; }
   std::vector<uint32_t> toff((size_t)nseq + 1);
   ctx->h_tlen.resize(nseq);
   uint32_t pos = 0;
@@ -786,7 +787,7 @@ extern "C" int64_t pa_load_proteins(pa_ctx *ctx, const char *aa, const uint64_t 
   ctx->ntargets = nseq;
   ctx->nframes = 1;
   ctx->target_abc = abc;
-  if (build_length_tables(ctx) != 0) return -1;
+  { const int lrc = build_length_tables(ctx); if (lrc != 0) return lrc; }
   return nseq;
 }
 

@@ -21,6 +21,8 @@
 
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <mutex>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -41,7 +43,7 @@ struct FileJob {
   int format = 0;      // 0 guess, 1 fastq, 2 fasta
   // phase 1 output: the inflated text and its line table (rstripped)
   std::string text;
-  std::vector<std::pair<uint64_t, uint32_t>> lines;  // (offset, length after rstrip)
+  std::vector<std::pair<uint64_t, uint64_t>> lines;  // (offset, length after rstrip)
   std::string error;
 };
 
@@ -85,7 +87,7 @@ void split_lines(FileJob &fj) {
     }
     size_t r = e;
     while (r > i && py_space((unsigned char)t[r - 1])) r--;
-    fj.lines.emplace_back((uint64_t)i, (uint32_t)(r - i));
+    fj.lines.emplace_back((uint64_t)i, (uint64_t)(r - i));
     i = next;
   }
   if (fj.format == 0) {  // guess from the first line (lib/library.py:160-166)
@@ -98,12 +100,12 @@ void split_lines(FileJob &fj) {
   }
 }
 
-// bump allocator: keys and tags are never freed individually
+// bump allocator: keys, tags and record texts are never freed individually; pointers stay valid until the ingest is destroyed
 struct Arena {
   std::vector<std::unique_ptr<char[]>> slabs;
   size_t left = 0;
   char *cur = nullptr;
-  const char *put(const char *p, size_t n) {
+  char *alloc(size_t n) {
     if (n > left) {
       const size_t sz = std::max<size_t>(n, (size_t)16 << 20);
       slabs.emplace_back(new char[sz]);
@@ -111,9 +113,13 @@ struct Arena {
       left = sz;
     }
     char *d = cur;
-    memcpy(d, p, n);
     cur += n;
     left -= n;
+    return d;
+  }
+  const char *put(const char *p, size_t n) {
+    char *d = alloc(n);
+    memcpy(d, p, n);
     return d;
   }
 };
@@ -148,26 +154,70 @@ struct ExtraTag {
   int64_t next;
 };
 
+// One record of all.raw.fasta, in EMISSION order: text = '>' id '\n' [body '\n'].  The body is the sequence; on the FASTA
+// fast path it keeps the line breaks of the input.  Records are appended by the single phase-2 thread and read by any number
+// of consumers up to `published` (release/acquire), so the search can start while the ingest is still running.
+struct Rec {
+  const char *text;
+  uint64_t body_len;
+  uint32_t id_len;
+  uint32_t has_body;
+  uint64_t text_len() const { return (uint64_t)id_len + 2 + (has_body ? body_len + 1 : 0); }
+};
+struct RecStore {
+  static constexpr uint64_t BLK = 1ull << 20;
+  std::unique_ptr<Rec *[]> blocks{new Rec *[1 << 16]()};  // fixed directory: readers never see it move
+  uint64_t n = 0;
+  std::atomic<uint64_t> published{0};
+  ~RecStore() {
+    for (uint64_t b = 0; b * BLK < n; b++) delete[] blocks[b];
+  }
+  bool push(const Rec &r) {
+    if (n % BLK == 0) {
+      if (n / BLK >= (1u << 16)) return false;
+      blocks[n / BLK] = new Rec[BLK];
+    }
+    blocks[n / BLK][n % BLK] = r;
+    n++;
+    published.store(n, std::memory_order_release);
+    return true;
+  }
+  const Rec &at(uint64_t i) const { return blocks[i / BLK][i % BLK]; }
+};
+
 }  // namespace
 
 struct pa_ingest {
   int merge_len = 250, split_len = 0, split_slide = 0, nthreads = 1;
   std::vector<FileJob> files;
   std::string err;
-  bool finished = false;
+  std::atomic<bool> finished{false};
+  bool started = false;
+  int rc = 0;
+  std::thread runner;
   // results
-  std::string raw;  // final all.raw.fasta text
+  Arena text;       // record texts
+  RecStore recs;    // emission order
+  std::vector<uint64_t> final_order;  // emission index of every final position; empty = identity (no chunk fold happened)
+  uint64_t id_dups = 0;               // records whose id repeats an earlier record's id (read_fastx keeps one entry per id)
   std::vector<std::pair<std::string, int64_t>> counts;
   std::string merged_txt, counts_txt;
-  // record table of `raw` in final order (ids / sequences for direct GPU feeding)
+  // materialised on demand (pa_ingest_views): the final all.raw.fasta text and its record table in final order
+  bool have_raw = false;
+  std::string raw;
   std::vector<uint64_t> id_off, id_len, seq_off, seq_len;
+  ~pa_ingest() {
+    if (runner.joinable()) runner.join();
+  }
 };
 
 namespace {
 
 struct Builder {
   pa_ingest &S;
-  std::vector<std::string> chunks;
+  // chunk files of the reference as runs (first emission index, count) of records
+  std::vector<std::vector<std::pair<uint64_t, uint64_t>>> chunks;
+  bool folded = false;
   size_t cur = 0;
   uint64_t data_size = 0, each_size = 10000000;
   // open-addressing table (hash, group index + 1); groups in insertion order == Python dict order
@@ -175,6 +225,9 @@ struct Builder {
   std::vector<MergeGroup> groups;
   std::vector<ExtraTag> extras;
   Arena arena;
+  // ids seen so far (hash, record index + 1): counts the records whose id is not new
+  std::vector<std::pair<uint64_t, uint64_t>> idtab = std::vector<std::pair<uint64_t, uint64_t>>(1 << 16);
+  uint64_t n_ids = 0;
 
   int64_t find(std::string_view seq, uint64_t h) const {
     const size_t mask = table.size() - 1;
@@ -204,6 +257,29 @@ struct Builder {
     while (table[i].second) i = (i + 1) & mask;
     table[i] = {h, gi + 1};
   }
+  void note_id(const char *id, uint32_t len, uint64_t rec_index) {
+    const uint64_t h = hash_bytes(id, len);
+    if ((n_ids + 1) * 2 > idtab.size()) {
+      std::vector<std::pair<uint64_t, uint64_t>> nt(idtab.size() * 2);
+      const size_t mask = nt.size() - 1;
+      for (const auto &e : idtab)
+        if (e.second) {
+          size_t i = e.first & mask;
+          while (nt[i].second) i = (i + 1) & mask;
+          nt[i] = e;
+        }
+      idtab.swap(nt);
+    }
+    const size_t mask = idtab.size() - 1;
+    for (size_t i = h & mask;; i = (i + 1) & mask) {
+      auto &e = idtab[i];
+      if (e.second == 0) { e = {h, rec_index + 1}; n_ids++; return; }
+      if (e.first == h) {
+        const Rec &r = S.recs.at(e.second - 1);
+        if (r.id_len == len && !memcmp(r.text + 1, id, len)) { S.id_dups++; return; }
+      }
+    }
+  }
 
   explicit Builder(pa_ingest &s) : S(s) { chunks.emplace_back(); }
 
@@ -212,16 +288,26 @@ struct Builder {
       data_size = 0;
       cur++;
       if (cur >= 1000) {
-        for (size_t i = 100; i < 1000; i++) { chunks[i % 100] += chunks[i]; }
+        for (size_t i = 100; i < 1000; i++) chunks[i % 100].insert(chunks[i % 100].end(), chunks[i].begin(), chunks[i].end());
         chunks.resize(100);
         cur = 100;
         each_size *= 10;
+        folded = true;
       }
       if (chunks.size() <= cur) chunks.resize(cur + 1);
     }
   }
+  // append a finished record (text already in S.text) to chunk `ch`
+  bool add_record(size_t ch, const char *text, uint32_t id_len, uint64_t body_len, bool has_body) {
+    const uint64_t idx = S.recs.n;
+    note_id(text + 1, id_len, idx);
+    auto &runs = chunks[ch];
+    if (!runs.empty() && runs.back().first + runs.back().second == idx) runs.back().second++;
+    else runs.emplace_back(idx, 1);
+    return S.recs.push(Rec{text, body_len, id_len, has_body ? 1u : 0u});
+  }
   // one sequence (or split fragment) with its tag: merge or write
-  void emit(const std::string &tagid, std::string_view seq, uint64_t size_add, bool may_register, const std::string *append_as = nullptr) {
+  bool emit(const std::string &tagid, std::string_view seq, uint64_t size_add, bool may_register, const std::string *append_as = nullptr) {
     uint64_t h = 0;
     if ((int64_t)seq.size() <= S.merge_len) {
       h = hash_bytes(seq.data(), seq.size());
@@ -233,83 +319,103 @@ struct Builder {
         if (g.extra_tail >= 0) extras[(size_t)g.extra_tail].next = (int64_t)extras.size() - 1;
         else g.extra_head = (int64_t)extras.size() - 1;
         g.extra_tail = (int64_t)extras.size() - 1;
-        return;
+        return true;
       }
     }
-    std::string &c = chunks[cur];
-    c += '>'; c += tagid; c += '\n'; c.append(seq.data(), seq.size()); c += '\n';
+    if (tagid.size() >= (1ull << 32)) return false;
+    char *d = S.text.alloc(tagid.size() + seq.size() + 3);
+    d[0] = '>';
+    memcpy(d + 1, tagid.data(), tagid.size());
+    d[1 + tagid.size()] = '\n';
+    memcpy(d + 2 + tagid.size(), seq.data(), seq.size());
+    d[2 + tagid.size() + seq.size()] = '\n';
+    if (!add_record(cur, d, (uint32_t)tagid.size(), seq.size(), true)) return false;
     data_size += size_add;
     rotate_if_full();
     if (may_register) {
       MergeGroup g;
-      g.key = arena.put(seq.data(), seq.size());
+      g.key = d + 2 + tagid.size();   // the record text itself is the key: no second copy of the sequence
       g.key_len = (uint32_t)seq.size();
-      g.tag = arena.put(tagid.data(), tagid.size());
+      g.tag = d + 1;
       g.tag_len = (uint32_t)tagid.size();
       insert(h, groups.size());
       groups.push_back(g);
     }
+    return true;
   }
 };
 
-}  // namespace
-
-extern "C" pa_ingest *pa_ingest_create(int merge_len, int split_len, int split_slide, int nthreads) {
-  pa_ingest *S = new pa_ingest();
-  S->merge_len = merge_len;
-  S->split_len = split_len > 0 ? split_len : 0;
-  S->split_slide = S->split_len ? (split_slide > 0 ? split_slide : S->split_len / 2) : 0;
-  S->nthreads = nthreads > 0 ? nthreads : 1;
-  return S;
-}
-
-extern "C" void pa_ingest_destroy(pa_ingest *S) { delete S; }
-extern "C" const char *pa_ingest_last_error(pa_ingest *S) { return S ? S->err.c_str() : "null ingest handle"; }
-
-extern "C" int pa_ingest_add_file(pa_ingest *S, const char *path, const char *species, int file_index, const char *format) {
-  if (!S || S->finished) return -1;
-  FileJob fj;
-  fj.path = path;
-  fj.species = species;
-  fj.file_index = file_index;
-  fj.format = !strcmp(format, "fastq") ? 1 : !strcmp(format, "fasta") ? 2 : !strcmp(format, "guess") ? 0 : -1;
-  if (fj.format < 0) { S->err = "file format must be guess, fastq or fasta"; return -2; }
-  S->files.push_back(std::move(fj));
-  return 0;
-}
-
-extern "C" int pa_ingest_run(pa_ingest *S) {
-  if (!S || S->finished) return -1;
+// the whole pipeline; runs on S->runner (pa_ingest_start) or on the caller's thread (pa_ingest_run)
+int run_pipeline(pa_ingest *S) {
   if (S->split_len && S->split_slide <= 0) { S->err = "split_slide must be positive (the reference would loop forever)"; return -2; }
   const bool dbg = getenv("PA_INGEST_DEBUG") != nullptr;
   auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   const double t0 = now();
-  // ---- phase 1: inflate + line split, one file per worker
-  {
-    std::atomic<size_t> next{0};
-    auto work = [&]() {
-      for (;;) {
-        const size_t i = next.fetch_add(1);
-        if (i >= S->files.size()) break;
-        if (inflate_file(S->files[i])) split_lines(S->files[i]);
+  // ---- phase 1: inflate + line split on worker threads, at most `ahead` files beyond the phase-2 cursor (bounded memory)
+  const size_t nfiles = S->files.size();
+  std::vector<char> ready(nfiles, 0);
+  std::mutex mu;
+  std::condition_variable cv;
+  size_t consumed = 0;           // files phase 2 is done with
+  bool stop = false;
+  const int nworkers = (int)std::min<size_t>((size_t)std::max(1, S->nthreads - 1), std::max<size_t>(1, nfiles));
+  const size_t ahead = (size_t)nworkers + 1;
+  std::atomic<size_t> next{0};
+  auto work = [&]() {
+    for (;;) {
+      const size_t i = next.fetch_add(1);
+      if (i >= nfiles) break;
+      {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return stop || i < consumed + ahead; });
+        if (stop) break;
       }
-    };
-    std::vector<std::thread> th;
-    const int nt = (int)std::min<size_t>((size_t)S->nthreads, std::max<size_t>(1, S->files.size()));
-    for (int t = 1; t < nt; t++) th.emplace_back(work);
-    work();
+      if (inflate_file(S->files[i])) split_lines(S->files[i]);
+      {
+        std::lock_guard<std::mutex> lk(mu);
+        ready[i] = 1;
+      }
+      cv.notify_all();
+    }
+  };
+  std::vector<std::thread> th;
+  for (int t = 0; t < nworkers; t++) th.emplace_back(work);
+  auto finish_workers = [&]() {
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      stop = true;
+    }
+    cv.notify_all();
     for (auto &t : th) t.join();
-  }
-  for (auto &f : S->files)
-    if (!f.error.empty()) { S->err = f.error; return -2; }
+  };
 
-  const double t1 = now();
+  double t_wait = 0;
   // ---- phase 2: the reference's single pass, in file order
   Builder B(*S);
   const bool fastpath = S->merge_len == 0 && S->split_len == 0;
   const int split_len = S->split_len, slide = S->split_slide;
   std::string tagid, seqstr, prefix_tag;
-  for (FileJob &fj : S->files) {
+  std::string fast_text;      // FASTA fast path: the record being copied
+  size_t fast_chunk = 0;
+  uint32_t fast_idlen = 0;
+  bool fast_open = false;
+  auto fast_close = [&]() -> bool {
+    if (!fast_open) return true;
+    fast_open = false;
+    const uint64_t body = fast_text.size() - (fast_idlen + 2);
+    const char *d = S->text.put(fast_text.data(), fast_text.size());
+    return B.add_record(fast_chunk, d, fast_idlen, body ? body - 1 : 0, body != 0);
+  };
+  bool ok = true;
+  for (size_t fi = 0; fi < nfiles && ok; fi++) {
+    FileJob &fj = S->files[fi];
+    {
+      const double w0 = now();
+      std::unique_lock<std::mutex> lk(mu);
+      cv.wait(lk, [&] { return ready[fi] != 0; });
+      t_wait += now() - w0;
+    }
+    if (!fj.error.empty()) { S->err = fj.error; ok = false; break; }
     int64_t *count = nullptr;
     for (auto &kv : S->counts)
       if (kv.first == fj.species) count = &kv.second;
@@ -330,7 +436,7 @@ extern "C" int pa_ingest_run(pa_ingest *S) {
       size_t pos = 0;
       while ((int64_t)(s.size() - pos) > split_len) {
         make_tag(split_start + 1, split_start + split_len);
-        B.emit(tagid, std::string_view(s).substr(pos, (size_t)split_len), (uint64_t)split_len, split_len <= S->merge_len);
+        ok = ok && B.emit(tagid, std::string_view(s).substr(pos, (size_t)split_len), (uint64_t)split_len, split_len <= S->merge_len);
         split_start += slide;
         pos += (size_t)slide;
         if (pos > s.size()) pos = s.size();
@@ -340,7 +446,7 @@ extern "C" int pa_ingest_run(pa_ingest *S) {
     uint64_t line_num = 0;
     for (const auto &ln : fj.lines) {
       const char *lp = T.data() + ln.first;
-      const uint32_t ll = ln.second;
+      const uint64_t ll = ln.second;
       if (fj.format == 1 && ll > 0 && lp[0] == '@' && line_num % 4 == 0) {
         seqid.assign(lp + 1, ll - 1);
         for (char &c : seqid)
@@ -350,26 +456,32 @@ extern "C" int pa_ingest_run(pa_ingest *S) {
         if (have_id) {
           if (!seqstr.empty()) {
             make_tag(split_start + 1, split_start + (int64_t)seqstr.size());
-            B.emit(tagid, seqstr, seqstr.size(), (int64_t)seqstr.size() <= S->merge_len);
+            ok = ok && B.emit(tagid, seqstr, seqstr.size(), (int64_t)seqstr.size() <= S->merge_len);
           }
           (*count)++;
           split_start = 0;
         }
         // seqid = line.lstrip('>').split()[0]
-        uint32_t a = 0;
+        uint64_t a = 0;
         while (a < ll && lp[a] == '>') a++;
         while (a < ll && py_space((unsigned char)lp[a])) a++;
-        uint32_t b = a;
+        uint64_t b = a;
         while (b < ll && !py_space((unsigned char)lp[b])) b++;
-        if (a == b) { S->err = "FASTA header without an identifier in " + fj.path + " (the reference raises IndexError)"; return -2; }
+        if (a == b) { S->err = "FASTA header without an identifier in " + fj.path + " (the reference raises IndexError)"; ok = false; break; }
         seqid.assign(lp + a, b - a);
         have_id = true;
         seqstr.clear();
         have_seqstr_obj = true;
         if (fastpath) {
+          ok = ok && fast_close();
           B.rotate_if_full();
-          std::string &c = B.chunks[B.cur];
-          c += '>'; c += seqid; c += suffix; c += '\n';
+          fast_chunk = B.cur;
+          fast_text.assign(1, '>');
+          fast_text += seqid;
+          fast_text += suffix;
+          fast_idlen = (uint32_t)(fast_text.size() - 1);
+          fast_text += '\n';
+          fast_open = true;
         }
       } else if (have_id) {
         if (fj.format == 1) {
@@ -379,14 +491,13 @@ extern "C" int pa_ingest_run(pa_ingest *S) {
             emit_windows(seqstr);
           }
           make_tag(split_start + 1, split_start + (int64_t)seqstr.size());
-          B.emit(tagid, seqstr, seqstr.size(), (int64_t)seqstr.size() <= S->merge_len);
+          ok = ok && B.emit(tagid, seqstr, seqstr.size(), (int64_t)seqstr.size() <= S->merge_len);
           (*count)++;
           have_id = false;
           seqid.clear();
         } else if (fastpath) {
-          std::string &c = B.chunks[B.cur];
-          c.append(lp, ll);
-          c += '\n';
+          fast_text.append(lp, ll);
+          fast_text += '\n';
           B.data_size += ll;
         } else {
           seqstr.append(lp, ll);
@@ -395,20 +506,27 @@ extern "C" int pa_ingest_run(pa_ingest *S) {
       }
       line_num++;
     }
-    if (fj.format == 2 && have_seqstr_obj && !seqstr.empty()) {  // trailing FASTA record (lib/aln.py:401-420)
+    if (ok && fj.format == 2 && have_seqstr_obj && !seqstr.empty()) {  // trailing FASTA record (lib/aln.py:401-420)
       make_tag(split_start + 1, split_start + (int64_t)seqstr.size());
-      B.emit(tagid, seqstr, seqstr.size(), (int64_t)seqstr.size() <= S->merge_len, &seqid);
+      ok = ok && B.emit(tagid, seqstr, seqstr.size(), (int64_t)seqstr.size() <= S->merge_len, &seqid);
       (*count)++;
     }
+    ok = ok && fast_close();
     std::string().swap(fj.text);
-    std::vector<std::pair<uint64_t, uint32_t>>().swap(fj.lines);
+    std::vector<std::pair<uint64_t, uint64_t>>().swap(fj.lines);
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      consumed = fi + 1;
+    }
+    cv.notify_all();
+  }
+  finish_workers();
+  if (!ok) {
+    if (S->err.empty()) S->err = "ingest: record table overflow";
+    return -2;
   }
   const double t2 = now();
   // ---- outputs
-  size_t total = 0;
-  for (auto &c : B.chunks) total += c.size();
-  S->raw.reserve(total);
-  for (auto &c : B.chunks) { S->raw += c; std::string().swap(c); }
   for (auto &kv : S->counts) { S->counts_txt += kv.first; S->counts_txt += '\t'; S->counts_txt += std::to_string(kv.second); S->counts_txt += '\n'; }
   for (auto &g : B.groups)
     if (g.extra_head >= 0) {
@@ -419,38 +537,106 @@ extern "C" int pa_ingest_run(pa_ingest *S) {
       }
       S->merged_txt += '\n';
     }
-  // record table (the fast path may hold multi-line records: sequence = first line..last line, newlines inside)
-  {
-    const std::string &R = S->raw;
-    size_t i = 0, n = R.size();
-    while (i < n) {
-      if (R[i] != '>') { S->err = "internal: malformed raw FASTA"; return -1; }
-      const char *nl = (const char *)memchr(R.data() + i, '\n', n - i);
-      const size_t e = nl ? (size_t)(nl - R.data()) : n;
-      S->id_off.push_back(i + 1);
-      S->id_len.push_back(e - i - 1);
-      size_t s = e + 1, j = s;
-      // sequence lines until the next header at line start
-      while (j < n && R[j] != '>') {
-        const char *nl2 = (const char *)memchr(R.data() + j, '\n', n - j);
-        j = nl2 ? (size_t)(nl2 - R.data()) + 1 : n;
-      }
-      S->seq_off.push_back(s);
-      S->seq_len.push_back(j > s ? j - s - 1 : 0);
-      i = j;
-    }
+  if (B.folded) {  // the chunk fold permuted the record order (inputs beyond 10 Gbases): final position -> emission index
+    S->final_order.reserve(S->recs.n);
+    for (auto &runs : B.chunks)
+      for (auto &r : runs)
+        for (uint64_t k = 0; k < r.second; k++) S->final_order.push_back(r.first + k);
   }
-  if (dbg) fprintf(stderr, "pa_ingest_run: inflate+split %.3f s, tag+merge %.3f s, outputs %.3f s\n", t1 - t0, t2 - t1, now() - t2);
-  S->finished = true;
+  if (dbg) fprintf(stderr, "pa_ingest: phase 2 %.3f s (of which %.3f s waiting for inflate), outputs %.3f s, %llu records, %llu repeated ids\n",
+                   t2 - t0, t_wait, now() - t2, (unsigned long long)S->recs.n, (unsigned long long)S->id_dups);
   return 0;
 }
 
-extern "C" int64_t pa_ingest_num_records(pa_ingest *S) { return S && S->finished ? (int64_t)S->id_off.size() : -1; }
+inline uint64_t final_to_emitted(const pa_ingest *S, uint64_t pos) { return S->final_order.empty() ? pos : S->final_order[pos]; }
+
+// final all.raw.fasta text + record table, built on first use (the streaming path never needs it)
+void materialise_raw(pa_ingest *S) {
+  if (S->have_raw) return;
+  const uint64_t n = S->recs.n;
+  uint64_t total = 0;
+  for (uint64_t i = 0; i < n; i++) total += S->recs.at(i).text_len();
+  S->raw.reserve(total);
+  S->id_off.reserve(n); S->id_len.reserve(n); S->seq_off.reserve(n); S->seq_len.reserve(n);
+  for (uint64_t pos = 0; pos < n; pos++) {
+    const Rec &r = S->recs.at(final_to_emitted(S, pos));
+    const uint64_t o = S->raw.size();
+    S->raw.append(r.text, r.text_len());
+    S->id_off.push_back(o + 1);
+    S->id_len.push_back(r.id_len);
+    S->seq_off.push_back(o + r.id_len + 2);
+    S->seq_len.push_back(r.body_len);
+  }
+  S->have_raw = true;
+}
+
+}  // namespace
+
+extern "C" pa_ingest *pa_ingest_create(int merge_len, int split_len, int split_slide, int nthreads) {
+  pa_ingest *S = new pa_ingest();
+  S->merge_len = merge_len;
+  S->split_len = split_len > 0 ? split_len : 0;
+  S->split_slide = S->split_len ? (split_slide > 0 ? split_slide : S->split_len / 2) : 0;
+  S->nthreads = nthreads > 0 ? nthreads : 1;
+  return S;
+}
+
+extern "C" void pa_ingest_destroy(pa_ingest *S) { delete S; }
+extern "C" const char *pa_ingest_last_error(pa_ingest *S) { return S ? S->err.c_str() : "null ingest handle"; }
+
+extern "C" int pa_ingest_add_file(pa_ingest *S, const char *path, const char *species, int file_index, const char *format) {
+  if (!S || S->started) return -1;
+  FileJob fj;
+  fj.path = path;
+  fj.species = species;
+  fj.file_index = file_index;
+  fj.format = !strcmp(format, "fastq") ? 1 : !strcmp(format, "fasta") ? 2 : !strcmp(format, "guess") ? 0 : -1;
+  if (fj.format < 0) { S->err = "file format must be guess, fastq or fasta"; return -2; }
+  S->files.push_back(std::move(fj));
+  return 0;
+}
+
+extern "C" int pa_ingest_start(pa_ingest *S) {
+  if (!S || S->started) return -1;
+  S->started = true;
+  S->runner = std::thread([S] {
+    S->rc = run_pipeline(S);
+    S->finished.store(true, std::memory_order_release);
+  });
+  return 0;
+}
+
+extern "C" int pa_ingest_wait(pa_ingest *S) {
+  if (!S || !S->started) return -1;
+  if (S->runner.joinable()) S->runner.join();
+  return S->rc;
+}
+
+extern "C" int pa_ingest_run(pa_ingest *S) {
+  const int rc = pa_ingest_start(S);
+  return rc ? rc : pa_ingest_wait(S);
+}
+
+extern "C" int pa_ingest_done(pa_ingest *S) { return S && S->finished.load(std::memory_order_acquire) ? 1 : 0; }
+
+extern "C" int64_t pa_ingest_emitted(pa_ingest *S) { return S ? (int64_t)S->recs.published.load(std::memory_order_acquire) : -1; }
+
+extern "C" int64_t pa_ingest_num_records(pa_ingest *S) { return S && S->finished.load(std::memory_order_acquire) && S->rc == 0 ? (int64_t)S->recs.n : -1; }
+
+extern "C" int64_t pa_ingest_repeated_ids(pa_ingest *S) { return S && S->finished.load(std::memory_order_acquire) && S->rc == 0 ? (int64_t)S->id_dups : -1; }
+
+extern "C" int pa_ingest_final_order(pa_ingest *S, uint64_t *emitted_index) {
+  if (!S || !S->finished.load(std::memory_order_acquire) || S->rc != 0) return -1;
+  if (S->final_order.empty()) return 0;
+  if (emitted_index) memcpy(emitted_index, S->final_order.data(), S->final_order.size() * sizeof(uint64_t));
+  return 1;
+}
 
 extern "C" int pa_ingest_views(pa_ingest *S, const char **raw, uint64_t *raw_len, const uint64_t **id_off, const uint64_t **id_len,
                                const uint64_t **seq_off, const uint64_t **seq_len, const char **counts, uint64_t *counts_len,
                                const char **merged, uint64_t *merged_len) {
-  if (!S || !S->finished) return -1;
+  if (!S || !S->finished.load(std::memory_order_acquire) || S->rc != 0) return -1;
+  if (raw || raw_len || id_off || id_len || seq_off || seq_len) materialise_raw(S);
   if (raw) *raw = S->raw.data();
   if (raw_len) *raw_len = S->raw.size();
   if (id_off) *id_off = S->id_off.data();
@@ -465,7 +651,7 @@ extern "C" int pa_ingest_views(pa_ingest *S, const char **raw, uint64_t *raw_len
 }
 
 extern "C" int pa_ingest_write(pa_ingest *S, const char *raw_fasta, const char *total_counts, const char *merged_redundance) {
-  if (!S || !S->finished) return -1;
+  if (!S || !S->finished.load(std::memory_order_acquire) || S->rc != 0) return -1;
   auto dump = [&](const char *path, const std::string &s) -> bool {
     if (!path) return true;
     FILE *f = fopen(path, "wb");
@@ -475,26 +661,98 @@ extern "C" int pa_ingest_write(pa_ingest *S, const char *raw_fasta, const char *
     if (!ok) S->err = std::string("short write on ") + path;
     return ok;
   };
-  return dump(raw_fasta, S->raw) && dump(total_counts, S->counts_txt) && dump(merged_redundance, S->merged_txt) ? 0 : -2;
+  if (raw_fasta) {  // straight from the record texts, contiguous spans in one write: no second copy of the file in memory
+    FILE *f = fopen(raw_fasta, "wb");
+    if (!f) { S->err = std::string("cannot write ") + raw_fasta; return -2; }
+    setvbuf(f, nullptr, _IOFBF, 1 << 22);
+    const uint64_t n = S->recs.n;
+    bool ok = true;
+    const char *span = nullptr;
+    uint64_t span_len = 0;
+    for (uint64_t pos = 0; pos < n && ok; pos++) {
+      const Rec &r = S->recs.at(final_to_emitted(S, pos));
+      if (span && span + span_len == r.text) span_len += r.text_len();
+      else {
+        if (span) ok = fwrite(span, 1, span_len, f) == span_len;
+        span = r.text;
+        span_len = r.text_len();
+      }
+    }
+    if (ok && span) ok = fwrite(span, 1, span_len, f) == span_len;
+    ok = (fclose(f) == 0) && ok;
+    if (!ok) { S->err = std::string("short write on ") + raw_fasta; return -2; }
+  }
+  return dump(total_counts, S->counts_txt) && dump(merged_redundance, S->merged_txt) ? 0 : -2;
 }
 
-// Sequences [first, first + count) of the final record order, concatenated for pa_load_reads
-// (off_out has count + 1 entries). Returns the number of bytes written or a negative error.
-extern "C" int64_t pa_ingest_pack(pa_ingest *S, uint64_t first, uint64_t count, char *nt_out, uint64_t cap, uint64_t *off_out) {
-  if (!S || !S->finished) return -1;
-  if (first + count > S->id_off.size()) { S->err = "pa_ingest_pack: range out of bounds"; return -2; }
+static int64_t pack_records(pa_ingest *S, uint64_t first, uint64_t count, bool final_order, char *nt_out, uint64_t cap, uint64_t *off_out) {
   uint64_t pos = 0;
   for (uint64_t i = 0; i < count; i++) {
-    const uint64_t o = S->seq_off[first + i], l = S->seq_len[first + i];
+    const Rec &r = S->recs.at(final_order ? final_to_emitted(S, first + i) : first + i);
+    const char *body = r.text + r.id_len + 2;
     off_out[i] = pos;
-    if (pos + l > cap) { S->err = "pa_ingest_pack: output buffer too small"; return -3; }
-    for (uint64_t k = 0; k < l; k++) {  // the FASTA fast path keeps line breaks inside a record: drop them
-      const char c = S->raw[o + k];
-      if (c != '\n') nt_out[pos++] = c;
-    }
+    if (pos + r.body_len > cap) { S->err = "pa_ingest_pack: output buffer too small"; return -3; }
+    if (!memchr(body, '\n', r.body_len)) { memcpy(nt_out + pos, body, r.body_len); pos += r.body_len; }
+    else
+      for (uint64_t k = 0; k < r.body_len; k++)  // the FASTA fast path keeps line breaks inside a record: drop them
+        if (body[k] != '\n') nt_out[pos++] = body[k];
   }
   off_out[count] = pos;
   return (int64_t)pos;
+}
+
+// Sequences [first, first + count) of the FINAL record order (all.raw.fasta order), concatenated for pa_load_reads
+// (off_out has count + 1 entries). Returns the number of bytes written or a negative error.
+extern "C" int64_t pa_ingest_pack(pa_ingest *S, uint64_t first, uint64_t count, char *nt_out, uint64_t cap, uint64_t *off_out) {
+  if (!S || !S->finished.load(std::memory_order_acquire) || S->rc != 0) return -1;
+  if (first + count > S->recs.n) { S->err = "pa_ingest_pack: range out of bounds"; return -2; }
+  return pack_records(S, first, count, true, nt_out, cap, off_out);
+}
+
+// Same in EMISSION order, valid while the ingest is still running for records below pa_ingest_emitted()
+extern "C" int64_t pa_ingest_pack_emitted(pa_ingest *S, uint64_t first, uint64_t count, char *nt_out, uint64_t cap, uint64_t *off_out) {
+  if (!S) return -1;
+  if (first + count > S->recs.published.load(std::memory_order_acquire)) { S->err = "pa_ingest_pack_emitted: records not emitted yet"; return -2; }
+  return pack_records(S, first, count, false, nt_out, cap, off_out);
+}
+
+// total sequence bytes of emitted records [first, first + count) (sizing of the pack buffer / byte-bounded chunks)
+extern "C" int64_t pa_ingest_emitted_bytes(pa_ingest *S, uint64_t first, uint64_t count) {
+  if (!S || first + count > S->recs.published.load(std::memory_order_acquire)) return -1;
+  uint64_t tot = 0;
+  for (uint64_t i = 0; i < count; i++) tot += S->recs.at(first + i).body_len;
+  return (int64_t)tot;
+}
+
+// ids (what = 0) or sequences (what = 1, line breaks of the FASTA fast path removed) of selected records (emission
+// indices), concatenated; out_off has n + 1 entries; out may be NULL (sizes only). Returns bytes written or <0.
+static int64_t emitted_fields(pa_ingest *S, int what, const uint64_t *idx, uint64_t n, char *out, uint64_t cap, uint64_t *out_off) {
+  if (!S) return -1;
+  const uint64_t have = S->recs.published.load(std::memory_order_acquire);
+  uint64_t pos = 0;
+  for (uint64_t i = 0; i < n; i++) {
+    if (idx[i] >= have) { S->err = "pa_ingest_emitted_*: record not emitted yet"; return -2; }
+    const Rec &r = S->recs.at(idx[i]);
+    out_off[i] = pos;
+    const char *src = what ? r.text + r.id_len + 2 : r.text + 1;
+    const uint64_t len = what ? r.body_len : r.id_len;
+    if (out && pos + len > cap) { S->err = "pa_ingest_emitted_*: output buffer too small"; return -3; }
+    if (what && memchr(src, '\n', len)) {
+      for (uint64_t k = 0; k < len; k++)
+        if (src[k] != '\n') { if (out) out[pos] = src[k]; pos++; }
+    } else {
+      if (out) memcpy(out + pos, src, len);
+      pos += len;
+    }
+  }
+  out_off[n] = pos;
+  return (int64_t)pos;
+}
+extern "C" int64_t pa_ingest_emitted_ids(pa_ingest *S, const uint64_t *idx, uint64_t n, char *out, uint64_t cap, uint64_t *out_off) {
+  return emitted_fields(S, 0, idx, n, out, cap, out_off);
+}
+extern "C" int64_t pa_ingest_emitted_seqs(pa_ingest *S, const uint64_t *idx, uint64_t n, char *out, uint64_t cap, uint64_t *out_off) {
+  return emitted_fields(S, 1, idx, n, out, cap, out_off);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------

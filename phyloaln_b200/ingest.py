@@ -33,6 +33,21 @@ def _lib():
         L.pa_ingest_write.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_char_p]
         L.pa_ingest_pack.restype = i64
         L.pa_ingest_pack.argtypes = [vp, u64, u64, vp, u64, vp]
+        for f in ("pa_ingest_start", "pa_ingest_wait", "pa_ingest_done"):
+            getattr(L, f).argtypes = [vp]
+        L.pa_ingest_emitted.restype = i64
+        L.pa_ingest_emitted.argtypes = [vp]
+        L.pa_ingest_pack_emitted.restype = i64
+        L.pa_ingest_pack_emitted.argtypes = [vp, u64, u64, vp, u64, vp]
+        L.pa_ingest_emitted_bytes.restype = i64
+        L.pa_ingest_emitted_bytes.argtypes = [vp, u64, u64]
+        L.pa_ingest_emitted_ids.restype = i64
+        L.pa_ingest_emitted_ids.argtypes = [vp, vp, u64, vp, u64, vp]
+        L.pa_ingest_emitted_seqs.restype = i64
+        L.pa_ingest_emitted_seqs.argtypes = [vp, vp, u64, vp, u64, vp]
+        L.pa_ingest_repeated_ids.restype = i64
+        L.pa_ingest_repeated_ids.argtypes = [vp]
+        L.pa_ingest_final_order.argtypes = [vp, vp]
         L.pa_fasta_open.restype = vp
         L.pa_fasta_open.argtypes = [C.c_char_p, C.c_char_p, i32]
         L.pa_fasta_num_records.restype = i64
@@ -89,7 +104,9 @@ class Ingest:
     """rawdata: {species: [files]} in the reference's iteration order (dict order, lib/aln.py:287-289)."""
 
     def __init__(self, rawdata: dict, merge_len: int = 250, split_len: int | None = None, split_slide: int | None = None,
-                 file_format: str = "guess", threads: int | None = None):
+                 file_format: str = "guess", threads: int | None = None, wait: bool = True):
+        """wait=False returns while the files are still being decoded: records stream out in emission order
+        (emitted / pack_emitted / ids_of) and the search can start on them; call wait() before anything else."""
         self.L = _lib()
         if split_len is not None and split_slide is None:
             split_slide = int(split_len / 2)          # lib/main.py:207-208
@@ -98,8 +115,65 @@ class Ingest:
         for sp, files in rawdata.items():
             for j, f in enumerate(files):
                 self._check(self.L.pa_ingest_add_file(self.h, os.fspath(f).encode(), sp.encode(), j + 1, file_format.encode()))
-        self._check(self.L.pa_ingest_run(self.h))
-        self.n = int(self.L.pa_ingest_num_records(self.h))
+        self.n = -1
+        self._check(self.L.pa_ingest_start(self.h))
+        if wait:
+            self.wait()
+
+    def wait(self):
+        """Join the background pass; raises on its error. Idempotent."""
+        if self.n < 0:
+            self._check(self.L.pa_ingest_wait(self.h))
+            self.n = int(self.L.pa_ingest_num_records(self.h))
+        return self
+
+    def done(self) -> bool:
+        return bool(self.L.pa_ingest_done(self.h))
+
+    def emitted(self) -> int:
+        return int(self.L.pa_ingest_emitted(self.h))
+
+    def emitted_bytes(self, first: int, count: int) -> int:
+        return int(self.L.pa_ingest_emitted_bytes(self.h, first, count))
+
+    def pack_emitted(self, first: int, count: int):
+        """(nt uint8[], off uint64[count+1]) of emitted records [first, first+count); valid while the ingest runs."""
+        cap = self.emitted_bytes(first, count) + 1
+        nt = np.zeros(cap, dtype=np.uint8)
+        off = np.zeros(count + 1, dtype=np.uint64)
+        got = self.L.pa_ingest_pack_emitted(self.h, first, count, nt.ctypes.data, cap, off.ctypes.data)
+        self._check(got)
+        return nt[:max(int(got), 1)], off
+
+    def _fields_of(self, fn, idx) -> list[str]:
+        idx = np.ascontiguousarray(idx, dtype=np.uint64)
+        off = np.zeros(len(idx) + 1, dtype=np.uint64)
+        need = fn(self.h, idx.ctypes.data, len(idx), None, 0, off.ctypes.data)
+        self._check(need)
+        buf = C.create_string_buffer(max(1, int(need)))
+        self._check(fn(self.h, idx.ctypes.data, len(idx), buf, int(need), off.ctypes.data))
+        raw = buf.raw
+        return [raw[int(off[i]):int(off[i + 1])].decode() for i in range(len(idx))]
+
+    def ids_of(self, idx) -> list[str]:
+        """Tagged ids of the records with emission indices idx (only reads with hits ever need their id as a str)."""
+        return self._fields_of(self.L.pa_ingest_emitted_ids, idx)
+
+    def seqs_of(self, idx) -> list[str]:
+        """Raw nucleotide sequences of the records with emission indices idx (targets.fas, lib/aln.py:559-561)."""
+        return self._fields_of(self.L.pa_ingest_emitted_seqs, idx)
+
+    def repeated_ids(self) -> int:
+        self.wait()
+        return int(self.L.pa_ingest_repeated_ids(self.h))
+
+    def final_order(self):
+        """None when all.raw.fasta order == emission order, else emission index of every final position."""
+        self.wait()
+        perm = np.zeros(max(1, self.n), dtype=np.uint64)
+        rc = self.L.pa_ingest_final_order(self.h, perm.ctypes.data)
+        self._check(rc)
+        return perm[:self.n] if rc == 1 else None
 
     def _check(self, rc):
         if rc < 0:
@@ -117,6 +191,7 @@ class Ingest:
             pass
 
     def _views(self):
+        self.wait()
         raw, cnt, mrg = C.c_char_p(), C.c_char_p(), C.c_char_p()
         rl, cl, ml = C.c_uint64(), C.c_uint64(), C.c_uint64()
         ptrs = [C.POINTER(C.c_uint64)() for _ in range(4)]
@@ -152,6 +227,7 @@ class Ingest:
 
     def pack(self, first: int = 0, count: int | None = None):
         """(nt uint8[], off uint64[count+1]) of records [first, first+count) for ``Context.load_reads``."""
+        self.wait()
         count = self.n - first if count is None else count
         cap = int(self.seq_lengths()[first:first + count].sum()) + 1
         nt = np.zeros(cap, dtype=np.uint8)
@@ -162,15 +238,18 @@ class Ingest:
 
     def write(self, outdir: str = "."):
         """all.raw.fasta, total_counts.tsv, merged_redundance.txt exactly where the reference puts them."""
+        self.wait()
         self._check(self.L.pa_ingest_write(self.h, os.path.join(outdir, "all.raw.fasta").encode(),
                                            os.path.join(outdir, "total_counts.tsv").encode(),
                                            os.path.join(outdir, "merged_redundance.txt").encode()))
 
 
-def prepare_target(rawdata: dict, args, outdir: str = ".") -> Ingest:
+def prepare_target(rawdata: dict, args, outdir: str = ".", wait: bool = True) -> Ingest:
     """Drop-in for the ingest half of the reference's prepare_target(rawdata, args): same arguments
-    (args.file_format, args.split_len, args.split_slide, args.merge_len, args.cpu), same three files."""
+    (args.file_format, args.split_len, args.split_slide, args.merge_len, args.cpu), same three files.
+    wait=False: return while the files are still being decoded (the caller writes the files after wait())."""
     ing = Ingest(rawdata, merge_len=args.merge_len, split_len=args.split_len, split_slide=args.split_slide,
-                 file_format=args.file_format, threads=getattr(args, "cpu", None))
-    ing.write(outdir)
+                 file_format=args.file_format, threads=getattr(args, "cpu", None), wait=wait)
+    if wait:
+        ing.write(outdir)
     return ing

@@ -102,6 +102,98 @@ def frame_suffix(frame: int, nframes: int, translated: bool):
     return ("", "+", None) if frame == 0 else ("_rev", "rev", None)
 
 
+def _exp_times(lnP: np.ndarray, scale: float, cut: float) -> np.ndarray:
+    """exp(lnP) * scale <= cut, decided with math.exp where numpy's exp could differ from it in the last place."""
+    v = np.exp(lnP.astype(np.float64)) * scale
+    ok = v <= cut
+    for i in np.flatnonzero(np.abs(v - cut) <= 1e-9 * abs(cut)):
+        ok[i] = math.exp(float(lnP[i])) * scale <= cut
+    return ok
+
+
+def report_index(hits: np.ndarray, target_names, Z: float, opts: SearchOptions, n_hmm: int):
+    """Reporting thresholds and HMMER's report order, vectorised: no per-hit Python objects.
+
+    Returns (Zeff, {hmm_index: (idx, domZ)}): idx = indices into `hits` of the reported domains in report order (sequences by
+    E-value ascending, ties by name; the domains of a sequence consecutive, in dom_idx order)."""
+    Zeff = float(opts.Z) if opts.Z is not None else float(Z)
+    out = {}
+    if len(hits) == 0:
+        return Zeff, out
+    order = np.lexsort((hits["dom_idx"], hits["target"], hits["hmm"]))
+    hh, tt = hits["hmm"][order], hits["target"][order]
+    first = np.r_[True, (hh[1:] != hh[:-1]) | (tt[1:] != tt[:-1])]
+    starts = np.flatnonzero(first)
+    ends = np.r_[starts[1:], len(order)]
+    s_hmm = hh[starts]
+    s_lnP = hits["seq_lnP"][order[starts]]
+    if opts.T is not None:
+        s_ok = hits["seq_bits"][order[starts]].astype(np.float64) >= opts.T
+    else:
+        s_ok = _exp_times(s_lnP, Zeff, opts.E)
+    d_lnP = hits["dom_lnP"][order]
+    d_bits = hits["dom_bits"][order].astype(np.float64)
+    # sequences are grouped by profile already (primary sort key)
+    hb = np.searchsorted(s_hmm, np.arange(n_hmm + 1))
+    for h in range(n_hmm):
+        lo, hi = int(hb[h]), int(hb[h + 1])
+        if lo == hi:
+            continue
+        sel = lo + np.flatnonzero(s_ok[lo:hi])
+        if len(sel) == 0:
+            continue
+        domZ = float(opts.domZ) if opts.domZ is not None else float(len(sel))
+        k = np.argsort(s_lnP[sel], kind="stable")
+        sel = sel[k]
+        lp = s_lnP[sel]
+        ties = np.flatnonzero(lp[1:] == lp[:-1])
+        if len(ties):  # equal E-values: by name (strcmp), as HMMER's sort does
+            i = 0
+            sel = sel.copy()
+            while i < len(sel):
+                j = i + 1
+                while j < len(sel) and lp[j] == lp[i]:
+                    j += 1
+                if j - i > 1:
+                    grp = sorted(sel[i:j], key=lambda q: target_names(int(tt[starts[q]])).encode())
+                    sel[i:j] = grp
+                i = j
+        # all domains of the selected sequences, sequence by sequence
+        cnt = ends[sel] - starts[sel]
+        pos = np.repeat(starts[sel] - np.r_[0, np.cumsum(cnt)[:-1]], cnt) + np.arange(int(cnt.sum()))
+        if opts.domT is not None:
+            d_ok = d_bits[pos] >= opts.domT
+        else:
+            d_ok = _exp_times(d_lnP[pos], domZ, opts.domE)
+        out[h] = (order[pos[d_ok]], domZ)
+    return Zeff, out
+
+
+def rows_from_index(hits, idx, domZ, Zeff, model, aligned, target_names, pp=None):
+    """Row dicts of one profile (the form write_tblout / write_domtblout / hmmer_text consume) from report_index's indices."""
+    rows = []
+    ln2 = math.log(2.0)
+    names = {}
+    for g in idx:
+        g = int(g)
+        r = hits[g]
+        t = int(r["target"])
+        if t not in names:
+            names[t] = target_names(t)
+        dl, sl = float(r["dom_lnP"]), float(r["seq_lnP"])
+        rows.append({"hmm": int(r["hmm"]), "target": t, "name": names[t], "dom_idx": int(r["dom_idx"]),
+                     "hmmfrom": int(r["hmmfrom"]), "hmmto": int(r["hmmto"]), "alifrom": int(r["iali"]),
+                     "alito": int(r["jali"]), "envfrom": int(r["ienv"]), "envto": int(r["jenv"]),
+                     "seq_bits": float(r["seq_bits"]), "seq_evalue": math.exp(sl) * Zeff,
+                     "seq_bias": float(r["seqbias"]) / ln2,
+                     "dom_bits": float(r["dom_bits"]), "dom_cevalue": math.exp(dl) * domZ,
+                     "dom_ievalue": math.exp(dl) * Zeff,
+                     "dom_bias": float(r["dombias"]) / ln2, "ndom": int(r["ndom_in_seq"]),
+                     "oasc": float(r["oasc"]), "domZ": domZ, "Z": Zeff,
+                     "model": model[g], "aligned": aligned[g], "pp": pp[g] if pp is not None else None})
+    return rows
+
+
 def report(hits: np.ndarray, model, aligned, target_names, Z: float, opts: SearchOptions, n_hmm: int, pp=None):
     """Apply reporting thresholds and HMMER's report order per profile.
 
@@ -110,51 +202,9 @@ def report(hits: np.ndarray, model, aligned, target_names, Z: float, opts: Searc
     Returns {hmm_index: [domain dict, ...]} in report order.
     """
     out = {h: [] for h in range(n_hmm)}
-    if len(hits) == 0:
-        return out
-    order = np.lexsort((hits["dom_idx"], hits["target"], hits["hmm"]))
-    hs = hits[order]
-    key = hs["hmm"].astype(np.int64) * (1 << 40) + hs["target"].astype(np.int64)
-    starts = np.flatnonzero(np.r_[True, key[1:] != key[:-1]])
-    ends = np.r_[starts[1:], len(hs)]
-    Zeff = float(opts.Z) if opts.Z is not None else float(Z)
-    per_hmm: dict[int, list] = {}
-    for s, e in zip(starts, ends):
-        h = int(hs["hmm"][s])
-        lnP = float(hs["seq_lnP"][s])
-        score = float(hs["seq_bits"][s])
-        if opts.T is not None:
-            ok = score >= opts.T
-        else:
-            ok = math.exp(lnP) * Zeff <= opts.E
-        if ok:
-            per_hmm.setdefault(h, []).append((s, e))
-    for h, seqs in per_hmm.items():
-        domZ = float(opts.domZ) if opts.domZ is not None else float(len(seqs))
-        names = {s: target_names(int(hs["target"][s])) for s, _ in seqs}
-        # sort key -lnP descending (E-value ascending); ties by name (strcmp)
-        seqs.sort(key=lambda se: (float(hs["seq_lnP"][se[0]]), names[se[0]].encode()))
-        rows = []
-        for s, e in seqs:
-            for g in range(s, e):
-                if opts.domT is not None:
-                    ok = float(hs["dom_bits"][g]) >= opts.domT
-                else:
-                    ok = math.exp(float(hs["dom_lnP"][g])) * domZ <= opts.domE
-                if not ok:
-                    continue
-                og = int(order[g])
-                rows.append({"hmm": h, "target": int(hs["target"][g]), "name": names[s], "dom_idx": int(hs["dom_idx"][g]),
-                             "hmmfrom": int(hs["hmmfrom"][g]), "hmmto": int(hs["hmmto"][g]), "alifrom": int(hs["iali"][g]),
-                             "alito": int(hs["jali"][g]), "envfrom": int(hs["ienv"][g]), "envto": int(hs["jenv"][g]),
-                             "seq_bits": float(hs["seq_bits"][g]), "seq_evalue": math.exp(float(hs["seq_lnP"][g])) * Zeff,
-                             "seq_bias": float(hs["seqbias"][g]) / math.log(2.0),
-                             "dom_bits": float(hs["dom_bits"][g]), "dom_cevalue": math.exp(float(hs["dom_lnP"][g])) * domZ,
-                             "dom_ievalue": math.exp(float(hs["dom_lnP"][g])) * Zeff,
-                             "dom_bias": float(hs["dombias"][g]) / math.log(2.0), "ndom": int(hs["ndom_in_seq"][g]),
-                             "oasc": float(hs["oasc"][g]), "domZ": domZ, "Z": Zeff,
-                             "model": model[og], "aligned": aligned[og], "pp": pp[og] if pp is not None else None})
-        out[h] = rows
+    Zeff, index = report_index(hits, target_names, Z, opts, n_hmm)
+    for h, (idx, domZ) in index.items():
+        out[h] = rows_from_index(hits, idx, domZ, Zeff, model, aligned, target_names, pp)
     return out
 
 
@@ -235,21 +285,75 @@ def shard_bounds(nreads: int, world: int, rank: int):
     return min(nreads, rank * per), min(nreads, (rank + 1) * per)
 
 
-def gather_hits_distributed(hits: np.ndarray, model, aligned, dst: int = 0):
-    """Host-side gather of per-rank hit lists (the only cross-rank step; no collective on the DP path).
-
-    Uses torch.distributed object gather so it works with the nccl and gloo backends alike.
+def gather_hits_files(hits: np.ndarray, model, aligned, rank: int, world: int, directory: str, dst: int = 0,
+                      timeout: float = 3600.0):
+    """Host-side gather of per-rank hit lists for one-process-per-GPU runs (the only cross-rank step; there is no
+    collective on the DP path and no torch / NCCL in the product): every rank writes its records into `directory`
+    (a path all ranks see, e.g. the PhyloAln output directory), rank `dst` waits for all of them.
     Returns (hits, model, aligned) on rank dst, (None, None, None) elsewhere."""
-    import torch.distributed as dist
-    world, rank = dist.get_world_size(), dist.get_rank()
-    payload = (hits.tobytes(), list(model), list(aligned))
-    bucket = [None] * world if rank == dst else None
-    dist.gather_object(payload, bucket, dst=dst)
+    import pickle
+    import time
+    os.makedirs(directory, exist_ok=True)
+    tmp = os.path.join(directory, f".hits_rank{rank}.tmp")
+    with open(tmp, "wb") as fh:
+        pickle.dump((hits.tobytes(), list(model), list(aligned)), fh, protocol=4)
+    os.replace(tmp, os.path.join(directory, f"hits_rank{rank}.pkl"))     # atomic: a reader never sees a partial file
     if rank != dst:
         return None, None, None
-    parts = [np.frombuffer(b[0], dtype=capi.HIT_DTYPE) for b in bucket]
-    allhits = np.concatenate(parts) if parts else np.zeros(0, dtype=capi.HIT_DTYPE)
-    return allhits, [m for b in bucket for m in b[1]], [m for b in bucket for m in b[2]]
+    parts, t_end = [], time.time() + timeout
+    for r in range(world):
+        path = os.path.join(directory, f"hits_rank{r}.pkl")
+        while not os.path.exists(path):
+            if time.time() > t_end:
+                raise TimeoutError(f"rank {r} never delivered its hit list ({path})")
+            time.sleep(0.01)
+        with open(path, "rb") as fh:
+            parts.append(pickle.load(fh))
+        os.remove(path)
+    allhits = np.concatenate([np.frombuffer(b[0], dtype=capi.HIT_DTYPE) for b in parts]) if parts else np.zeros(0, dtype=capi.HIT_DTYPE)
+    return allhits, [m for b in parts for m in b[1]], [m for b in parts for m in b[2]]
+
+
+class ArraySource:
+    """Reads already in host memory: (nt uint8, off uint64[n+1])."""
+
+    def __init__(self, nt: np.ndarray, off: np.ndarray):
+        self.nt, self.off = nt, off
+
+    def finished(self):
+        return True
+
+    def available(self):
+        return len(self.off) - 1
+
+    def nbytes(self, a, b):
+        return int(self.off[b] - self.off[a])
+
+    def pack(self, a, b):
+        sub_nt = self.nt[int(self.off[a]):int(self.off[b])]
+        return (sub_nt if len(sub_nt) else np.zeros(1, dtype=np.uint8)), (self.off[a:b + 1] - self.off[a]).astype(np.uint64)
+
+
+class IngestSource:
+    """Records of a (possibly still running) native ingest, in emission order (ingest.Ingest, pa_ingest_*)."""
+
+    def __init__(self, ing):
+        self.ing = ing
+
+    def finished(self):
+        return self.ing.done()
+
+    def available(self):
+        return self.ing.emitted()
+
+    def nbytes(self, a, b):
+        return self.ing.emitted_bytes(a, b - a)
+
+    def pack(self, a, b):
+        return self.ing.pack_emitted(a, b - a)
+
+
+CHUNK_BYTE_LIMIT = (1 << 32) - (1 << 20)   # pa_load_reads: 2 * nt + 32 * reads must stay below 4 GiB
 
 
 class B200Searcher:
@@ -273,32 +377,54 @@ class B200Searcher:
             c.close()
         self.ctxs = []
 
-    def search_reads(self, nt: np.ndarray, off: np.ndarray, mol_type: str = "prot", gencode: int = 1, no_reverse: bool = False,
-                     codon: bool = False, chunk_reads: int = 1 << 18, want_pp: bool = False):
-        """Search concatenated ASCII reads. Returns (hits, model, aligned, Z, nframes, translated); with want_pp the PP
-        annotation lines of the alignments are left in ``self.last_pp`` (same order as hits).
+    def search_reads(self, nt: np.ndarray, off: np.ndarray, **kw):
+        """Search concatenated ASCII reads (host arrays). See :meth:`search_source`."""
+        return self.search_source(ArraySource(nt, off), **kw)
+
+    def search_source(self, src, mol_type: str = "prot", gencode: int = 1, no_reverse: bool = False, codon: bool = False,
+                      chunk_reads: int = 1 << 18, want_pp: bool = False):
+        """Search every record of `src` (ArraySource / IngestSource). Returns (hits, model, aligned, Z, nframes, translated);
+        with want_pp the PP annotation lines of the alignments are left in ``self.last_pp`` (same order as hits).
 
         ``mol_type`` follows PhyloAln's -m: 'dna*' searches nucleotide targets, everything else translates
-        (lib/aln.py:241-258). Reads are cut into chunks; chunk c goes to GPU c mod n (contexts run in
-        parallel threads; ctypes releases the GIL). Hit target indices are global."""
+        (lib/aln.py:241-258).  One thread per GPU context pulls the next contiguous range of records from a shared
+        cursor as soon as the source has them (a running ingest keeps producing while earlier ranges are searched), at
+        most chunk_reads records and 2*nt + 32*reads < 4 GiB per range; ctypes releases the GIL during the calls.  Hit
+        target indices are global (record index * nframes + frame).  Z = records * nframes once the source has ended."""
+        import time
         translated = not mol_type.startswith("dna")
-        nreads = len(off) - 1
-        bounds = list(range(0, nreads, chunk_reads)) + [nreads]
-        results = [None] * (len(bounds) - 1)
+        results = []
         nframes_box = [1]
         errors = []
+        lock = threading.Lock()
+        cursor = [0]
+        min_chunk = max(1, chunk_reads // 4)
+
+        def next_range():
+            while not errors:
+                with lock:
+                    fin = src.finished()       # read before available(): once finished the count is final
+                    avail = src.available()
+                    a = cursor[0]
+                    if avail - a >= min_chunk or (fin and avail > a):
+                        b = min(avail, a + chunk_reads)
+                        while b - a > 1 and 2 * src.nbytes(a, b) + 32 * (b - a) + 64 >= CHUNK_BYTE_LIMIT:
+                            b = a + (b - a) // 2
+                        cursor[0] = b
+                        return a, b
+                    if fin:
+                        return None
+                time.sleep(0.002)
+            return None
 
         def search_range(ctx, a, b, out):
-            """Search reads [a, b); on a capacity error (-3) split the range (the library has no fallback)."""
-            sub_off = (off[a:b + 1] - off[a]).astype(np.uint64)
-            sub_nt = nt[int(off[a]):int(off[b])]
-            if len(sub_nt) == 0:
-                sub_nt = np.zeros(1, dtype=np.uint8)
-            ctx.load_reads(sub_nt, sub_off, moltype=0 if translated else 1, gencode=gencode, no_reverse=no_reverse,
-                           codon_only=codon)
-            nf = ctx.num_frames()
-            nframes_box[0] = nf
+            """Search records [a, b); on a capacity error (-3) split the range (the library has no fallback)."""
+            sub_nt, sub_off = src.pack(a, b)
             try:
+                ctx.load_reads(sub_nt, sub_off, moltype=0 if translated else 1, gencode=gencode, no_reverse=no_reverse,
+                               codon_only=codon)
+                nf = ctx.num_frames()
+                nframes_box[0] = nf
                 hits, model, aligned = ctx.search()
             except capi.PaError as e:
                 if "(-3)" in str(e) and b - a > 1:
@@ -310,31 +436,37 @@ class B200Searcher:
             pp = ctx.hit_pp(hits) if want_pp else [None] * len(hits)
             hits = hits.copy()
             hits["target"] += a * nf
-            out.append((hits, model, aligned, pp))
+            out.append((a, hits, model, aligned, pp))
 
-        def work(ci, ctx):
+        def work(ctx):
             try:
-                for c in range(ci, len(bounds) - 1, len(self.ctxs)):
+                while True:
+                    r = next_range()
+                    if r is None:
+                        break
                     parts = []
-                    search_range(ctx, bounds[c], bounds[c + 1], parts)
-                    results[c] = (np.concatenate([p[0] for p in parts]), [m for p in parts for m in p[1]],
-                                  [m for p in parts for m in p[2]], [m for p in parts for m in p[3]])
+                    search_range(ctx, r[0], r[1], parts)
+                    with lock:
+                        results.extend(parts)
             except Exception as e:  # surfaced after join
                 errors.append(e)
 
-        threads = [threading.Thread(target=work, args=(i, c)) for i, c in enumerate(self.ctxs)]
+        threads = [threading.Thread(target=work, args=(c,)) for c in self.ctxs]
         for t in threads:
             t.start()
         for t in threads:
             t.join()
         if errors:
             raise errors[0]
+        if cursor[0] == 0 and self.ctxs:      # no records at all: nframes still follows the mode
+            nframes_box[0] = ((1 if codon else 3) + (0 if no_reverse else 3)) if translated else (1 if no_reverse else 2)
         nframes = nframes_box[0]
-        res = [r for r in results if r is not None]
-        hits = np.concatenate([r[0] for r in res]) if res else np.zeros(0, dtype=capi.HIT_DTYPE)
-        model = [m for r in res for m in r[1]]
-        aligned = [m for r in res for m in r[2]]
-        self.last_pp = [m for r in res for m in r[3]] if want_pp else None
+        results.sort(key=lambda r: r[0])
+        hits = np.concatenate([r[1] for r in results]) if results else np.zeros(0, dtype=capi.HIT_DTYPE)
+        model = [m for r in results for m in r[2]]
+        aligned = [m for r in results for m in r[3]]
+        self.last_pp = [m for r in results for m in r[4]] if want_pp else None
+        nreads = src.available()
         Z = nreads * nframes
         return hits, model, aligned, Z, nframes, translated
 

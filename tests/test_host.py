@@ -19,7 +19,7 @@ def test_cabi_library_loads_and_exports_every_declared_symbol():
     for sym in declared:
         assert hasattr(L, sym), f"{sym} declared in include/phyloaln_b200.h but not exported"
     assert set(capi.EXPORTS) <= set(declared)
-    assert L.pa_abi_version() == 2
+    assert L.pa_abi_version() == 3
 
 
 def test_no_gpu_is_a_loud_error():

@@ -1,6 +1,7 @@
-"""N > 1 host path on CPU: two gloo ranks shard the reads by chunk, search their shard (the oracle
-stands in for the GPU on this CPU-only box), gather hit records on rank 0 and apply the global
-report (Z, domZ, order).  Must equal the single-process result -- no collective on the data path."""
+"""N > 1 host path on CPU: two ranks (launched with torchrun, gloo rendezvous -- the TEST's plumbing; the product's
+gather uses files, no torch and no NCCL) shard the reads by chunk, search their shard (the oracle stands in for the GPU
+on this CPU-only box), gather hit records on rank 0 and apply the global report (Z, domZ, order).  Must equal the
+single-process result -- no collective on the data path."""
 import json
 import os
 import subprocess
@@ -36,7 +37,8 @@ for hi, h in enumerate(hmms):
         r["target"] = d["target"] + a * 6          # local -> global target index
         recs.append(r); model.append(d["model"]); aligned.append(d["aligned"])
 hits = np.array(recs, dtype=capi.HIT_DTYPE) if recs else np.zeros(0, dtype=capi.HIT_DTYPE)
-hits, model, aligned = search.gather_hits_distributed(hits, model, aligned, dst=0)
+hits, model, aligned = search.gather_hits_files(hits, model, aligned, rank, world, sys.argv[2] + '.gather', dst=0)
+dist.barrier()
 if rank == 0:
     tname = lambda t: ids[t // 6] + search.frame_suffix(t % 6, 6, True)[0]
     rep = search.report(hits, model, aligned, tname, len(rl) * 6, search.SearchOptions(), len(hmms))
