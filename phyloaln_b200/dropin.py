@@ -21,6 +21,7 @@ import time
 
 import numpy as np
 
+from . import capi
 from .hmmer_text import write_text_report
 from .hmmio import read_hmm
 from .search import (ArraySource, B200Searcher, IngestSource, frame_suffix, parse_hmmsearch_parameters, report_index,
@@ -191,6 +192,7 @@ def hmmsearch_step(outdir: str, groups, mol_type: str = "prot", gencode: int = 1
         hits, model, aligned, Z, nframes, translated = searcher.search_source(
             src, mol_type=mol_type, gencode=gencode, no_reverse=no_reverse, codon=codon, chunk_reads=chunk_reads, want_pp=write_text)
         pp = searcher.last_pp
+        invalid = searcher.last_invalid
         stats = [c.stats() for c in searcher.ctxs]
     finally:
         searcher.close()
@@ -207,6 +209,14 @@ def hmmsearch_step(outdir: str, groups, mol_type: str = "prot", gencode: int = 1
             nrec = nent
         else:
             entry_rec = None
+    else:
+        entry_rec = None
+    if invalid:    # a record with a non-nucleotide letter is an error only if the reference would translate it
+        live = set(entry_rec.tolist()) if (ingest is not None and entry_rec is not None) else None
+        bad = [r for r in invalid if live is None or r in live]
+        if bad:
+            name = ingest.ids_of(bad[:1])[0] if ingest is not None else ids[bad[0]]
+            raise capi.PaError(f"invalid nucleotide character in read {name} (Biopython would raise TranslationError)")
     if sel is not None:
         model = [model[i] for i in sel]
         aligned = [aligned[i] for i in sel]

@@ -355,6 +355,19 @@ class IngestSource:
 
 CHUNK_BYTE_LIMIT = (1 << 32) - (1 << 20)   # pa_load_reads: 2 * nt + 32 * reads must stay below 4 GiB
 
+_VALID_NT = np.zeros(256, dtype=bool)          # what translate_kernel accepts = Biopython's unambiguous + IUPAC DNA/RNA letters
+_VALID_NT[list(b"ACGTURYMKSWHBVDNacgturymkswhbvdn")] = True
+
+
+def valid_reads_mask(nt: np.ndarray, off: np.ndarray) -> np.ndarray:
+    """Per read: does it consist of nucleotide letters only (same test as the device code, csrc/kernels.cuh nt_mask)?"""
+    n = len(off) - 1
+    bad = ~_VALID_NT[nt[:int(off[-1])]]
+    if not bad.any():
+        return np.ones(n, dtype=bool)
+    cs = np.r_[0, np.cumsum(bad)]
+    return (cs[off[1:].astype(np.int64)] - cs[off[:-1].astype(np.int64)]) == 0
+
 
 class B200Searcher:
     """All profiles x one read set on one or more B200s (one context per GPU, reads sharded by chunk)."""
@@ -396,6 +409,7 @@ class B200Searcher:
         results = []
         nframes_box = [1]
         errors = []
+        invalid = []
         lock = threading.Lock()
         cursor = [0]
         min_chunk = max(1, chunk_reads // 4)
@@ -418,11 +432,30 @@ class B200Searcher:
             return None
 
         def search_range(ctx, a, b, out):
-            """Search records [a, b); on a capacity error (-3) split the range (the library has no fallback)."""
+            """Search records [a, b); on a capacity error (-3) split the range (the library has no fallback).  Records with a
+            character Biopython's translate() would reject are left out and remembered (self.last_invalid): whether they
+            are an error is the caller's call -- read_fastx's dictionary may drop them before the reference translates."""
             sub_nt, sub_off = src.pack(a, b)
+            keep = None
             try:
-                ctx.load_reads(sub_nt, sub_off, moltype=0 if translated else 1, gencode=gencode, no_reverse=no_reverse,
-                               codon_only=codon)
+                try:
+                    ctx.load_reads(sub_nt, sub_off, moltype=0 if translated else 1, gencode=gencode, no_reverse=no_reverse,
+                                   codon_only=codon)
+                except capi.PaError as e:
+                    if "(-2)" not in str(e) or "invalid nucleotide" not in str(e):
+                        raise
+                    valid = valid_reads_mask(sub_nt, sub_off)
+                    if valid.all():
+                        raise
+                    keep = np.flatnonzero(valid)
+                    with lock:
+                        invalid.extend((a + np.flatnonzero(~valid)).tolist())
+                    lens = (sub_off[1:] - sub_off[:-1]).astype(np.int64)[keep]
+                    off2 = np.zeros(len(keep) + 1, dtype=np.uint64)
+                    off2[1:] = np.cumsum(lens)
+                    pos = np.repeat(sub_off[:-1].astype(np.int64)[keep] - off2[:-1].astype(np.int64), lens) + np.arange(int(off2[-1]))
+                    nt2 = sub_nt[pos] if len(pos) else np.zeros(1, dtype=np.uint8)
+                    ctx.load_reads(nt2, off2, moltype=0 if translated else 1, gencode=gencode, no_reverse=no_reverse, codon_only=codon)
                 nf = ctx.num_frames()
                 nframes_box[0] = nf
                 hits, model, aligned = ctx.search()
@@ -435,7 +468,10 @@ class B200Searcher:
                 raise
             pp = ctx.hit_pp(hits) if want_pp else [None] * len(hits)
             hits = hits.copy()
-            hits["target"] += a * nf
+            if keep is None:
+                hits["target"] += a * nf
+            else:
+                hits["target"] = ((a + keep[hits["target"] // nf]) * nf + hits["target"] % nf).astype(hits["target"].dtype)
             out.append((a, hits, model, aligned, pp))
 
         def work(ctx):
@@ -468,11 +504,14 @@ class B200Searcher:
         self.last_pp = [m for r in results for m in r[4]] if want_pp else None
         nreads = src.available()
         Z = nreads * nframes
+        self.last_invalid = sorted(invalid)
         return hits, model, aligned, Z, nframes, translated
 
     def search_and_report(self, nt, off, ids, **kw):
         hits, model, aligned, Z, nframes, translated = self.search_reads(nt, off, **kw)
         self.last_Z = Z
+        if self.last_invalid:
+            raise capi.PaError(f"invalid nucleotide character in read {ids[self.last_invalid[0]]} (Biopython would raise TranslationError)")
 
         def tname(t):
             read, frame = divmod(t, nframes)

@@ -71,6 +71,8 @@ class FakeCtx:
         n = len(off) - 1
         if 2 * int(off[-1]) + 32 * n + 64 >= search.CHUNK_BYTE_LIMIT or n > self.max_reads:
             raise capi.PaError("pa_load_reads failed (-3): split the chunk")
+        if not search.valid_reads_mask(nt, off).all():
+            raise capi.PaError("pa_load_reads failed (-2): invalid nucleotide character in reads (Biopython would raise TranslationError)")
         self.nt, self.off = nt, off
         self.calls.append(n)
         return n * 6
@@ -242,3 +244,21 @@ def test_gather_hits_files_roundtrip(tmp_path):
     hits, model, aligned = res[0]
     assert list(hits["target"]) == [0, 100, 101, 200, 201, 202] and model == ["m0", "m1", "m1", "m2", "m2", "m2"]
     assert os.listdir(tmp_path / "g") == []
+
+
+def test_records_with_invalid_letters_are_set_aside_not_fatal():
+    """A FASTQ quirk of the reference (config 1 has it) leaves records whose 'sequence' is a quality or header line; the
+    reference's dictionary drops most of them before translating.  The scheduler searches the rest of the chunk, keeps
+    global indices right and reports the records it left out."""
+    rng = np.random.default_rng(9)
+    marked = [3, 40, 41, 77]
+    nt, off = _reads(100, rng, marked)
+    nt = nt.copy()
+    for r in (5, 41, 99):                        # 41 is a marked read: its hit must disappear with it
+        nt[int(off[r]) + 2] = ord("!")
+    s = _searcher([FakeCtx()])
+    hits, *_ = s.search_reads(nt, off, chunk_reads=64)
+    assert s.last_invalid == [5, 41, 99]
+    assert sorted(int(t) for t in hits["target"]) == [6 * r + 2 for r in (3, 40, 77)]
+    with pytest.raises(capi.PaError, match="invalid nucleotide"):
+        s.search_and_report(nt, off, [f"r{i}" for i in range(100)], chunk_reads=64)
