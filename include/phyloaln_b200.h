@@ -232,7 +232,8 @@ int64_t pa_ingest_emitted_bytes(pa_ingest *ing, uint64_t first, uint64_t count);
 int64_t pa_ingest_emitted_ids(pa_ingest *ing, const uint64_t *idx, uint64_t n, char *out, uint64_t cap, uint64_t *out_off);
 int64_t pa_ingest_emitted_seqs(pa_ingest *ing, const uint64_t *idx, uint64_t n, char *out, uint64_t cap, uint64_t *out_off); /* same, sequences */
 /* after the end: number of records whose id repeats an earlier record's id (the reference's read_fastx dictionary,
- * lib/library.py:186-198, keeps one entry per id: first position, last sequence; 0 = every record is its own target) */
+ * lib/library.py:186-198, keeps one entry per id: first position, last sequence; 0 = every record is its own target).
+ * Counted on 64-bit id hashes: 0 is exact, a non-zero count tells the caller to compare the ids themselves. */
 int64_t pa_ingest_repeated_ids(pa_ingest *ing);
 /* after the end: 0 = all.raw.fasta order is the emission order; 1 = the chunk fold of check_file_num (lib/aln.py:262-271)
  * permuted it and emitted_index[final position] (num_records entries, may be NULL) is filled */

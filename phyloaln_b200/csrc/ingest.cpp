@@ -195,6 +195,7 @@ struct pa_ingest {
   bool started = false;
   int rc = 0;
   std::thread runner;
+  std::mutex wait_mu;
   // results
   Arena text;       // record texts
   RecStore recs;    // emission order
@@ -225,8 +226,8 @@ struct Builder {
   std::vector<MergeGroup> groups;
   std::vector<ExtraTag> extras;
   Arena arena;
-  // ids seen so far (hash, record index + 1): counts the records whose id is not new
-  std::vector<std::pair<uint64_t, uint64_t>> idtab = std::vector<std::pair<uint64_t, uint64_t>>(1 << 16);
+  // hashes of the ids seen so far: counts the records whose id is (very probably) not new
+  std::vector<uint64_t> idtab = std::vector<uint64_t>(1 << 16, 0);
   uint64_t n_ids = 0;
 
   int64_t find(std::string_view seq, uint64_t h) const {
@@ -257,28 +258,31 @@ struct Builder {
     while (table[i].second) i = (i + 1) & mask;
     table[i] = {h, gi + 1};
   }
-  void note_id(const char *id, uint32_t len, uint64_t rec_index) {
-    const uint64_t h = hash_bytes(id, len);
+  // Set of 64-bit id hashes (0 = empty slot).  A hit counts as "this id was seen before"; the rare false positive of a
+  // hash collision only sends the caller down the exact path (dropin._dictionary_view compares the ids themselves).
+  void note_id(const char *id, uint32_t len) {
+    uint64_t h = hash_bytes(id, len);
+    if (h == 0) h = 1;
     if ((n_ids + 1) * 2 > idtab.size()) {
-      std::vector<std::pair<uint64_t, uint64_t>> nt(idtab.size() * 2);
+      std::vector<uint64_t> nt(idtab.size() * 2, 0);
       const size_t mask = nt.size() - 1;
-      for (const auto &e : idtab)
-        if (e.second) {
-          size_t i = e.first & mask;
-          while (nt[i].second) i = (i + 1) & mask;
+      for (const uint64_t e : idtab)
+        if (e) {
+          size_t i = e & mask;
+          while (nt[i]) i = (i + 1) & mask;
           nt[i] = e;
         }
       idtab.swap(nt);
     }
     const size_t mask = idtab.size() - 1;
     for (size_t i = h & mask;; i = (i + 1) & mask) {
-      auto &e = idtab[i];
-      if (e.second == 0) { e = {h, rec_index + 1}; n_ids++; return; }
-      if (e.first == h) {
-        const Rec &r = S.recs.at(e.second - 1);
-        if (r.id_len == len && !memcmp(r.text + 1, id, len)) { S.id_dups++; return; }
-      }
+      if (idtab[i] == 0) { idtab[i] = h; n_ids++; return; }
+      if (idtab[i] == h) { S.id_dups++; return; }
     }
+  }
+  // look-ahead of the single pass: pull the table slot of an upcoming sequence into the cache
+  void prefetch_seq(const char *p, size_t n) const {
+    if ((int64_t)n <= S.merge_len) __builtin_prefetch(&table[hash_bytes(p, n) & (table.size() - 1)]);
   }
 
   explicit Builder(pa_ingest &s) : S(s) { chunks.emplace_back(); }
@@ -300,7 +304,7 @@ struct Builder {
   // append a finished record (text already in S.text) to chunk `ch`
   bool add_record(size_t ch, const char *text, uint32_t id_len, uint64_t body_len, bool has_body) {
     const uint64_t idx = S.recs.n;
-    note_id(text + 1, id_len, idx);
+    note_id(text + 1, id_len);
     auto &runs = chunks[ch];
     if (!runs.empty() && runs.back().first + runs.back().second == idx) runs.back().second++;
     else runs.emplace_back(idx, 1);
@@ -444,9 +448,15 @@ int run_pipeline(pa_ingest *S) {
       if (pos) s.erase(0, pos);
     };
     uint64_t line_num = 0;
+    const size_t nlines = fj.lines.size();
+    constexpr size_t AHEAD = 48;   // lines: 12 FASTQ records ahead of the pass
     for (const auto &ln : fj.lines) {
       const char *lp = T.data() + ln.first;
       const uint64_t ll = ln.second;
+      if (fj.format == 1 && !split_len && (line_num & 3) == 1 && line_num + AHEAD < nlines) {
+        const auto &la = fj.lines[line_num + AHEAD];
+        B.prefetch_seq(T.data() + la.first, la.second);
+      }
       if (fj.format == 1 && ll > 0 && lp[0] == '@' && line_num % 4 == 0) {
         seqid.assign(lp + 1, ll - 1);
         for (char &c : seqid)
@@ -608,6 +618,7 @@ extern "C" int pa_ingest_start(pa_ingest *S) {
 
 extern "C" int pa_ingest_wait(pa_ingest *S) {
   if (!S || !S->started) return -1;
+  std::lock_guard<std::mutex> lk(S->wait_mu);   // any number of threads may wait; one of them joins
   if (S->runner.joinable()) S->runner.join();
   return S->rc;
 }

@@ -176,8 +176,18 @@ def hmmsearch_step(outdir: str, groups, mol_type: str = "prot", gencode: int = 1
         return counts
     t0 = time.perf_counter()
     ids = nt = off = None
+    fin_thread, fin_err = None, []
     if ingest is not None:
         src = IngestSource(ingest)
+
+        def finish():     # all.raw.fasta & co. are written as soon as the ingest has ended, next to the last searches
+            try:
+                _finish_prepare_target(outdir, ingest)
+            except Exception as e:
+                fin_err.append(e)
+        import threading
+        fin_thread = threading.Thread(target=finish)
+        fin_thread.start()
     else:
         raw_fasta = raw_fasta or os.path.join(outdir, "all.raw.fasta")
         from .ingest import load_raw_fasta     # native loader; read_raw_fasta above is its plain-Python statement
@@ -201,7 +211,7 @@ def hmmsearch_step(outdir: str, groups, mol_type: str = "prot", gencode: int = 1
     nrec = src.available()
     sel = None
     if ingest is not None:
-        _finish_prepare_target(outdir, ingest)
+        ingest.wait()
         tm["finish_ingest_s"] = time.perf_counter() - t0
         if ingest.repeated_ids() > 0:    # read_fastx keeps one entry per id (config 1 does this: SURVEY B.5)
             hits, sel, nent, entry_rec = _dictionary_view(ingest, hits, nframes)
@@ -275,5 +285,11 @@ def hmmsearch_step(outdir: str, groups, mol_type: str = "prot", gencode: int = 1
         open(os.path.join(outdir, "ok", f"extract_reads_{g}.ok"), "w").close()
         counts[g] = len(idx)
     tm["write_outputs_s"] = time.perf_counter() - t0
+    if fin_thread is not None:
+        t0 = time.perf_counter()
+        fin_thread.join()
+        tm["wait_raw_fasta_written_s"] = time.perf_counter() - t0
+        if fin_err:
+            raise fin_err[0]
     hmmsearch_step.last_stats = stats
     return counts

@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import threading
 
 import numpy as np
 
@@ -116,15 +117,17 @@ class Ingest:
             for j, f in enumerate(files):
                 self._check(self.L.pa_ingest_add_file(self.h, os.fspath(f).encode(), sp.encode(), j + 1, file_format.encode()))
         self.n = -1
+        self._wait_lock = threading.Lock()
         self._check(self.L.pa_ingest_start(self.h))
         if wait:
             self.wait()
 
     def wait(self):
         """Join the background pass; raises on its error. Idempotent."""
-        if self.n < 0:
-            self._check(self.L.pa_ingest_wait(self.h))
-            self.n = int(self.L.pa_ingest_num_records(self.h))
+        with self._wait_lock:
+            if self.n < 0:
+                self._check(self.L.pa_ingest_wait(self.h))
+                self.n = int(self.L.pa_ingest_num_records(self.h))
         return self
 
     def done(self) -> bool:

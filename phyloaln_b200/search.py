@@ -375,19 +375,37 @@ class B200Searcher:
     def __init__(self, hmms, devices=(0,), options: SearchOptions | None = None):
         self.opts = options or SearchOptions()
         self.hmms = [h if isinstance(h, HMM) else read_hmm(h) for h in hmms]
-        self.ctxs = []
-        for d in devices:
-            c = capi.Context(d)
-            c.set_opts(F1=self.opts.F1, F2=self.opts.F2, F3=self.opts.F3, do_bias=not self.opts.nobias,
-                       do_null2=not self.opts.nonull2, do_max=self.opts.max)
-            for h in self.hmms:
-                c.add_hmm(h)
-            c.commit()
-            self.ctxs.append(c)
+        devices = list(devices)
+        self.ctxs = [None] * len(devices)
+        errors = []
+
+        def setup(k, d):     # one thread per GPU: context creation, profile configuration and upload run side by side
+            try:
+                c = capi.Context(d)
+                self.ctxs[k] = c
+                c.set_opts(F1=self.opts.F1, F2=self.opts.F2, F3=self.opts.F3, do_bias=not self.opts.nobias,
+                           do_null2=not self.opts.nonull2, do_max=self.opts.max)
+                for h in self.hmms:
+                    c.add_hmm(h)
+                c.commit()
+            except Exception as e:
+                errors.append(e)
+        if len(devices) == 1:
+            setup(0, devices[0])
+        else:
+            th = [threading.Thread(target=setup, args=(k, d)) for k, d in enumerate(devices)]
+            for t in th:
+                t.start()
+            for t in th:
+                t.join()
+        if errors:
+            self.close()
+            raise errors[0]
 
     def close(self):
         for c in self.ctxs:
-            c.close()
+            if c is not None:
+                c.close()
         self.ctxs = []
 
     def search_reads(self, nt: np.ndarray, off: np.ndarray, **kw):
