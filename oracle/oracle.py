@@ -19,7 +19,7 @@ _LIB = None
 class OrcOpts(C.Structure):
     _fields_ = [("F1", C.c_double), ("F2", C.c_double), ("F3", C.c_double), ("E", C.c_double),
                 ("domE", C.c_double), ("do_bias", C.c_int), ("do_null2", C.c_int), ("do_max", C.c_int),
-                ("Z", C.c_double), ("domZ", C.c_double), ("simd_msv", C.c_int), ("reserved", C.c_int)]
+                ("Z", C.c_double), ("domZ", C.c_double), ("simd_msv", C.c_int), ("simd_vit", C.c_int)]
 
 
 class OrcHit(C.Structure):
@@ -66,8 +66,12 @@ def lib():
         L.orc_digitize.argtypes = [C.c_int, C.c_char_p, C.c_int, C.c_void_p]
         L.orc_null1.restype = C.c_float
         L.orc_null1.argtypes = [C.c_int]
-        for f in (L.orc_msv, L.orc_vit, L.orc_msv_simd):
+        for f in (L.orc_msv, L.orc_vit, L.orc_msv_simd, L.orc_vit_simd):
             f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int)]
+        L.orc_search_many.restype = C.c_longlong
+        L.orc_search_many.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(OrcOpts), C.c_int, C.c_void_p]
+        L.orc_translate_reads.restype = C.c_longlong
+        L.orc_translate_reads.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
         L.orc_bias_filtersc.restype = C.c_float
         L.orc_bias_filtersc.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.orc_fwd_parser.restype = C.c_float
@@ -168,6 +172,13 @@ class Profile:
         rc = self.L.orc_msv_simd(self.p, d.ctypes.data, len(seq), C.byref(sc), C.byref(raw))
         return None if rc < 0 else (sc.value, raw.value)
 
+    def vit_simd(self, seq: str):
+        """(score, raw xC) from the striped AVX2 Viterbi filter, or None without AVX2."""
+        d = self.digitize(seq)
+        sc, raw = C.c_float(), C.c_int()
+        rc = self.L.orc_vit_simd(self.p, d.ctypes.data, len(seq), C.byref(sc), C.byref(raw))
+        return None if rc < 0 else (sc.value, raw.value)
+
     def vit(self, seq: str):
         d = self.digitize(seq)
         sc, raw = C.c_float(), C.c_int()
@@ -235,10 +246,13 @@ class Profile:
             trace = np.ctypeslib.as_array(tr).copy() if n else None
         return out, trace
 
-    def score_all(self, seqs: list[str]):
-        """Raw (msv, vit, fwd) nats for every sequence (no filtering) -- used for calibration."""
-        msv = np.array([self.msv(s)[0] for s in seqs], dtype=np.float64)
-        vit = np.array([self.vit(s)[0] for s in seqs], dtype=np.float64)
+    def score_all(self, seqs: list[str], simd: bool = False):
+        """Raw (msv, vit, fwd) nats for every sequence (no filtering) -- used for calibration.  simd: the striped AVX2
+        filters (same numbers, tests/test_oracle.py) where the CPU has them."""
+        fm = (lambda s: self.msv_simd(s) or self.msv(s)) if simd else self.msv
+        fv = (lambda s: self.vit_simd(s) or self.vit(s)) if simd else self.vit
+        msv = np.array([fm(s)[0] for s in seqs], dtype=np.float64)
+        vit = np.array([fv(s)[0] for s in seqs], dtype=np.float64)
         fwd = np.array([self.fwd(s)[0] for s in seqs], dtype=np.float64)
         return msv, vit, fwd
 
@@ -273,3 +287,29 @@ def six_frames(nt: str, table: int = 1, no_reverse: bool = False, codon: bool = 
         for j in (1, 2, 3):
             out.append((f"_rev_pos{j}", translate(rc[j - 1:], table)))
     return out
+
+
+def translate_reads(nt: np.ndarray, off: np.ndarray, table: int = 1, nthreads: int = 1):
+    """Six-frame translation + digitisation of concatenated reads in C: (dsq uint8, off int64[6n+1])."""
+    nt = np.ascontiguousarray(nt, dtype=np.uint8)
+    off = np.ascontiguousarray(off, dtype=np.int64)
+    n = len(off) - 1
+    dsq = np.zeros(2 * int(off[-1]) + 8, dtype=np.uint8)
+    toff = np.zeros(6 * n + 1, dtype=np.int64)
+    rc = lib().orc_translate_reads(nt.ctypes.data, off.ctypes.data, n, table, dsq.ctypes.data, toff.ctypes.data, nthreads)
+    if rc < 0:
+        raise ValueError("invalid nucleotide character (Biopython would raise TranslationError)")
+    return dsq, toff
+
+
+def search_many(profiles, dsq: np.ndarray, off: np.ndarray, opts: OrcOpts | None = None, nthreads: int = 1):
+    """Every profile against every digital target in one OpenMP region (the CPU baseline of bench.py).
+    Returns (number of domains, stage counts[6])."""
+    opts = opts or default_opts()
+    arr = (C.c_void_p * len(profiles))(*[p.p for p in profiles])
+    st = np.zeros(6, dtype=np.int64)
+    nd = lib().orc_search_many(arr, len(profiles), dsq.ctypes.data, off.ctypes.data, len(off) - 1, C.byref(opts), nthreads,
+                               st.ctypes.data)
+    if nd < 0:
+        raise MemoryError("oracle hit buffers too small")
+    return int(nd), st

@@ -388,6 +388,26 @@ ORC_PROFILE *orc_profile_create(const ORC_HMM *h) {
       p->twv[k * 8 + t] = v < cap ? v : cap;
     }
 
+  /* striped copies for orc_vit_simd */
+  p->Qw = (M + 15) / 16;
+  p->rwv_s = p->twv_s = NULL;
+  if (posix_memalign((void **)&p->rwv_s, 32, (size_t)Kp * p->Qw * 32) != 0) p->rwv_s = NULL;
+  if (posix_memalign((void **)&p->twv_s, 32, (size_t)8 * p->Qw * 32) != 0) p->twv_s = NULL;
+  if (p->rwv_s && p->twv_s) {
+    const int Qw = p->Qw;
+    for (size_t i = 0; i < (size_t)Kp * Qw * 16; i++) p->rwv_s[i] = -32768;
+    for (size_t i = 0; i < (size_t)8 * Qw * 16; i++) p->twv_s[i] = -32768;
+    static const int kind[8] = {ORC_BM, ORC_MM, ORC_IM, ORC_DM, ORC_MI, ORC_II, ORC_MD, ORC_DD};
+    for (int k = 1; k <= M; k++) {
+      const size_t pos = (size_t)((k - 1) % Qw) * 16 + (size_t)((k - 1) / Qw);
+      for (int x = 0; x < Kp; x++) p->rwv_s[(size_t)x * Qw * 16 + pos] = p->rwv[x * (M + 1) + k];
+      for (int z = 0; z < 8; z++) {
+        const int node = (z == 4 || z == 5) ? k : k - 1;   /* MI, II belong to node k; the others lead from k-1 to k */
+        p->twv_s[(size_t)z * Qw * 16 + pos] = p->twv[node * 8 + kind[z]];
+      }
+    }
+  }
+
   /* float odds */
   for (int i = 0; i < Kp * (M + 1); i++) p->rfv[i] = expf(p->msc[i]);
   for (int i = 0; i < (M + 1) * 8; i++) p->tfv[i] = expf(p->tsc[i]);
@@ -400,6 +420,8 @@ void orc_profile_free(ORC_PROFILE *p) {
   free(p->msc);
   free(p->rbv);
   free(p->rbv_s);
+  free(p->rwv_s);
+  free(p->twv_s);
   free(p->rwv);
   free(p->twv);
   free(p->rfv);

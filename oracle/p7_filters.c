@@ -185,6 +185,108 @@ int orc_vit(const ORC_PROFILE *p, const uint8_t *dsq, int L, float *ret_sc, int 
   return 0;
 }
 
+/* ---------------- Viterbi filter, striped AVX2 (16 signed saturating words per vector) ----------------
+ * The recurrences of orc_vit above on Farrar's striped layout.  M and I of a row only need the previous row; D(k) also
+ * needs D(k-1) of the SAME row, which crosses vector lanes: a first sweep assumes nothing enters a lane from its left
+ * neighbour, then the D->D path is pushed across the lane boundaries until no cell changes ("lazy F").  Saturating max-plus
+ * arithmetic gives the same words as the serial recurrence whatever the evaluation order. */
+#if defined(__x86_64__)
+__attribute__((target("avx2"))) static inline __m256i shift_words(__m256i v) {
+  /* lane j <- lane j-1, lane 0 <- -32768 */
+  __m256i t = _mm256_permute2x128_si256(v, v, 0x08);
+  __m256i r = _mm256_alignr_epi8(v, t, 14);
+  return _mm256_or_si256(r, _mm256_set_epi16(0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, (short)0x8000));
+}
+
+__attribute__((target("avx2"))) int orc_vit_simd(const ORC_PROFILE *p, const uint8_t *dsq, int L, float *ret_sc, int *xC_raw) {
+  if (!p->rwv_s || !p->twv_s || !orc_have_avx2()) return -1;
+  const int Q = p->Qw;
+  float pmove = (2.0f + 1.0f) / ((float)L + 2.0f + 1.0f);
+  int xw_move = p7i_wordify(p->scale_w, logf(pmove));
+  int xw_E = p7i_wordify(p->scale_w, -0.69314718055994529f);
+  const __m256i *tBM = (const __m256i *)p->twv_s, *tMM = tBM + Q, *tIM = tMM + Q, *tDM = tIM + Q, *tMI = tDM + Q, *tII = tMI + Q,
+                *tMD = tII + Q, *tDD = tMD + Q;
+  __m256i stackbuf[3 * 48];
+  __m256i *mmx = Q <= 48 ? stackbuf : (__m256i *)aligned_alloc(32, (size_t)3 * Q * 32);
+  __m256i *imx = mmx + Q, *dmx = imx + Q;
+  const __m256i neg = _mm256_set1_epi16(-32768);
+  for (int q = 0; q < 3 * Q; q++) mmx[q] = neg;
+  int xN = p->base_w, xB = sat_adds16(xN, xw_move), xJ = -32768, xC = -32768;
+  int overflow = 0;
+  for (int i = 1; i <= L; i++) {
+    const __m256i *rsc = (const __m256i *)(p->rwv_s + (size_t)dsq[i] * Q * 16);
+    const __m256i xBv = _mm256_set1_epi16((short)xB);
+    __m256i mpv = shift_words(mmx[Q - 1]), ipv = shift_words(imx[Q - 1]), dpv = shift_words(dmx[Q - 1]);
+    __m256i xEv = neg;
+    for (int q = 0; q < Q; q++) {
+      __m256i sv = _mm256_adds_epi16(xBv, tBM[q]);
+      sv = _mm256_max_epi16(sv, _mm256_adds_epi16(mpv, tMM[q]));
+      sv = _mm256_max_epi16(sv, _mm256_adds_epi16(ipv, tIM[q]));
+      sv = _mm256_max_epi16(sv, _mm256_adds_epi16(dpv, tDM[q]));
+      sv = _mm256_adds_epi16(sv, rsc[q]);
+      xEv = _mm256_max_epi16(xEv, sv);
+      mpv = mmx[q];
+      ipv = imx[q];
+      dpv = dmx[q];
+      imx[q] = _mm256_max_epi16(_mm256_adds_epi16(mpv, tMI[q]), _mm256_adds_epi16(ipv, tII[q]));
+      mmx[q] = sv;
+    }
+    __m128i m = _mm_max_epi16(_mm256_castsi256_si128(xEv), _mm256_extracti128_si256(xEv, 1));
+    m = _mm_max_epi16(m, _mm_srli_si128(m, 8));
+    m = _mm_max_epi16(m, _mm_srli_si128(m, 4));
+    m = _mm_max_epi16(m, _mm_srli_si128(m, 2));
+    int xE = (int)(short)(_mm_cvtsi128_si32(m) & 0xffff);
+    if (xE >= 32767) { overflow = 1; break; }
+    /* D of this row: first sweep inside the lanes */
+    __m256i mleft = shift_words(mmx[Q - 1]), dleft = neg;
+    for (int q = 0; q < Q; q++) {
+      __m256i d = _mm256_max_epi16(_mm256_adds_epi16(mleft, tMD[q]), _mm256_adds_epi16(dleft, tDD[q]));
+      dmx[q] = d;
+      mleft = mmx[q];
+      dleft = d;
+    }
+    /* then across the lanes until nothing changes (at most 16 sweeps: one per lane) */
+    for (int pass = 0; pass < 16; pass++) {
+      dleft = shift_words(dmx[Q - 1]);
+      int q;
+      for (q = 0; q < Q; q++) {
+        __m256i cand = _mm256_adds_epi16(dleft, tDD[q]);
+        if (_mm256_movemask_epi8(_mm256_cmpgt_epi16(cand, dmx[q])) == 0) break;
+        dmx[q] = _mm256_max_epi16(dmx[q], cand);
+        dleft = dmx[q];
+      }
+      if (q < Q) break;
+    }
+    xC = MAX2(xC, xE + xw_E);
+    xJ = MAX2(xJ, xE + xw_E);
+    xB = MAX2(xJ + xw_move, xN + xw_move);
+    if (xC < -32768) xC = -32768;
+    if (xJ < -32768) xJ = -32768;
+    if (xB < -32768) xB = -32768;
+  }
+  if (mmx != stackbuf) free(mmx);
+  if (overflow) {
+    *ret_sc = INFINITY;
+    if (xC_raw) *xC_raw = 32767;
+    return 1;
+  }
+  if (xC_raw) *xC_raw = xC;
+  if (xC > -32768) {
+    float sc = (float)xC + (float)xw_move - (float)p->base_w;
+    sc /= p->scale_w;
+    sc -= 3.0f;
+    *ret_sc = sc;
+  } else
+    *ret_sc = -INFINITY;
+  return 0;
+}
+#else
+int orc_vit_simd(const ORC_PROFILE *p, const uint8_t *dsq, int L, float *ret_sc, int *xC_raw) {
+  (void)p; (void)dsq; (void)L; (void)ret_sc; (void)xC_raw;
+  return -1;
+}
+#endif
+
 /* ---------------- bias filter: 2-state HMM forward ---------------- */
 float orc_bias_filtersc(const ORC_PROFILE *p, const uint8_t *dsq, int L) {
   int K = p->K, Kp = p->Kp;

@@ -64,7 +64,7 @@ static int one_target(const ORC_PROFILE *p, const uint8_t *seq, int L, int tidx,
   t.filtersc = filtersc;
   t.stage = 2;
   if (P > F2) {
-    orc_vit(p, dsq, L, &vfsc, &t.vit_xC);
+    if (o->simd_vit == 0 || orc_vit_simd(p, dsq, L, &vfsc, &t.vit_xC) < 0) orc_vit(p, dsq, L, &vfsc, &t.vit_xC);
     t.vfsc = vfsc;
     seq_score = (float)((vfsc - filtersc) / LN2);
     P = orc_gumbel_surv(seq_score, ev[2], ev[3]);
@@ -209,4 +209,76 @@ int orc_search(const ORC_PROFILE *p, const uint8_t *dsq, const int64_t *off, int
   free(lt);
   free(lused);
   return overflow ? -1 : nhits;
+}
+
+long long orc_search_many(const ORC_PROFILE *const *profs, int nprof, const uint8_t *dsq, const int64_t *off, int n,
+                          const ORC_OPTS *o, int nthreads, long long *stage_counts) {
+  orc_flogsum(0.0f, 0.0f); /* init table before threads */
+  if (nthreads < 1) nthreads = 1;
+  const int BLK = 1024;
+  const int nblk = (n + BLK - 1) / BLK;
+  int maxL = 0, maxM = 0;
+  for (int t = 0; t < n; t++)
+    if ((int)(off[t + 1] - off[t]) > maxL) maxL = (int)(off[t + 1] - off[t]);
+  for (int h = 0; h < nprof; h++)
+    if (profs[h]->M > maxM) maxM = profs[h]->M;
+  const int cap = 8 * maxL + 8 * maxM + 128;
+  long long ndom = 0, st[6] = {0, 0, 0, 0, 0, 0};
+  int failed = 0;
+#pragma omp parallel num_threads(nthreads) reduction(+ : ndom, st[:6])
+  {
+    char *m = (char *)malloc((size_t)cap), *g = (char *)malloc((size_t)cap);
+    ORC_HIT tmp[MAXDOM_PER_SEQ];
+    /* profile-major: the threads walk the blocks of one profile together, so its tables stay in the shared cache */
+#pragma omp for schedule(dynamic, 1)
+    for (long long w = 0; w < (long long)nprof * nblk; w++) {
+      const int h = (int)(w / nblk), b = (int)(w % nblk);
+      const int t1 = (b + 1) * BLK < n ? (b + 1) * BLK : n;
+      for (int t = b * BLK; t < t1; t++) {
+        ORC_TRACE tr;
+        int pu = 0;
+        const int nh = one_target(profs[h], dsq + off[t], (int)(off[t + 1] - off[t]), t, o, &tr, tmp, MAXDOM_PER_SEQ, m, g, cap, &pu);
+        if (nh < 0) failed = 1;
+        else ndom += nh;
+        st[tr.stage]++;
+      }
+    }
+    free(m);
+    free(g);
+  }
+  if (stage_counts)
+    for (int i = 0; i < 6; i++) stage_counts[i] = st[i];
+  return failed ? -1 : ndom;
+}
+
+long long orc_translate_reads(const char *nt, const int64_t *off, int nreads, int table, uint8_t *dsq_out, int64_t *off_out,
+                              int nthreads) {
+  if (nthreads < 1) nthreads = 1;
+  int64_t pos = 0;
+  for (int r = 0; r < nreads; r++) {
+    const int L = (int)(off[r + 1] - off[r]);
+    for (int f = 0; f < 6; f++) {
+      const int j = f % 3;
+      off_out[(size_t)6 * r + f] = pos;
+      pos += (L - j) >= 3 ? (L - j) / 3 : 0;
+    }
+  }
+  off_out[(size_t)6 * nreads] = pos;
+  int bad = 0;
+#pragma omp parallel for schedule(static) num_threads(nthreads)
+  for (int r = 0; r < nreads; r++) {
+    const int L = (int)(off[r + 1] - off[r]);
+    char *rc = (char *)malloc((size_t)L + 1), *aa = (char *)malloc((size_t)L / 3 + 2);
+    orc_revcomp(nt + off[r], L, rc);
+    for (int f = 0; f < 6; f++) {
+      const int j = f % 3;
+      const char *src = (f < 3 ? nt + off[r] : rc) + j;
+      const int naa = (L - j) >= 3 ? orc_translate(src, L - j, table, aa) : 0;
+      if (naa < 0) { bad = 1; continue; }
+      orc_digitize(ORC_AMINO, aa, naa, dsq_out + off_out[(size_t)6 * r + f]);
+    }
+    free(rc);
+    free(aa);
+  }
+  return bad ? -1 : (long long)6 * nreads;
 }

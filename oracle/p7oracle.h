@@ -74,6 +74,10 @@ typedef struct {
   /* float odds */
   float *rfv;          /* Kp*(M+1) = expf(msc)                                */
   float *tfv;          /* (M+1)*8  = expf(tsc)                                */
+  /* striped copies for the AVX2 Viterbi filter (orc_vit_simd): cell k -> vector (k-1) % Qw, word lane (k-1) / Qw   */
+  int16_t *rwv_s;      /* Kp * Qw * 16, padding -32768                        */
+  int16_t *twv_s;      /* 8 * Qw * 16: BM MM IM DM (k-1 -> k) | MI II (k) | MD DD (k-1 -> k), padding -32768 */
+  int Qw;              /* vectors per row = ceil(M/16)                        */
 } ORC_PROFILE;
 
 typedef struct {
@@ -82,7 +86,7 @@ typedef struct {
   int do_bias, do_null2, do_max;
   double Z, domZ;          /* <=0: set by number of targets / reported */
   int simd_msv;            /* 1: MSV through the striped AVX2 filter (same numbers; bench.py's CPU baseline) */
-  int reserved;
+  int simd_vit;            /* 1: Viterbi filter through the striped AVX2 filter (same numbers)                */
 } ORC_OPTS;
 
 typedef struct {
@@ -128,6 +132,9 @@ int orc_profile_rbv(const ORC_PROFILE *p, int x, int k);
  * Returns -1 if the CPU has no AVX2 (callers then use orc_msv). */
 int orc_msv_simd(const ORC_PROFILE *p, const uint8_t *dsq, int L, float *ret_sc, int *xJ_raw);
 int orc_have_avx2(void);
+/* Striped AVX2 Viterbi filter (16 signed words per vector, Farrar layout with lazy D->D propagation, the way HMMER's
+ * p7_ViterbiFilter is vectorised): same xC word and score as orc_vit, bit for bit. -1 without AVX2. */
+int orc_vit_simd(const ORC_PROFILE *p, const uint8_t *dsq, int L, float *ret_sc, int *xC_raw);
 int orc_profile_rwv(const ORC_PROFILE *p, int x, int k);
 int orc_profile_bytes(const ORC_PROFILE *p, int which);
 
@@ -154,6 +161,17 @@ double orc_generic_viterbi(const ORC_PROFILE *p, const uint8_t *dsq, int L, int 
 int orc_search(const ORC_PROFILE *p, const uint8_t *dsq, const int64_t *off, int n,
                const ORC_OPTS *o, ORC_HIT *hits, int maxhits, char *model_pool, char *target_pool,
                int poolcap, ORC_TRACE *trace, int nthreads);
+
+/* CPU baseline driver (bench.py): every profile against every target in ONE OpenMP region (profile-major blocks of
+ * targets, per-thread scratch), hits counted but not returned.  stage_counts[6]: targets that ended in each ORC_TRACE.stage
+ * summed over profiles.  Returns the number of domains, or -1. */
+long long orc_search_many(const ORC_PROFILE *const *profs, int nprof, const uint8_t *dsq, const int64_t *off, int n,
+                          const ORC_OPTS *o, int nthreads, long long *stage_counts);
+/* Six-frame translation + digitisation of a chunk of reads (reference lib/aln.py:249-258 frame order: pos1..3, rev_pos1..3)
+ * into the layout orc_search* takes: dsq_out (capacity 2*total nt + 8), off_out[6*nreads + 1].  Returns 6*nreads, -1 on an
+ * invalid nucleotide. */
+long long orc_translate_reads(const char *nt, const int64_t *off, int nreads, int table, uint8_t *dsq_out, int64_t *off_out,
+                              int nthreads);
 
 /* domain-definition internals exposed for tests */
 int orc_domain_decoding(const ORC_PROFILE *p, const uint8_t *dsq, int L, float *btot, float *etot,

@@ -268,3 +268,61 @@ def test_simd_msv_equals_scalar_msv(oracle):
     a, _ = P.search(seqs, opts=oracle.default_opts(simd_msv=1), nthreads=2)
     b, _ = P.search(seqs, nthreads=2)
     assert [(x["target"], x["iali"], x["jali"], x["seq_bits"]) for x in a] == [(x["target"], x["iali"], x["jali"], x["seq_bits"]) for x in b]
+
+
+def test_simd_viterbi_equals_scalar_viterbi(oracle):
+    """The AVX2 striped Viterbi filter (lazy D->D sweeps) returns the scalar filter's xC word and score, for amino and DNA
+    profiles, widths around the 16-lane stripe boundaries, planted fragments (long D chains across lanes) and overflow."""
+    import numpy as np
+    from phyloaln_b200 import hmmbuild_lite as hb, synth
+    from tests import helpers
+    rng = np.random.default_rng(6)
+    for abc, M in (("amino", 1), ("amino", 15), ("amino", 16), ("amino", 17), ("amino", 200), ("amino", 470), ("dna", 333), ("amino", 2100), ("dna", 800)):
+        h = helpers.calibrated_hmm(f"v{M}", M, seed=700 + M, n=8, abc=abc, bg_mix=0.1)
+        P = oracle.Profile.from_hmm(h)
+        seqs = [hb.random_sequences(abc, 1, int(rng.integers(1, 160)), rng)[0] for _ in range(60)]
+        for _ in range(25):   # fragments with deletions in the middle: D->D runs that cross stripe lanes
+            a = int(rng.integers(1, max(2, M // 2)))
+            b = int(rng.integers(a, M + 1))
+            frag = synth.sample_protein(h, rng, a, b)
+            if len(frag) > 12:
+                cut = int(rng.integers(2, len(frag) - 2))
+                frag = frag[:cut] + frag[cut + int(rng.integers(1, max(2, min(40, len(frag) - cut - 1)))):]
+            seqs.append(frag)
+        if M >= 200:
+            seqs.append(synth.sample_protein(h, rng, 1, M) * 3)   # overflow of the 16-bit range
+        for s in seqs:
+            got = P.vit_simd(s)
+            if got is None:
+                pytest.skip("no AVX2 on this host")
+            assert got == P.vit(s), (abc, M, len(s))
+
+
+def test_search_many_and_translate_reads_equal_the_per_profile_calls(oracle):
+    """bench.py's CPU baseline driver (one OpenMP region over all profiles, SIMD filters, C six-frame translation) counts
+    the same funnel and domains as per-profile scalar searches over Python-translated frames."""
+    import numpy as np
+    from phyloaln_b200 import synth
+    from tests import helpers
+    rng = np.random.default_rng(12)
+    hmms = [helpers.calibrated_hmm(f"m{i}", M, seed=50 + i, bg_mix=0.1, n=24) for i, M in enumerate([60, 140, 333])]
+    reads = synth.random_reads(500, 150, rng)
+    synth.plant_reads(reads, hmms, 0.2, rng, sub_rate=0.02)
+    reads[7, 10] = ord("N")
+    reads[8, 11] = ord("r")
+    off = np.arange(len(reads) + 1, dtype=np.int64) * 150
+    dsq, toff = oracle.translate_reads(reads.reshape(-1), off, 1, nthreads=3)
+    frames = [p for r in reads for _, p in oracle.six_frames(r.tobytes().decode(), 1)]
+    assert len(toff) == len(frames) + 1 and [int(b - a) for a, b in zip(toff[:-1], toff[1:])] == [len(f) for f in frames]
+    cat = "".join(frames).encode()
+    want = np.zeros(len(cat), dtype=np.uint8)
+    oracle.lib().orc_digitize(0, cat, len(cat), want.ctypes.data)
+    assert np.array_equal(dsq[:len(cat)], want)
+    profs = [oracle.Profile.from_hmm(h) for h in hmms]
+    nd, st = oracle.search_many(profs, dsq, toff, oracle.default_opts(simd_msv=1, simd_vit=1), nthreads=4)
+    ndom, stages = 0, np.zeros(6, dtype=np.int64)
+    for P in profs:
+        hits, tr = P.search(frames, nthreads=4)
+        ndom += len(hits)
+        stages += np.bincount(tr["stage"], minlength=6)
+    assert nd == ndom and st.tolist() == stages.tolist() and nd > 30
