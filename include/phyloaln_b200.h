@@ -166,7 +166,9 @@ int pa_score_all(pa_ctx *ctx, int hmm, float *msv, int32_t *msv_raw, float *vit,
 /* Measured issue rates of the instructions the filters are built from (no reference equivalent;
  * roofline denominators). mode 0 VIADDMNMX.S16x2.RELU, 1 VIMNMX3.S16x2, 2 DPX SSV mix (8 VIADDMNMX +
  * 4 VIMNMX3), 3 VIADDMNMX.S32, 4 HFMA2.RELU, 5 fp16 SSV mix of msv_tmem_kernel (8 HFMA2.RELU + 4
- * VIMNMX3.S16x2 per 16 cells). Result in giga thread-instructions per second over the whole GPU. */
+ * VIMNMX3.S16x2 per 16 cells), 6 HFMA2.RELU warps next to DPX-mix warps (even / odd warps of a CTA), 7 both formulations in
+ * every warp; 6 and 7 count the cell-update instructions only (2 cells each). Result in giga thread-instructions per second
+ * over the whole GPU. */
 int pa_microbench_dpx(pa_ctx *ctx, int mode, double *ginstr_per_s);
 
 /* The order in which the MSV kernels walk their work items (no reference equivalent): item -> (profile slot, target tile),

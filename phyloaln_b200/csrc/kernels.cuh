@@ -1100,9 +1100,9 @@ static __global__ void __launch_bounds__(128) fwd_kernel_t(FwdTArgs a) {
 namespace pa {
 template <int MODE>
 static __global__ void __launch_bounds__(256) dpx_microbench_kernel(uint32_t *out, int iters, uint32_t seed) {
-  uint32_t v[8], d = seed ^ threadIdx.x, m = 0;
+  uint32_t v[8], u[8], d = seed ^ threadIdx.x, d2 = (seed >> 3) ^ threadIdx.x, m = 0;
 #pragma unroll
-  for (int i = 0; i < 8; i++) v[i] = (threadIdx.x * 2654435761u + i) & 0x00ff00ffu;
+  for (int i = 0; i < 8; i++) { v[i] = (threadIdx.x * 2654435761u + i) & 0x00ff00ffu; u[i] = v[i] ^ 0x00110011u; }
   for (int it = 0; it < iters; it++) {
 #pragma unroll
     for (int i = 0; i < 8; i++) {
@@ -1115,7 +1115,28 @@ static __global__ void __launch_bounds__(256) dpx_microbench_kernel(uint32_t *ou
         if (MODE == 5 && (i & 1)) m = __vimax3_s16x2(m, v[i], v[i - 1]);  // + running max (ALU pipe)
       }
     }
+    if (MODE == 6 || MODE == 7) {
+      // can the ALU pipe's DPX formulation run NEXT TO the FMA pipe's fp16 formulation?  6: even warps HFMA2.RELU chains, odd
+      // warps the DPX SSV mix (8 VIADDMNMX.S16x2.RELU + 4 VIMNMX3.S16x2); 7: both in every warp, on independent registers
+      const bool fma_warp = MODE == 7 || ((threadIdx.x >> 5) & 1) == 0, dpx_warp = MODE == 7 || !fma_warp;
+      if (fma_warp) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) asm("fma.rn.relu.f16x2 %0, %0, %1, %2;" : "+r"(v[i]) : "r"(0x3c003c00u), "r"(d));
+      }
+      if (dpx_warp) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          u[i] = __viaddmax_s16x2_relu(u[i], d2, 0u);
+          if (i & 1) m = __vimax3_s16x2(m, u[i], u[i - 1]);
+        }
+      }
+      d2 += 0x00010001u;
+    }
     if (MODE >= 4) d ^= 0x80008000u; else d += 0x00010001u;
+  }
+  if (MODE >= 6) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) m ^= u[i];
   }
   uint32_t r = m;
 #pragma unroll

@@ -206,6 +206,7 @@ __global__ void __launch_bounds__(MsvTmemCfg<Q>::THREADS, MsvTmemCfg<Q>::MINB) m
   extern __shared__ __align__(16) uint32_t s_tab[];  // (nrows + 1) * SROW words (hybrid only)
   __shared__ uint32_t s_slot;
   __shared__ unsigned long long s_item;
+  __shared__ unsigned int s_next;
   // the shuffle tells the compiler that the warp index (and everything derived from it: target index,
   // length, loop bounds) is warp-uniform, so shuffles inside those loops need no divergence guards
   const int lane = threadIdx.x & 31, wib = __shfl_sync(PA_FULL, (int)(threadIdx.x >> 5), 0), wpb = blockDim.x >> 5;
@@ -217,10 +218,12 @@ __global__ void __launch_bounds__(MsvTmemCfg<Q>::THREADS, MsvTmemCfg<Q>::MINB) m
   unsigned long long ncand = 0;
   const int lanem1 = (lane + 31) & 31;
   // work items (profile-major) are handed out through an atomic counter: CTAs finish within one item of
-  // each other, and neighbouring items share the profile, so the TMEM table is refilled rarely
+  // each other, and neighbouring items share the profile, so the TMEM table is refilled rarely.  Inside an
+  // item the warps claim targets one at a time from a shared-memory counter, so a warp that has to re-run a
+  // candidate with the exact recurrence does not keep the others waiting at the item's barrier.
   for (;;) {
     __syncthreads();
-    if (threadIdx.x == 0) s_item = atomicAdd(a.work, 1ull);
+    if (threadIdx.x == 0) { s_item = atomicAdd(a.work, 1ull); s_next = (unsigned int)wpb; }
     __syncthreads();
     const unsigned long long item = s_item;
     if (item >= nitems) break;
@@ -250,17 +253,22 @@ __global__ void __launch_bounds__(MsvTmemCfg<Q>::THREADS, MsvTmemCfg<Q>::MINB) m
       cur_h = h;
     }
     const int bias = hm.bias, base = hm.base, tec = hm.tec, tbm = hm.tbm;
-    const uint32_t t1 = min(a.tg.n, (tile + 1) * a.tile);
-    uint32_t t = tile * a.tile + wib;
+    const uint32_t t0 = tile * a.tile, t1 = min(a.tg.n, (tile + 1) * a.tile);
+    uint32_t t = t0 + wib, tn;
     int nxL = 0, nxli = 0;
     uint32_t nxoff = 0;
     if (t < t1) { nxL = (int)a.tg.len[t]; nxoff = a.tg.off[t]; nxli = a.tg.lidx[t]; }
     int pre_x = 0;          // this lane's residue of the next block to be processed
     bool have_pre = false;  // warp-uniform
-    for (; t < t1; t += wpb) {
+    for (; t < t1; t = tn) {
       const int L = nxL, li = nxli;
       const uint8_t *p = a.tg.dsq + nxoff;
-      if (t + wpb < t1) { nxL = (int)a.tg.len[t + wpb]; nxoff = a.tg.off[t + wpb]; nxli = a.tg.lidx[t + wpb]; }
+      {  // claim this warp's next target and fetch its metadata one target ahead
+        unsigned int c = 0;
+        if (lane == 0) c = atomicAdd(&s_next, 1u);
+        tn = t0 + __shfl_sync(PA_FULL, c, 0);
+      }
+      if (tn < t1) { nxL = (int)a.tg.len[tn]; nxoff = a.tg.off[tn]; nxli = a.tg.lidx[tn]; }
       else nxL = 0;
       if (L == 0) { have_pre = false; continue; }
       const int tjb = a.tjb_li[li];
@@ -382,6 +390,7 @@ __global__ void __launch_bounds__(1024, 1) msv_pack_kernel(MsvPackArgs pa_, int 
   const MsvArgs &a = pa_.a;
   __shared__ uint32_t s_slot;
   __shared__ unsigned long long s_item;
+  __shared__ unsigned int s_next;
   const int lane = threadIdx.x & 31, wib = __shfl_sync(PA_FULL, (int)(threadIdx.x >> 5), 0), wpb = blockDim.x >> 5;
   const uint32_t tbase = tmem_alloc(&s_slot, (uint32_t)ncols);
   const uint32_t lanebase = tbase + ((uint32_t)((wib & 3) * 32) << 16);
@@ -392,7 +401,7 @@ __global__ void __launch_bounds__(1024, 1) msv_pack_kernel(MsvPackArgs pa_, int 
   const int lanem1 = (lane + 31) & 31;
   for (;;) {
     __syncthreads();
-    if (threadIdx.x == 0) s_item = atomicAdd(a.work, 1ull);
+    if (threadIdx.x == 0) { s_item = atomicAdd(a.work, 1ull); s_next = (unsigned int)wpb; }   // warp w starts with target w of the item
     __syncthreads();
     const unsigned long long item = s_item;
     if (item >= nitems) break;
@@ -419,17 +428,23 @@ __global__ void __launch_bounds__(1024, 1) msv_pack_kernel(MsvPackArgs pa_, int 
       tmem_cta_sync();
       cur_pk = pk;
     }
-    const uint32_t t1 = min(a.tg.n, (tile + 1) * a.tile);
-    uint32_t t = tile * a.tile + wib;
+    const uint32_t t0 = tile * a.tile, t1 = min(a.tg.n, (tile + 1) * a.tile);
+    uint32_t t = t0 + wib, tn;
     int nxL = 0, nxli = 0;
     uint32_t nxoff = 0;
     if (t < t1) { nxL = (int)a.tg.len[t]; nxoff = a.tg.off[t]; nxli = a.tg.lidx[t]; }
     int pre_x = 0;
     bool have_pre = false;
-    for (; t < t1; t += wpb) {
+    for (; t < t1; t = tn) {
       const int L = nxL, li = nxli;
       const uint8_t *p = a.tg.dsq + nxoff;
-      if (t + wpb < t1) { nxL = (int)a.tg.len[t + wpb]; nxoff = a.tg.off[t + wpb]; nxli = a.tg.lidx[t + wpb]; }
+      {  // targets of the item are claimed one at a time (shared-memory counter): a warp busy with an exact re-run
+         // does not hold up the item; the next target's metadata and first residues are fetched one target ahead
+        unsigned int c = 0;
+        if (lane == 0) c = atomicAdd(&s_next, 1u);
+        tn = t0 + __shfl_sync(PA_FULL, c, 0);
+      }
+      if (tn < t1) { nxL = (int)a.tg.len[tn]; nxoff = a.tg.off[tn]; nxli = a.tg.lidx[tn]; }
       else nxL = 0;
       if (L == 0) { have_pre = false; continue; }
       // ---- SSV pass over the whole pack

@@ -27,6 +27,7 @@ ap.add_argument("--config", type=int, required=True)
 ap.add_argument("--fraction", type=float, default=1.0)
 ap.add_argument("--chunk", type=int, default=0)
 ap.add_argument("--out", default=None)
+ap.add_argument("--profile-region", action="store_true", help="cudaProfilerStart after calibration (ncu --profile-from-start off)")
 a = ap.parse_args()
 rng = synth.config_rng(a.config)
 shape = synth.CONFIG_SHAPES[a.config]
@@ -46,6 +47,8 @@ funnel = {k: 0 for k in ("n_pairs", "n_cells", "n_past_ssv", "n_past_msv", "n_pa
 stage = {k: 0.0 for k in ("ms_translate", "ms_msv", "ms_bias", "ms_vit", "ms_fwd", "ms_domain", "ms_total")}
 done = 0
 vit_exact = 0
+if a.profile_region:
+    capi.profiler_range(True)
 while done < n_units:
     n = min(chunk, n_units - done)
     nt, off, npl = synth.config_chunk(a.config, n, rng, hmms)
