@@ -206,6 +206,17 @@ int pa_map_hits_ex(pa_ctx *ctx, int32_t nhits, const char *model, const char *al
                    pa_maprec *rec, char *base_pool, char *codon_pool, int32_t *unmap_pool, int64_t pool_cols_cap,
                    int64_t unmap_cap);
 
+/* merge_hits() of the reference (lib/assemble.py:889-954), histogram part, as a segmented left fold: chain j merges items
+ * chain_off[j] .. chain_off[j+1]-1 in order (newhit = merge_hits(newhit, hit) repeatedly, lib/assemble.py:995-1766).  Item i
+ * carries the counts of reference columns item_q0[i] .. item_q0[i]+item_ncols[i]-1 as [column][3][32] ints at row item_row[i] of
+ * hist_in (layout of pa_accum.hist) and, in key_in, the insertion rank of each symbol inside the item's own dictionaries.
+ * Per chain (columns 1 .. chain_ncols[j] at row chain_row[j]): hist_out = summed counts; who_out = position in the chain of the
+ * first item with a non-zero count (INT32_MAX = none) and key_out = that item's rank -- together the Python dict insertion
+ * order of the merged hit.  qend / seqids / count / fill_gap bookkeeping stays on the host (phyloaln_b200.mapping). */
+int pa_merge_hists(pa_ctx *ctx, int32_t nchains, const int32_t *chain_off, const int32_t *item_q0, const int32_t *item_ncols,
+                   const int64_t *item_row, const int32_t *hist_in, const int32_t *key_in, const int64_t *chain_row,
+                   const int32_t *chain_ncols, int32_t *hist_out, int32_t *who_out, int32_t *key_out);
+
 /* ---- native target preparation (host only; replaces the body of prepare_target(), lib/aln.py:274-433,
  * and the text iteration of read_fastx(return_iter=True), lib/library.py:157-176).  Files are inflated and
  * parsed in parallel; tagging, sliding-window splitting, exact-duplicate merging and the 10 MB chunk order are

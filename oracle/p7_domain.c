@@ -380,7 +380,7 @@ int p7d_rescore_envelope(const ORC_PROFILE *p, const uint8_t *dsq, int L, int ie
 
 /* ---- multi-domain regions: stochastic traceback ensemble + clustering (A.7) ---- */
 #define P7D_NSAMPLES 200
-#define P7D_MAXSEG 8 /* domain segments kept per sampled trace (further ones are dropped) */
+#define P7D_MAXSEG 16 /* domain segments kept per sampled trace (further ones are dropped) */
 typedef struct { int t, i, j, k, m; } P7D_SEG;
 
 static inline float p7d_rng_uniform(uint64_t *x) { /* xorshift64*, top 24 bits -> [0,1) */

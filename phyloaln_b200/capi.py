@@ -60,7 +60,7 @@ MAPREC_DTYPE = np.dtype(PaMapRec)
 
 EXPORTS = ["pa_abi_version", "pa_create", "pa_destroy", "pa_last_error", "pa_set_opts", "pa_add_hmm", "pa_set_evparam",
            "pa_commit_hmms", "pa_num_hmms", "pa_load_reads", "pa_load_proteins", "pa_num_frames", "pa_get_targets",
-           "pa_search", "pa_get_hits", "pa_get_hit_pp", "pa_hit_pool_bytes", "pa_get_stats", "pa_score_all", "pa_map_hits", "pa_map_hits_ex", "pa_microbench_dpx",
+           "pa_search", "pa_get_hits", "pa_get_hit_pp", "pa_hit_pool_bytes", "pa_get_stats", "pa_score_all", "pa_map_hits", "pa_map_hits_ex", "pa_merge_hists", "pa_microbench_dpx",
            "pa_profiler_range", "pa_msv_item_decode", "pa_hmm_file_parse",
            "pa_ingest_create", "pa_ingest_destroy", "pa_ingest_last_error", "pa_ingest_add_file", "pa_ingest_run", "pa_ingest_start",
            "pa_ingest_wait", "pa_ingest_done", "pa_ingest_emitted", "pa_ingest_num_records", "pa_ingest_views", "pa_ingest_write",
@@ -111,6 +111,7 @@ def load_library():
     L.pa_map_hits.argtypes = [vp, C.c_int32, C.c_char_p, C.c_char_p, vp, C.c_char_p] + [vp] * 10 + [i32, C.c_double, vp, vp, vp, vp, i64, i64]
     L.pa_map_hits_ex.argtypes = ([vp, C.c_int32, C.c_char_p, C.c_char_p, vp, C.c_char_p] + [vp] * 13 +
                                  [C.POINTER(PaMapOpts), C.POINTER(PaAccum), vp, vp, vp, vp, i64, i64])
+    L.pa_merge_hists.argtypes = [vp, C.c_int32] + [vp] * 11
     L.pa_microbench_dpx.argtypes = [vp, i32, C.POINTER(C.c_double)]
     L.pa_profiler_range.argtypes = [i32]
     _lib = L
@@ -128,6 +129,19 @@ class PaError(RuntimeError):
 
 def _ptr(a):
     return None if a is None else a.ctypes.data
+
+
+def prepare_hmm(hmm, require_stats: bool = True):
+    """The arguments of pa_add_hmm for one hmmio.HMM (contiguous float64 arrays, encoded strings), made once per profile."""
+    mat = np.ascontiguousarray(hmm.mat, dtype=np.float64)
+    ins = np.ascontiguousarray(hmm.ins, dtype=np.float64)
+    t = np.ascontiguousarray(hmm.t, dtype=np.float64)
+    compo = None if hmm.compo is None else np.ascontiguousarray(hmm.compo, dtype=np.float64)
+    has = all(k in hmm.stats for k in ("MSV", "VITERBI", "FORWARD"))
+    if require_stats and not has:
+        hmm.evparams()  # raises the descriptive error
+    ev = np.ascontiguousarray(hmm.evparams(), dtype=np.float32) if has else np.array([-10, 0.7, -11, 0.7, -4, 0.7], dtype=np.float32)
+    return (hmm.name.encode(), 0 if hmm.abc == "amino" else 1, hmm.M, mat, ins, t, compo, hmm.consensus().encode(), ev)
 
 
 class Context:
@@ -163,20 +177,11 @@ class Context:
         self._check(self.L.pa_set_opts(self.h, C.byref(o)), "pa_set_opts")
 
     def add_hmm(self, hmm, require_stats: bool = True) -> int:
-        """hmm: phyloaln_b200.hmmio.HMM"""
-        mat = np.ascontiguousarray(hmm.mat, dtype=np.float64)
-        ins = np.ascontiguousarray(hmm.ins, dtype=np.float64)
-        t = np.ascontiguousarray(hmm.t, dtype=np.float64)
-        compo = None if hmm.compo is None else np.ascontiguousarray(hmm.compo, dtype=np.float64)
-        has = all(k in hmm.stats for k in ("MSV", "VITERBI", "FORWARD"))
-        if require_stats and not has:
-            hmm.evparams()  # raises the descriptive error
-        ev = np.ascontiguousarray(hmm.evparams(), dtype=np.float32) if has else np.array(
-            [-10, 0.7, -11, 0.7, -4, 0.7], dtype=np.float32)
-        idx = self._check(self.L.pa_add_hmm(self.h, hmm.name.encode(), 0 if hmm.abc == "amino" else 1, hmm.M, _ptr(mat),
-                                            _ptr(ins), _ptr(t), _ptr(compo), hmm.consensus().encode(), _ptr(ev)),
+        """hmm: phyloaln_b200.hmmio.HMM, or the tuple prepare_hmm() made of it (several contexts share one conversion)"""
+        name, abc, M, mat, ins, t, compo, cons, ev = hmm if isinstance(hmm, tuple) else prepare_hmm(hmm, require_stats)
+        idx = self._check(self.L.pa_add_hmm(self.h, name, abc, M, _ptr(mat), _ptr(ins), _ptr(t), _ptr(compo), cons, _ptr(ev)),
                           "pa_add_hmm")
-        self.names.append(hmm.name)
+        self.names.append(name.decode())
         return idx
 
     def set_evparam(self, idx: int, ev):

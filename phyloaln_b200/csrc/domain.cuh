@@ -20,8 +20,8 @@ namespace pa {
 
 #define PA_MAXREG 64
 #define PA_NSAMPLES 200   // stochastic tracebacks per multi-domain region (HMMER: 200)
-#define PA_MAXSEG 8      // domain segments kept per sampled trace
-#define PA_MAXENV 8      // envelopes kept per multi-domain region
+#define PA_MAXSEG 16     // domain segments per sampled trace; more is an error (status bit 1), never a silent drop
+#define PA_MAXENV 16     // envelopes per multi-domain region; same
 
 struct DomRec {
   uint32_t t;
@@ -284,7 +284,7 @@ __device__ __forceinline__ int md_choose(const float *pr, int n, float u) {
 
 // One stochastic traceback, run by ONE lane. Writes up to PA_MAXSEG segments {i, j, k, m}; returns their number.
 __device__ int md_sample_trace(const FwdTabs &T, const float *FM, const float *FI, const float *FD, const Specials *sf,
-                               const int *ef, int Lr, const XF &xf, int t, int *seg4) {
+                               const int *ef, int Lr, const XF &xf, int t, int *seg4, int *status) {
   const int M = T.M, B = T.B, W = T.W;
   unsigned long long rng = 42ull * 0x9E3779B97F4A7C15ull + (unsigned long long)(t + 1) * 0xBF58476D1CE4E5B9ull;
   int nseg = 0, i = Lr, k = 0;
@@ -366,6 +366,7 @@ __device__ int md_sample_trace(const FwdTabs &T, const float *FM, const float *F
       } break;
       case 'B': {
         if (have_m && nseg < PA_MAXSEG) { seg4[4 * nseg] = seg_i; seg4[4 * nseg + 1] = seg_j; seg4[4 * nseg + 2] = seg_k; seg4[4 * nseg + 3] = seg_m; nseg++; }
+        else if (have_m) atomicOr(status, 2);
         have_m = 0;
         pr[0] = __fmul_rn(sf[i].xN, xf.tNB);
         pr[1] = __fmul_rn(sf[i].xJ, xf.tJB);
@@ -397,7 +398,7 @@ __device__ __forceinline__ bool md_linked(const int *a, const int *b) {  // {t, 
 // start then end. Whole warp. scratch: segraw 4*NS*MAXSEG | segc 5*NS*MAXSEG | lab NS*MAXSEG | nper NS; cnt_i/cnt_j: Lr+2 ints.
 __device__ int resolve_multidomain(const FwdTabs &T, const uint8_t *sub, int Lr, int Lfull, int ireg, float *rows, float *FM,
                                    float *FI, float *FD, Specials *sf, int *ef, int *segscratch, int *cnt_i, int *cnt_j,
-                                   int *envl, int lane) {
+                                   int *envl, int lane, int *status) {
   const XF xf = xf_config(Lfull, 1);
   int Ze;
   float Zm;
@@ -406,7 +407,7 @@ __device__ int resolve_multidomain(const FwdTabs &T, const uint8_t *sub, int Lr,
   int *segraw = segscratch, *segc = segraw + 4 * PA_NSAMPLES * PA_MAXSEG, *lab = segc + 5 * PA_NSAMPLES * PA_MAXSEG,
       *nper = lab + PA_NSAMPLES * PA_MAXSEG;
   for (int t = lane; t < PA_NSAMPLES; t += 32)
-    nper[t] = md_sample_trace(T, FM, FI, FD, sf, ef, Lr, xf, t, segraw + 4 * t * PA_MAXSEG);
+    nper[t] = md_sample_trace(T, FM, FI, FD, sf, ef, Lr, xf, t, segraw + 4 * t * PA_MAXSEG, status);
   __syncwarp();
   int nseg = 0;
   if (lane == 0) {  // compact, trace by trace
@@ -464,6 +465,7 @@ __device__ int resolve_multidomain(const FwdTabs &T, const uint8_t *sub, int Lr,
         }
         if (bj < jmin) bj = arg;
         if (nenv < PA_MAXENV && bj >= bi) { envl[2 * nenv] = bi + ireg - 1; envl[2 * nenv + 1] = bj + ireg - 1; nenv++; }
+        else if (bj >= bi) atomicOr(status, 2);
       }
       for (int a = c; a < nseg; a++)
         if (lab[a] == c) { cnt_i[segc[5 * a + 1]] = 0; cnt_j[segc[5 * a + 2]] = 0; }
@@ -551,6 +553,7 @@ static __global__ void __launch_bounds__(128) domain_kernel(DomArgs a) {
             mx = fmaxf(mx, fminf(aa, bb));
           }
           if (nreg < PA_MAXREG) { reg[3 * nreg] = i; reg[3 * nreg + 1] = j; reg[3 * nreg + 2] = mx >= rt3; nreg++; }
+          else atomicOr(a.status, 2);
           i = -1;
           trig = 0;
         }
@@ -564,7 +567,7 @@ static __global__ void __launch_bounds__(128) domain_kernel(DomArgs a) {
      int nenv = 1;
      if (multi) {
        nenv = resolve_multidomain(T, p + ireg - 1, jreg - ireg + 1, L, ireg, rows, FM, FI, FD, sf, ef, segscratch,
-                                  reinterpret_cast<int *>(ppN), reinterpret_cast<int *>(ppJ), envl, lane);
+                                  reinterpret_cast<int *>(ppN), reinterpret_cast<int *>(ppJ), envl, lane, a.status);
      } else if (lane == 0) { envl[0] = ireg; envl[1] = jreg; }
      __syncwarp();
      for (int en = 0; en < nenv; en++) {

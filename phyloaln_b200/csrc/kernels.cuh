@@ -146,6 +146,12 @@ static __device__ void translate_read_generic(const char *__restrict__ nt, unsig
     if (m == 0) { atomicExch(err, 1); m = 15; }
     return m;
   };
+  // complement of the letter at i as a mask.  'U' is not in Biopython's DNA complement table (Bio.Seq >= 1.80), so
+  // reverse_complement() leaves it in place and it is read as T on the reverse strand too (oracle: orc_revcomp)
+  auto comp_at = [&](int i) -> int {
+    const uint8_t c = (uint8_t)nt[o + i] & 0xDF;
+    return c == 'U' ? 1 : comp_mask(mask_at(i));
+  };
   uint32_t pos = target_base(o, r);
   for (int f = 0; f < nframes; f++) {
     const bool rev = (moltype == 1) ? (f == 1) : (f >= nfwd);
@@ -162,12 +168,12 @@ static __device__ void translate_read_generic(const char *__restrict__ nt, unsig
         if (c < nres) {
           const int p0 = j + step * c;
           if (moltype == 1) {
-            int m = rev ? comp_mask(mask_at(L - 1 - p0)) : mask_at(p0);
+            int m = rev ? comp_at(L - 1 - p0) : mask_at(p0);
             code = dna_code(m);
           } else {
             int m0, m1, m2;
             if (!rev) { m0 = mask_at(p0); m1 = mask_at(p0 + 1); m2 = mask_at(p0 + 2); }
-            else { m0 = comp_mask(mask_at(L - 1 - p0)); m1 = comp_mask(mask_at(L - 2 - p0)); m2 = comp_mask(mask_at(L - 3 - p0)); }
+            else { m0 = comp_at(L - 1 - p0); m1 = comp_at(L - 2 - p0); m2 = comp_at(L - 3 - p0); }
             code = codon_code(m0, m1, m2, tab64);
           }
         }
@@ -197,7 +203,10 @@ static __global__ void __launch_bounds__(256) translate_generic_kernel(const cha
 
 // Exact IUPAC path for one triplet (Biopython rules): forward residue and the residue of the reverse
 // complement.  Kept out of line: it runs for the ~0.3 % of triplets that contain a non-ACGTU letter.
-static __device__ __noinline__ int translate_ambiguous(int m0, int m1, int m2, const uint8_t *tab64) {
+// t0..t2: the s_nt bytes of the three letters (bits 4-7 IUPAC mask; bit 0 set for 'U', whose complement is itself = T)
+static __device__ __noinline__ int translate_ambiguous(int t0, int t1, int t2, const uint8_t *tab64) {
+  const int m0 = t0 >> 4, m1 = t1 >> 4, m2 = t2 >> 4;
+  const int r0 = (t0 & 1) ? 1 : comp_mask(m0), r1 = (t1 & 1) ? 1 : comp_mask(m1), r2 = (t2 & 1) ? 1 : comp_mask(m2);
   auto one = [&](int a0, int a1, int a2) -> int {
     uint32_t seen = 0;
     int nstop = 0, ntot = 0;
@@ -220,7 +229,7 @@ static __device__ __noinline__ int translate_ambiguous(int m0, int m1, int m2, c
     if ((seen & ~((1u << 7) | (1u << 9))) == 0) return 22;   // I,L -> J
     return 26;
   };
-  return one(m0, m1, m2) | (one(comp_mask(m2), comp_mask(m1), comp_mask(m0)) << 8);
+  return one(m0, m1, m2) | (one(r2, r1, r0) << 8);
 }
 
 // Translation (reference lib/aln.py:233-259), HBM-bound design.  One warp per read:
@@ -249,11 +258,13 @@ static __global__ void __launch_bounds__(256) translate_kernel(const char *__res
     s_tabF[f] = tab64[m(c0) * 16 + m(c1) * 4 + m(c2)];
     s_tabR[f] = tab64[m(c2 ^ 2) * 16 + m(c1 ^ 2) * 4 + m(c0 ^ 2)];
   }
-  {  // per character: bits 0-1 code, bit 2 = not A/C/G/T/U, bit 3 = not a nucleotide letter at all, bits 4-7 IUPAC mask
+  {  // per character: bits 0-1 code (A/C/G/T only), bit 2 = not A/C/G/T (exact path), bit 3 = not a nucleotide letter at all,
+     // bits 4-7 IUPAC mask; 'U' takes the exact path with bit 0 as its marker (forward: T; complement: itself, see above)
     const int c = threadIdx.x;
     const int mk = nt_mask((uint8_t)c);
-    const bool plain = mk == 1 || mk == 2 || mk == 4 || mk == 8;
-    s_nt[c] = (uint8_t)(((c >> 1) & 3) | (plain ? 0 : 4) | (mk == 0 ? 8 : 0) | ((mk ? mk : 15) << 4));
+    const bool isU = (c & 0xDF) == 'U';
+    const bool plain = (mk == 1 || mk == 2 || mk == 4 || mk == 8) && !isU;
+    s_nt[c] = (uint8_t)((plain ? ((c >> 1) & 3) : (isU ? 1 : 0)) | (plain ? 0 : 4) | (mk == 0 ? 8 : 0) | ((mk ? mk : 15) << 4));
   }
   __syncthreads();
   const int lane = threadIdx.x & 31, wib = __shfl_sync(PA_FULL, (int)(threadIdx.x >> 5), 0), wpb = blockDim.x >> 5;
@@ -298,7 +309,7 @@ static __global__ void __launch_bounds__(256) translate_kernel(const char *__res
           aaR = s_tabR[f];
         } else {
           if ((cur | c1 | c2) & 8) atomicExch(err, 1);
-          const int both = translate_ambiguous(cur >> 4, c1 >> 4, c2 >> 4, s_tab);
+          const int both = translate_ambiguous(cur, c1, c2, s_tab);
           aaF = both & 0xff;
           aaR = both >> 8;
         }

@@ -152,3 +152,64 @@ extern "C" int pa_map_hits(pa_ctx *ctx, int32_t nhits, const char *model, const 
                         comp_off, ncols_ref, nullptr, nullptr, nullptr, &o, nullptr, rec, base_pool, codon_pool, unmap_pool,
                         pool_cols_cap, unmap_cap);
 }
+
+// merge_hits() histograms as a segmented fold on the GPU (see merge_kernel, mapping.cuh)
+extern "C" int pa_merge_hists(pa_ctx *ctx, int32_t nchains, const int32_t *chain_off, const int32_t *item_q0, const int32_t *item_ncols,
+                              const int64_t *item_row, const int32_t *hist_in, const int32_t *key_in, const int64_t *chain_row,
+                              const int32_t *chain_ncols, int32_t *hist_out, int32_t *who_out, int32_t *key_out) {
+  if (!ctx) return -1;
+  if (nchains <= 0) return 0;
+  cudaSetDevice(pa_ctx_device(ctx));
+  cudaStream_t s = pa_ctx_stream(ctx);
+  const int nitems = chain_off[nchains];
+  long long in_rows = 0, out_rows = 0;
+  int maxcols = 1;
+  for (int i = 0; i < nitems; i++) {
+    if (item_ncols[i] < 0 || item_row[i] < 0) { pa_ctx_set_error(ctx, "pa_merge_hists: bad item table"); return -2; }
+    in_rows = std::max<long long>(in_rows, item_row[i] + item_ncols[i]);
+  }
+  for (int j = 0; j < nchains; j++) {
+    if (chain_off[j + 1] < chain_off[j] || chain_ncols[j] < 0) { pa_ctx_set_error(ctx, "pa_merge_hists: bad chain table"); return -2; }
+    out_rows = std::max<long long>(out_rows, chain_row[j] + chain_ncols[j]);
+    maxcols = std::max(maxcols, (int)chain_ncols[j]);
+  }
+  DevPool pool;
+#define MCK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) { pa_ctx_set_error(ctx, std::string("pa_merge_hists: ") + cudaGetErrorString(e_)); return -1; } \
+  } while (0)
+  int *d_coff, *d_q0, *d_nc, *d_cnc, *d_hin, *d_kin, *d_hout, *d_who, *d_kout;
+  long long *d_irow, *d_crow;
+  const size_t NI = (size_t)nitems, NC = (size_t)nchains, CI = (size_t)in_rows * 96, CO = (size_t)out_rows * 96;
+  MCK(pool.alloc(&d_coff, NC + 1)); MCK(pool.alloc(&d_q0, NI)); MCK(pool.alloc(&d_nc, NI)); MCK(pool.alloc(&d_irow, NI));
+  MCK(pool.alloc(&d_crow, NC)); MCK(pool.alloc(&d_cnc, NC)); MCK(pool.alloc(&d_hin, CI)); MCK(pool.alloc(&d_kin, CI));
+  MCK(pool.alloc(&d_hout, CO)); MCK(pool.alloc(&d_who, CO)); MCK(pool.alloc(&d_kout, CO));
+  MCK(cudaMemcpyAsync(d_coff, chain_off, 4 * (NC + 1), cudaMemcpyHostToDevice, s));
+  MCK(cudaMemcpyAsync(d_q0, item_q0, 4 * NI, cudaMemcpyHostToDevice, s));
+  MCK(cudaMemcpyAsync(d_nc, item_ncols, 4 * NI, cudaMemcpyHostToDevice, s));
+  MCK(cudaMemcpyAsync(d_irow, item_row, 8 * NI, cudaMemcpyHostToDevice, s));
+  MCK(cudaMemcpyAsync(d_crow, chain_row, 8 * NC, cudaMemcpyHostToDevice, s));
+  MCK(cudaMemcpyAsync(d_cnc, chain_ncols, 4 * NC, cudaMemcpyHostToDevice, s));
+  MCK(cudaMemcpyAsync(d_hin, hist_in, 4 * CI, cudaMemcpyHostToDevice, s));
+  MCK(cudaMemcpyAsync(d_kin, key_in, 4 * CI, cudaMemcpyHostToDevice, s));
+  MergeArgs m;
+  m.nchains = nchains; m.chain_off = d_coff; m.item_q0 = d_q0; m.item_ncols = d_nc; m.item_row = d_irow; m.chain_row = d_crow;
+  m.chain_ncols = d_cnc; m.hist_in = d_hin; m.key_in = d_kin; m.hist_out = d_hout; m.who_out = d_who; m.key_out = d_kout;
+  const unsigned gx = (unsigned)std::min<long long>(((long long)maxcols * 96 + 255) / 256, 1024);
+  for (int j0 = 0; j0 < nchains; j0 += 65535) {   // gridDim.y limit
+    MergeArgs mm = m;
+    const int nj = std::min(65535, nchains - j0);
+    mm.chain_off += j0; mm.chain_row += j0; mm.chain_ncols += j0;
+    // chain_off values stay absolute item indices; `who` is relative to the chain's first item
+    merge_kernel<<<dim3(gx, (unsigned)nj), 256, 0, s>>>(mm);
+    pa_ctx_count_launches(ctx, 1);
+    MCK(cudaGetLastError());
+  }
+  MCK(cudaMemcpyAsync(hist_out, d_hout, 4 * CO, cudaMemcpyDeviceToHost, s));
+  MCK(cudaMemcpyAsync(who_out, d_who, 4 * CO, cudaMemcpyDeviceToHost, s));
+  MCK(cudaMemcpyAsync(key_out, d_kout, 4 * CO, cudaMemcpyDeviceToHost, s));
+  MCK(cudaStreamSynchronize(s));
+#undef MCK
+  return 0;
+}

@@ -320,4 +320,40 @@ __global__ void accum_kernel(AccumArgs a) {
   }
 }
 
+// ---- merge_hits (lib/assemble.py:889-954), histogram part: a segmented left fold ----
+// Chain j folds items chain_off[j] .. chain_off[j+1]-1 in order (newhit = merge_hits(newhit, hit) repeatedly).  Item i holds the
+// counts of its reference columns item_q0[i] .. item_q0[i] + item_ncols[i] - 1 as [column][3][32] at row item_row[i], with
+// key_in (same shape) = the insertion rank of every symbol inside the item's own dictionaries.  Per chain the kernel writes the
+// summed counts over columns 1 .. chain_ncols[j] plus, for the dict insertion order of the result, the first item that brought
+// each symbol (position inside the chain) and that item's own rank for it.
+struct MergeArgs {
+  int nchains;
+  const int *chain_off, *item_q0, *item_ncols;
+  const long long *item_row, *chain_row;
+  const int *chain_ncols;
+  const int *hist_in, *key_in;
+  int *hist_out, *who_out, *key_out;
+};
+
+__global__ void merge_kernel(MergeArgs a) {
+  const int j = blockIdx.y;
+  const int cells = a.chain_ncols[j] * 96;
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < cells; c += gridDim.x * blockDim.x) {
+    const int col = c / 96 + 1, rest = c % 96;
+    int sum = 0, who = INT_MAX, key = INT_MAX;
+    for (int i = a.chain_off[j]; i < a.chain_off[j + 1]; i++) {
+      const int rel = col - a.item_q0[i];
+      if (rel < 0 || rel >= a.item_ncols[i]) continue;
+      const size_t cell = ((size_t)a.item_row[i] + rel) * 96 + rest;
+      const int v = a.hist_in[cell];
+      if (v != 0 && who == INT_MAX) { who = i - a.chain_off[j]; key = a.key_in[cell]; }
+      sum += v;
+    }
+    const size_t o = (size_t)a.chain_row[j] * 96 + c;
+    a.hist_out[o] = sum;
+    a.who_out[o] = who;
+    a.key_out[o] = key;
+  }
+}
+
 }  // namespace pa

@@ -158,8 +158,10 @@ def hmmsearch_step(outdir: str, groups, mol_type: str = "prot", gencode: int = 1
         return counts
     t0 = time.perf_counter()
     hmms, kept = [], []
-    for g in todo:
-        h = read_hmm(os.path.join(outdir, "ref_hmm", g + ".hmm"))
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(min(8, os.cpu_count() or 1)) as ex:     # the native reader releases the GIL
+        parsed = list(ex.map(lambda g: read_hmm(os.path.join(outdir, "ref_hmm", g + ".hmm")), todo))
+    for g, h in zip(todo, parsed):
         if h.M > MAX_M:
             hmmsearch_step.skipped.append(g)
             continue
@@ -195,7 +197,7 @@ def hmmsearch_step(outdir: str, groups, mol_type: str = "prot", gencode: int = 1
         src = ArraySource(nt, off)
     tm["load_reads_s"] = time.perf_counter() - t0
     t0 = time.perf_counter()
-    searcher = B200Searcher(hmms, devices=devices, options=opts)
+    searcher = B200Searcher(hmms, devices=devices, options=opts, defer=True)   # contexts come up inside the search workers
     tm["upload_profiles_s"] = time.perf_counter() - t0
     t0 = time.perf_counter()
     try:

@@ -265,3 +265,132 @@ def ref_score_tables(refseqs: dict, outgroup=(), ingroup=(), sep: str = ".", unk
     for i in range(ncols):
         out_tab[len(out_ids), i] = int(totals[i]) * aver
     return comp, out_ids + ["PhyloAln_Alt"], out_tab
+
+
+# ---------------------------------------------------------------------------------------------
+# merge_hits(): folding hits into contigs (lib/assemble.py:889-954; callers :995, :1074, :1157, :1198, :1214, :1580, :1766)
+# ---------------------------------------------------------------------------------------------
+def _absorb_intervals(have: list, new: list, codon: bool):
+    """--ref_split_len bookkeeping of merge_hits (:897-914): a fragment that continues an interval of the same strand (and,
+    with codons, the same reading frame) extends it, anything else is appended."""
+    for s, e, strand in new:
+        for iv in have:
+            if iv[2] != strand or (codon and (s - iv[0]) % 3 != 0):
+                continue
+            if strand == "+":
+                if iv[0] <= s <= iv[1] + 1 and e >= iv[1]:
+                    iv[1] = e
+                    break
+            elif e <= iv[1] and e + 1 >= iv[0] and s <= iv[0]:
+                iv[0] = s
+                break
+        else:
+            have.append([s, e, strand])
+
+
+def merge_hits_chains(ctx: capi.Context, chains, mol_type: str = "dna", split_len=None, fill_gap=False):
+    """Left fold of merge_hits() over every chain: chains[j] = [item, item, ...] in merge order, an item being a dict
+    {"qstart", "qend", "seq_comp", "seqids": {id: [[start, end, strand], ...]}, "count": {id: 1} | {"too much": n}} with
+    seq_comp in the reference's structure ({col: {nt: n}} for mol_type 'dna', {col: {1: {..}, 2: {..}, 3: {..}}} otherwise).
+
+    The per-column histograms -- the bulk of the data -- are summed on the GPU (pa_merge_hists: segmented fold that also
+    returns which item brought each symbol first, i.e. the insertion order of the reference's dictionaries); qend, the
+    target-sequence intervals, the counts and the fill_gap columns are host bookkeeping.  Returns one merged item per chain,
+    equal to the reference's result including dict order."""
+    codon = mol_type != "dna"
+    K = 3 if codon else 1
+    fill_sym = comp_symbol(fill_gap) if fill_gap else None
+    # ---- flatten: items (plus one synthetic gap item after every hit that opens a gap) -> dense [column][3][32] blocks
+    chain_off, q0s, ncs, blocks, metas = [0], [], [], [], []
+    for chain in chains:
+        if not chain:
+            raise ValueError("empty chain")
+        flat, end = [], None
+        for n, it in enumerate(chain):
+            flat.append(it["seq_comp"])
+            if n and fill_gap and it["qstart"] - end > 1:
+                cell = {fill_gap: 1}
+                flat.append({c: ({1: dict(cell), 2: dict(cell), 3: dict(cell)} if codon else dict(cell)) for c in range(end + 1, it["qstart"])})
+            end = it["qend"] if n == 0 else max(end, it["qend"])
+        metas.append(flat)
+        for comp in flat:
+            cols = list(comp)
+            lo, hi = (min(cols), max(cols)) if cols else (1, 0)
+            q0s.append(lo)
+            ncs.append(hi - lo + 1)
+            blocks.append(comp)
+        chain_off.append(len(q0s))
+    item_row = np.zeros(len(q0s) + 1, np.int64)
+    item_row[1:] = np.cumsum(ncs)
+    hist_in = np.zeros((max(int(item_row[-1]), 1), 3, 32), np.int32)
+    key_in = np.zeros_like(hist_in)
+    for i, comp in enumerate(blocks):
+        for c, d in comp.items():
+            row = int(item_row[i]) + c - q0s[i]
+            for k in range(K):
+                for rank, (ch, cnt) in enumerate((d[k + 1] if codon else d).items()):
+                    s = comp_symbol(ch)
+                    if s >= 28:
+                        raise ValueError(f"unexpected symbol {ch!r} in seq_comp")
+                    hist_in[row, k, s] += cnt
+                    key_in[row, k, s] = rank
+    chain_nc = np.array([max((q0s[i] + ncs[i] - 1 for i in range(chain_off[j], chain_off[j + 1])), default=0) for j in range(len(chains))],
+                        dtype=np.int32)
+    chain_nc = np.maximum(chain_nc, 0)
+    chain_row = np.zeros(len(chains) + 1, np.int64)
+    chain_row[1:] = np.cumsum(chain_nc)
+    hist = np.zeros((max(int(chain_row[-1]), 1), 3, 32), np.int32)
+    who, key = np.zeros_like(hist), np.zeros_like(hist)
+    P = capi._ptr
+    coff_a, q0_a, nc_a = (np.ascontiguousarray(x, dtype=np.int32) for x in (chain_off, q0s, ncs))   # keep alive across the call
+    rc = ctx.L.pa_merge_hists(ctx.h, len(chains), P(coff_a), P(q0_a), P(nc_a), P(item_row), P(hist_in), P(key_in), P(chain_row), P(chain_nc),
+                              P(hist), P(who), P(key))
+    ctx._check(rc, "pa_merge_hists")
+    # ---- rebuild the merged items
+    out = []
+    for j, chain in enumerate(chains):
+        first = chain[0]
+        new = {"qstart": first["qstart"], "qend": max(it["qend"] for it in chain)}
+        # column order: the first item's columns, then every later item's new columns in its own order (gap columns after the hit)
+        order = {}
+        for comp in metas[j]:
+            for c in comp:
+                order.setdefault(c, None)
+        H, W, Kk = (x[int(chain_row[j]):int(chain_row[j + 1])] for x in (hist, who, key))
+        seq_comp = {}
+        for c in order:
+            def one(k):
+                syms = np.flatnonzero(W[c - 1, k] != INT_MAX)
+                return {SYMS[s]: int(H[c - 1, k, s]) for s in sorted(syms, key=lambda s: (int(W[c - 1, k, s]), int(Kk[c - 1, k, s])))}
+            seq_comp[c] = {1: one(0), 2: one(1), 3: one(2)} if codon else one(0)
+        new["seq_comp"] = seq_comp
+        # target-sequence bookkeeping (:893-935, :941-949)
+        seqids = {k: [list(iv) for iv in v] for k, v in first["seqids"].items()}
+        count = dict(first["count"])
+        end = first["qend"]
+        for it in chain[1:]:
+            last_id = None
+            if "too much" not in count:
+                for sid, ivs in it["seqids"].items():
+                    last_id = sid
+                    have = seqids.setdefault(sid, [])
+                    if split_len:
+                        _absorb_intervals(have, ivs, codon)
+                    else:
+                        have.extend(list(iv) for iv in ivs)
+                    count[sid] = 1
+            else:
+                count["too much"] += it["count"]["too much"]
+            if fill_gap and it["qstart"] - end > 1 and "too much" not in count:
+                ivs = seqids[last_id]     # the reference looks at the last id of the merged-in hit (:942)
+                if ivs[-1][2] == "+":
+                    if ivs[-1][0] - ivs[-2][1] <= 1:
+                        ivs[-2][1] = ivs[-1][1]
+                        ivs.pop()
+                elif ivs[-2][0] - ivs[-1][1] <= 1:
+                    ivs[-2][0] = ivs[-1][0]
+                    ivs.pop()
+            end = max(end, it["qend"])
+        new["seqids"], new["count"] = seqids, count
+        out.append(new)
+    return out

@@ -372,28 +372,27 @@ def valid_reads_mask(nt: np.ndarray, off: np.ndarray) -> np.ndarray:
 class B200Searcher:
     """All profiles x one read set on one or more B200s (one context per GPU, reads sharded by chunk)."""
 
-    def __init__(self, hmms, devices=(0,), options: SearchOptions | None = None):
+    def __init__(self, hmms, devices=(0,), options: SearchOptions | None = None, defer: bool = False):
+        """defer=True: the per-GPU contexts (CUDA context, profile configuration, table upload) are created by the worker
+        threads of the first search, each GPU starting on the reads as soon as ITS context is ready."""
         self.opts = options or SearchOptions()
         self.hmms = [h if isinstance(h, HMM) else read_hmm(h) for h in hmms]
-        devices = list(devices)
-        self.ctxs = [None] * len(devices)
+        self.devices = list(devices)
+        self.ctxs = [None] * len(self.devices)
+        self._prepared = None
+        if defer:
+            return
         errors = []
 
-        def setup(k, d):     # one thread per GPU: context creation, profile configuration and upload run side by side
+        def setup(k):
             try:
-                c = capi.Context(d)
-                self.ctxs[k] = c
-                c.set_opts(F1=self.opts.F1, F2=self.opts.F2, F3=self.opts.F3, do_bias=not self.opts.nobias,
-                           do_null2=not self.opts.nonull2, do_max=self.opts.max)
-                for h in self.hmms:
-                    c.add_hmm(h)
-                c.commit()
+                self._setup(k)
             except Exception as e:
                 errors.append(e)
-        if len(devices) == 1:
-            setup(0, devices[0])
-        else:
-            th = [threading.Thread(target=setup, args=(k, d)) for k, d in enumerate(devices)]
+        if len(self.devices) == 1:
+            setup(0)
+        else:     # one thread per GPU: context creation, profile configuration and upload run side by side
+            th = [threading.Thread(target=setup, args=(k,)) for k in range(len(self.devices))]
             for t in th:
                 t.start()
             for t in th:
@@ -401,6 +400,21 @@ class B200Searcher:
         if errors:
             self.close()
             raise errors[0]
+
+    def _setup(self, k: int):
+        """Create context k (idempotent)."""
+        if self.ctxs[k] is not None:
+            return self.ctxs[k]
+        if self._prepared is None:      # benign race: two threads may both convert, the results are equal
+            self._prepared = [capi.prepare_hmm(h) for h in self.hmms]
+        c = capi.Context(self.devices[k])
+        self.ctxs[k] = c
+        c.set_opts(F1=self.opts.F1, F2=self.opts.F2, F3=self.opts.F3, do_bias=not self.opts.nobias,
+                   do_null2=not self.opts.nonull2, do_max=self.opts.max)
+        for p in self._prepared:
+            c.add_hmm(p)
+        c.commit()
+        return c
 
     def close(self):
         for c in self.ctxs:
@@ -492,8 +506,9 @@ class B200Searcher:
                 hits["target"] = ((a + keep[hits["target"] // nf]) * nf + hits["target"] % nf).astype(hits["target"].dtype)
             out.append((a, hits, model, aligned, pp))
 
-        def work(ctx):
+        def work(k):
             try:
+                ctx = self._setup(k)      # deferred contexts: this GPU starts as soon as its own context is ready
                 while True:
                     r = next_range()
                     if r is None:
@@ -505,7 +520,7 @@ class B200Searcher:
             except Exception as e:  # surfaced after join
                 errors.append(e)
 
-        threads = [threading.Thread(target=work, args=(c,)) for c in self.ctxs]
+        threads = [threading.Thread(target=work, args=(k,)) for k in range(len(self.ctxs))]
         for t in threads:
             t.start()
         for t in threads:

@@ -123,3 +123,28 @@ def test_too_wide_profile_is_rejected(gpu_ctx_factory):
     with pytest.raises(PaError, match="1..8192"):
         ctx.add_hmm(h, require_stats=False)
     ctx.close()
+
+
+def test_documented_capacity_limits_are_loud_errors(gpu_ctx_factory):
+    """65,535 profiles per context (Pass records carry a 16-bit profile index) and 65,535 distinct target lengths per chunk
+    (16-bit length-table index): one more is an error with a message, -2 (bad argument) and -3 (split the chunk) respectively."""
+    import ctypes as C
+    from phyloaln_b200 import capi, synth
+    from phyloaln_b200.capi import PaError
+    ctx = gpu_ctx_factory()
+    tiny = capi.prepare_hmm(synth.random_hmm("t", 1, np.random.default_rng(2)), require_stats=False)
+    for _ in range(65535):
+        ctx.add_hmm(tiny)
+    with pytest.raises(PaError, match=r"\(-2\).*too many profiles"):
+        ctx.add_hmm(tiny)
+    ctx.close()
+    ctx = gpu_ctx_factory()
+    lens = np.arange(65536, dtype=np.uint64)                      # 65,536 distinct lengths, 2.1 GB of residues
+    off = np.zeros(len(lens) + 1, dtype=np.uint64)
+    off[1:] = np.cumsum(lens)
+    aa = np.full(int(off[-1]), ord("A"), dtype=np.uint8)
+    rc = ctx.L.pa_load_proteins(ctx.h, aa.ctypes.data, off.ctypes.data, len(lens), 0)
+    assert rc == -3 and b"distinct target lengths" in ctx.L.pa_last_error(ctx.h)
+    rc = ctx.L.pa_load_proteins(ctx.h, aa.ctypes.data, off.ctypes.data, len(lens) - 1, 0)   # 65,535 distinct lengths fit
+    assert rc == len(lens) - 1
+    ctx.close()
