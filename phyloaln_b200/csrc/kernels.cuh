@@ -206,7 +206,8 @@ static __global__ void __launch_bounds__(256) translate_generic_kernel(const cha
 // t0..t2: the s_nt bytes of the three letters (bits 4-7 IUPAC mask; bit 0 set for 'U', whose complement is itself = T)
 static __device__ __noinline__ int translate_ambiguous(int t0, int t1, int t2, const uint8_t *tab64) {
   const int m0 = t0 >> 4, m1 = t1 >> 4, m2 = t2 >> 4;
-  const int r0 = (t0 & 1) ? 1 : comp_mask(m0), r1 = (t1 & 1) ? 1 : comp_mask(m1), r2 = (t2 & 1) ? 1 : comp_mask(m2);
+  // 'U' = exact-path flag (bit 2) + marker (bit 0); bit 0 alone is part of the 2-bit code of a plain letter
+  const int r0 = (t0 & 5) == 5 ? 1 : comp_mask(m0), r1 = (t1 & 5) == 5 ? 1 : comp_mask(m1), r2 = (t2 & 5) == 5 ? 1 : comp_mask(m2);
   auto one = [&](int a0, int a1, int a2) -> int {
     uint32_t seen = 0;
     int nstop = 0, ntot = 0;
