@@ -134,6 +134,8 @@ int pa_add_hmm(pa_ctx *ctx, const char *name, int abc, int M, const double *mat,
                const double *t, const double *compo, const char *cons, const float *evparam);
 int pa_set_evparam(pa_ctx *ctx, int hmm, const float *evparam);
 int pa_commit_hmms(pa_ctx *ctx);
+/* the same profile set on n GPUs: profiles (and options) of ctxs[0] are configured once and uploaded to every context */
+int pa_commit_hmms_multi(pa_ctx **ctxs, int n);
 int pa_num_hmms(pa_ctx *ctx);
 
 /* Targets. nt: concatenated ASCII nucleotides, off[nreads+1] byte offsets (HOST memory).

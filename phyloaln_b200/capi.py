@@ -59,7 +59,7 @@ HIT_DTYPE = np.dtype(PaHit)
 MAPREC_DTYPE = np.dtype(PaMapRec)
 
 EXPORTS = ["pa_abi_version", "pa_create", "pa_destroy", "pa_last_error", "pa_set_opts", "pa_add_hmm", "pa_set_evparam",
-           "pa_commit_hmms", "pa_num_hmms", "pa_load_reads", "pa_load_proteins", "pa_num_frames", "pa_get_targets",
+           "pa_commit_hmms", "pa_commit_hmms_multi", "pa_num_hmms", "pa_load_reads", "pa_load_proteins", "pa_num_frames", "pa_get_targets",
            "pa_search", "pa_get_hits", "pa_get_hit_pp", "pa_hit_pool_bytes", "pa_get_stats", "pa_score_all", "pa_map_hits", "pa_map_hits_ex", "pa_merge_hists", "pa_microbench_dpx",
            "pa_profiler_range", "pa_msv_item_decode", "pa_hmm_file_parse",
            "pa_ingest_create", "pa_ingest_destroy", "pa_ingest_last_error", "pa_ingest_add_file", "pa_ingest_run", "pa_ingest_start",
@@ -90,6 +90,7 @@ def load_library():
     L.pa_add_hmm.argtypes = [vp, C.c_char_p, i32, i32, vp, vp, vp, vp, C.c_char_p, vp]
     L.pa_set_evparam.argtypes = [vp, i32, vp]
     L.pa_commit_hmms.argtypes = [vp]
+    L.pa_commit_hmms_multi.argtypes = [vp, i32]
     L.pa_num_hmms.argtypes = [vp]
     L.pa_load_reads.restype = i64
     L.pa_load_reads.argtypes = [vp, vp, vp, u32, i32, i32, i32, i32]
@@ -129,6 +130,15 @@ class PaError(RuntimeError):
 
 def _ptr(a):
     return None if a is None else a.ctypes.data
+
+
+def commit_multi(ctxs) -> None:
+    """Commit the profiles added to ctxs[0] on every context of the list (configured and laid out once, uploaded to each GPU)."""
+    arr = (C.c_void_p * len(ctxs))(*[c.h for c in ctxs])
+    rc = ctxs[0].L.pa_commit_hmms_multi(arr, len(ctxs))
+    ctxs[0]._check(rc, "pa_commit_hmms_multi")
+    for c in ctxs[1:]:
+        c.names = list(ctxs[0].names)
 
 
 def prepare_hmm(hmm, require_stats: bool = True):

@@ -80,6 +80,8 @@ struct pa_ctx {
   DevBuf<DevHmm> d_hmms;
   DevBuf<uint32_t> d_msv, d_msvh;
   int msv_impl = 0;  // 0: TMEM kernel where the table fits (default), 1: shared-memory kernel everywhere (PA_MSV_IMPL=smem)
+  bool ftok = false; // the alphabet's table fits TMEM at 26 words per row (DNA): all-TMEM rows for Q 17..26, 1,664-cell packs, all-TMEM wide tiles
+  int pack_q = 16;   // words per lane of a pack (16, or 26 with ftok)
   DevBuf<int> d_vit;
   DevBuf<uint32_t> d_v16;   // packed tables of vit16_kernel
   DevBuf<uint8_t> d_need;   // per sorted Viterbi input: must the exact kernel run?
@@ -283,24 +285,31 @@ static inline uint16_t h16_exact(int v) {
   return (uint16_t)((sign << 15) | (e << 10) | mant);
 }
 
+static inline bool msv_fullt(const pa_ctx *ctx, int Q) { return ctx->ftok && Q > 16 && Q <= PA_TMEM_FULLQ; }
 static inline bool msv_use_tmem(const pa_ctx *ctx, int Q, int nrows) {
-  return ctx->msv_impl == 0 && Q <= PA_TMEM_MAXQ && msv_tmem_cols_needed(Q, nrows) <= 512;
+  return ctx->msv_impl == 0 && Q <= PA_TMEM_MAXQ && msv_tmem_cols_needed(Q, nrows, msv_fullt(ctx, Q)) <= 512;
 }
 
-extern "C" int pa_commit_hmms(pa_ctx *ctx) {
-  if (!ctx) return -1;
-  cudaSetDevice(ctx->device);
+// Host images of every per-profile device table (built once per profile set, uploaded to one or several GPUs)
+struct HostTables {
+  std::vector<uint32_t> msv, msvh, v16;
+  std::vector<int> vit, packmem, lists_rest, lists_all, lists_w;
+  std::vector<float> fwd;
+};
+
+static int build_tables(pa_ctx *ctx, HostTables &T) {
   const int nh = (int)ctx->hmms.size();
   if (nh == 0) { ctx->err = "no profiles"; return -2; }
-  std::vector<uint32_t> msv, msvh;
-  std::vector<int> vit;
-  std::vector<uint32_t> v16;
-  std::vector<float> fwd;
+  std::vector<uint32_t> &msv = T.msv, &msvh = T.msvh, &v16 = T.v16;
+  std::vector<int> &vit = T.vit;
+  std::vector<float> &fwd = T.fwd;
   ctx->h_dev.assign(nh, DevHmm{});
   ctx->maxB = 1;
   ctx->maxM = 1;
   std::map<int, std::vector<int>> byQ, byW;
   ctx->maxQ_wide = 0;
+  ctx->ftok = ctx->msv_impl == 0 && getenv("PA_MSV_NOFULLT") == nullptr && msv_tmem_full_ok(PA_TMEM_FULLQ, ctx->hmms[0].Kp);
+  ctx->pack_q = ctx->ftok ? PA_TMEM_FULLQ : 16;
   const bool maxmode = ctx->opts.do_max != 0;
   for (int h = 0; h < nh; h++) {
     const HostProfile &hp = ctx->hmms[h];
@@ -313,8 +322,9 @@ extern "C" int pa_commit_hmms(pa_ctx *ctx) {
     d.Q = M / 64 + 1;  // the last striped cell must be padding (see msv_kernel)
     d.B = (M + 31) / 32;
     const bool wide = d.Q > 32;  // wide.cuh: model-tiled MSV, multi-warp Viterbi, run-time-B Forward
-    d.nT = wide ? (d.Q + 31) / 32 : 0;
-    const int QW = wide ? (d.Q + d.nT - 1) / d.nT : 0;  // words per lane of one MSV tile, 17..32
+    const int tileQ = ctx->ftok ? PA_TMEM_FULLQ : 32;   // widest tile: all-TMEM rows for small alphabets, hybrid otherwise
+    d.nT = wide ? (d.Q + tileQ - 1) / tileQ : 0;
+    const int QW = wide ? (d.Q + d.nT - 1) / d.nT : 0;  // words per lane of one MSV tile, 17..32 (17..26 all-TMEM)
     d.NWv = wide ? (M <= 4096 ? 4 : 8) : 1;
     d.NW16 = wide ? (M <= 4096 ? 2 : 4) : 1;
     ctx->maxB = std::max(ctx->maxB, d.B);
@@ -355,8 +365,8 @@ extern "C" int pa_commit_hmms(pa_ctx *ctx) {
     d.msvh_off = msvh.size();
     if (wide) {
       // nT tiles of 64*QW cells, each laid out like a profile with Q = QW: tile m holds model cells m*64*QW + (2*lane + hf)*QW + q
-      if (msv_tmem_cols_needed(QW, Kp) > 512) { ctx->err = "alphabet too large for the tiled MSV kernel"; return -2; }
-      const int QT = 16, QS = QW - QT;
+      if (msv_tmem_cols_needed(QW, Kp, ctx->ftok) > 512) { ctx->err = "alphabet too large for the tiled MSV kernel"; return -2; }
+      const int QT = msv_tmem_qt(QW, ctx->ftok), QS = QW - QT;
       const size_t tilew = (size_t)Kp * QW * 32;
       msvh.resize(msvh.size() + tilew * d.nT, 0);
       for (int m = 0; m < d.nT; m++) {
@@ -375,7 +385,7 @@ extern "C" int pa_commit_hmms(pa_ctx *ctx) {
             }
       }
     } else if (msv_use_tmem(ctx, Q, Kp)) {
-      const int QT = msv_tmem_qt(Q), QS = Q - QT;
+      const int QT = msv_tmem_qt(Q, msv_fullt(ctx, Q)), QS = Q - QT;
       msvh.resize(msvh.size() + (size_t)Kp * roww, 0);
       uint32_t *tpart = msvh.data() + d.msvh_off, *spart = tpart + (size_t)Kp * QT * 32;
       for (int x = 0; x < Kp; x++)
@@ -500,20 +510,21 @@ extern "C" int pa_commit_hmms(pa_ctx *ctx) {
     }
   }
   // ---- packs of narrow profiles for msv_pack_kernel (first-fit decreasing into 64 half-lanes of 16 cells)
-  std::vector<int> packmem;
+  std::vector<int> &packmem = T.packmem;
   std::vector<char> packed(nh, 0);
   ctx->h_packs.clear();
   if (ctx->msv_impl == 0 && getenv("PA_MSV_NOPACK") == nullptr) {
     const int Kp0 = ctx->hmms[0].Kp;
-    if (msv_tmem_cols_needed(16, Kp0) <= 512) {
+    const int QP = ctx->pack_q;   // cells per half-lane = words per lane of the packed model
+    if (msv_tmem_cols_needed(QP, Kp0, ctx->ftok) <= 512) {
       std::vector<int> cand;
       for (int h = 0; h < nh; h++)
-        if (ctx->hmms[h].M / 16 + 1 <= 64) cand.push_back(h);
+        if (ctx->hmms[h].M / QP + 1 <= 64) cand.push_back(h);
       std::stable_sort(cand.begin(), cand.end(), [&](int x, int y) { return ctx->hmms[x].M > ctx->hmms[y].M; });
       std::vector<std::vector<int>> bins;
       std::vector<int> fill;
       for (int h : cand) {
-        const int n = ctx->hmms[h].M / 16 + 1;
+        const int n = ctx->hmms[h].M / QP + 1;
         size_t b = 0;
         while (b < bins.size() && fill[b] + n > 64) b++;
         if (b == bins.size()) { bins.emplace_back(); fill.push_back(0); }
@@ -527,12 +538,12 @@ extern "C" int pa_commit_hmms(pa_ctx *ctx) {
         pk.mem_off = (int)packmem.size();
         while (msvh.size() % 4) msvh.push_back(0);
         pk.msvh_off = msvh.size();
-        msvh.resize(msvh.size() + (size_t)Kp0 * 16 * 32, 0);
+        msvh.resize(msvh.size() + (size_t)Kp0 * QP * 32, 0);
         uint32_t *tab = msvh.data() + pk.msvh_off;
         std::vector<int> owner(64, -1), first(64, 0);
         int s = 0;
         for (int h : bin) {
-          const int n = ctx->hmms[h].M / 16 + 1;
+          const int n = ctx->hmms[h].M / QP + 1;
           packmem.push_back(h); packmem.push_back(s); packmem.push_back(n);
           for (int z = 0; z < n; z++) { owner[s + z] = h; first[s + z] = s; }
           s += n;
@@ -540,7 +551,7 @@ extern "C" int pa_commit_hmms(pa_ctx *ctx) {
         }
         for (int hl = 0; hl < 64; hl++) packmem.push_back(owner[hl]);  // per half-lane owner, read by msv_pack_kernel
         for (int x = 0; x < Kp0; x++)
-          for (int q = 0; q < 16; q++)
+          for (int q = 0; q < QP; q++)
             for (int lane = 0; lane < 32; lane++) {
               uint16_t half[2];
               for (int hf = 0; hf < 2; hf++) {
@@ -548,67 +559,104 @@ extern "C" int pa_commit_hmms(pa_ctx *ctx) {
                 int delta = PA_MSV_DEAD;
                 if (h >= 0) {
                   const HostProfile &hp = ctx->hmms[h];
-                  const int k = (hl - first[hl]) * 16 + q + 1;
+                  const int k = (hl - first[hl]) * QP + q + 1;
                   if (k <= hp.M) delta = (int)hp.bias_b - (int)hp.rbv[(size_t)x * (hp.M + 1) + k];
                 }
                 half[hf] = h16_exact(delta);
               }
-              tab[((size_t)x * 16 + q) * 32 + lane] = (uint32_t)half[0] | ((uint32_t)half[1] << 16);
+              tab[((size_t)x * QP + q) * 32 + lane] = (uint32_t)half[0] | ((uint32_t)half[1] << 16);
             }
         ctx->h_packs.push_back(pk);
       }
     }
   }
-  CK(ctx->d_packs.ensure(ctx->h_packs.size() + 1));
-  if (!ctx->h_packs.empty()) CK(cudaMemcpy(ctx->d_packs.p, ctx->h_packs.data(), sizeof(DevPack) * ctx->h_packs.size(), cudaMemcpyHostToDevice));
-  CK(ctx->d_packmem.ensure(packmem.size() + 1));
-  if (!packmem.empty()) CK(cudaMemcpy(ctx->d_packmem.p, packmem.data(), packmem.size() * 4, cudaMemcpyHostToDevice));
   {  // per-Q lists of the profiles that stay on the per-profile kernels
     std::map<int, std::vector<int>> rest;
     for (int h = 0; h < nh; h++)
       if (!packed[h] && ctx->h_dev[h].nT == 0) rest[ctx->h_dev[h].Q].push_back(h);
-    std::vector<int> lists;
     ctx->q_groups_rest.clear();
     for (auto &kv : rest) {
-      ctx->q_groups_rest[kv.first] = {(int)lists.size(), (int)kv.second.size()};
-      lists.insert(lists.end(), kv.second.begin(), kv.second.end());
+      ctx->q_groups_rest[kv.first] = {(int)T.lists_rest.size(), (int)kv.second.size()};
+      T.lists_rest.insert(T.lists_rest.end(), kv.second.begin(), kv.second.end());
     }
-    CK(ctx->d_hmm_lists_rest.ensure(lists.size() + 1));
-    if (!lists.empty()) CK(cudaMemcpy(ctx->d_hmm_lists_rest.p, lists.data(), lists.size() * 4, cudaMemcpyHostToDevice));
   }
-  CK(ctx->d_sort.ensure(3 * ((size_t)nh + 1)));
-  CK(ctx->d_hmms.ensure(nh));
-  CK(cudaMemcpy(ctx->d_hmms.p, ctx->h_dev.data(), sizeof(DevHmm) * nh, cudaMemcpyHostToDevice));
-  CK(ctx->d_msv.ensure(msv.size()));
-  CK(cudaMemcpy(ctx->d_msv.p, msv.data(), msv.size() * 4, cudaMemcpyHostToDevice));
-  CK(ctx->d_msvh.ensure(msvh.size() + 1));
-  if (!msvh.empty()) CK(cudaMemcpy(ctx->d_msvh.p, msvh.data(), msvh.size() * 4, cudaMemcpyHostToDevice));
-  CK(ctx->d_v16.ensure(v16.size() + 4));
-  CK(cudaMemcpy(ctx->d_v16.p, v16.data(), v16.size() * 4, cudaMemcpyHostToDevice));
-  CK(ctx->d_vit.ensure(vit.size()));
-  CK(cudaMemcpy(ctx->d_vit.p, vit.data(), vit.size() * 4, cudaMemcpyHostToDevice));
-  CK(ctx->d_fwd.ensure(fwd.size()));
-  CK(cudaMemcpy(ctx->d_fwd.p, fwd.data(), fwd.size() * 4, cudaMemcpyHostToDevice));
-  std::vector<int> lists;
   ctx->q_groups.clear();
   for (auto &kv : byQ) {
-    ctx->q_groups[kv.first] = {(int)lists.size(), (int)kv.second.size()};
-    lists.insert(lists.end(), kv.second.begin(), kv.second.end());
+    ctx->q_groups[kv.first] = {(int)T.lists_all.size(), (int)kv.second.size()};
+    T.lists_all.insert(T.lists_all.end(), kv.second.begin(), kv.second.end());
   }
-  CK(ctx->d_hmm_lists.ensure(lists.size() + 1));
-  if (!lists.empty()) CK(cudaMemcpy(ctx->d_hmm_lists.p, lists.data(), lists.size() * 4, cudaMemcpyHostToDevice));
-  {
-    std::vector<int> wl;
-    ctx->w_groups.clear();
-    for (auto &kv : byW) {
-      ctx->w_groups[kv.first] = {(int)wl.size(), (int)kv.second.size()};
-      wl.insert(wl.end(), kv.second.begin(), kv.second.end());
-    }
-    CK(ctx->d_hmm_lists_w.ensure(wl.size() + 1));
-    if (!wl.empty()) CK(cudaMemcpy(ctx->d_hmm_lists_w.p, wl.data(), wl.size() * 4, cudaMemcpyHostToDevice));
+  ctx->w_groups.clear();
+  for (auto &kv : byW) {
+    ctx->w_groups[kv.first] = {(int)T.lists_w.size(), (int)kv.second.size()};
+    T.lists_w.insert(T.lists_w.end(), kv.second.begin(), kv.second.end());
   }
+  return 0;
+}
+
+static int upload_tables(pa_ctx *ctx, const HostTables &T) {
+  cudaSetDevice(ctx->device);
+  const int nh = (int)ctx->hmms.size();
+  auto up = [&](auto &buf, const auto &vec, size_t extra) -> cudaError_t {
+    cudaError_t e = buf.ensure(vec.size() + extra);
+    if (e != cudaSuccess || vec.empty()) return e;
+    return cudaMemcpy(buf.p, vec.data(), vec.size() * sizeof(vec[0]), cudaMemcpyHostToDevice);
+  };
+  CK(up(ctx->d_packs, ctx->h_packs, 1));
+  CK(up(ctx->d_packmem, T.packmem, 1));
+  CK(up(ctx->d_hmm_lists_rest, T.lists_rest, 1));
+  CK(ctx->d_sort.ensure(3 * ((size_t)nh + 1)));
+  CK(up(ctx->d_hmms, ctx->h_dev, 0));
+  CK(up(ctx->d_msv, T.msv, 0));
+  CK(up(ctx->d_msvh, T.msvh, 1));
+  CK(up(ctx->d_v16, T.v16, 4));
+  CK(up(ctx->d_vit, T.vit, 0));
+  CK(up(ctx->d_fwd, T.fwd, 0));
+  CK(up(ctx->d_hmm_lists, T.lists_all, 1));
+  CK(up(ctx->d_hmm_lists_w, T.lists_w, 1));
   CK(ctx->d_counters.ensure(16));
   ctx->committed = true;
+  return 0;
+}
+
+extern "C" int pa_commit_hmms(pa_ctx *ctx) {
+  if (!ctx) return -1;
+  HostTables T;
+  const int rc = build_tables(ctx, T);
+  return rc ? rc : upload_tables(ctx, T);
+}
+
+// One profile set on several GPUs: the profiles were added to ctxs[0]; the search profiles are configured and the device
+// tables laid out ONCE, then uploaded to every context (the others take over ctxs[0]'s profile list and options).
+extern "C" int pa_commit_hmms_multi(pa_ctx **ctxs, int n) {
+  if (!ctxs || n < 1 || !ctxs[0]) return -1;
+  pa_ctx *c0 = ctxs[0];
+  HostTables T;
+  int rc = build_tables(c0, T);
+  if (rc) return rc;
+  for (int k = 0; k < n; k++) {
+    pa_ctx *c = ctxs[k];
+    if (!c) { c0->err = "pa_commit_hmms_multi: null context"; return -1; }
+    if (k) {
+      c->opts = c0->opts;
+      c->hmms = c0->hmms;
+      c->h_dev = c0->h_dev;
+      c->v16_classes = c0->v16_classes;
+      c->vit_classes = c0->vit_classes;
+      c->rank_B = c0->rank_B;
+      c->q_groups = c0->q_groups;
+      c->q_groups_rest = c0->q_groups_rest;
+      c->w_groups = c0->w_groups;
+      c->h_packs = c0->h_packs;
+      c->maxB = c0->maxB;
+      c->maxM = c0->maxM;
+      c->maxQ_wide = c0->maxQ_wide;
+      c->ftok = c0->ftok;
+      c->pack_q = c0->pack_q;
+      c->msv_impl = c0->msv_impl;
+    }
+    rc = upload_tables(c, T);
+    if (rc) { if (k) c0->err = c->err; return rc; }
+  }
   return 0;
 }
 
@@ -821,7 +869,7 @@ extern "C" int64_t pa_get_targets(pa_ctx *ctx, char *out, uint64_t cap, uint64_t
 static cudaError_t dispatch_msv(pa_ctx *ctx, int Q, MsvArgs &a, int nrows) {
   const bool tmem = msv_use_tmem(ctx, Q, nrows);
   if (tmem) a.tab = ctx->d_msvh.p;
-  return launch_msv_q(Q, tmem, a, nrows, ctx->num_sms, ctx->stream, &ctx->stats.kernel_launches);
+  return launch_msv_q(Q, tmem, tmem && msv_fullt(ctx, Q), a, nrows, ctx->num_sms, ctx->stream, &ctx->stats.kernel_launches);
 }
 
 static cudaError_t side_fork(pa_ctx *ctx);

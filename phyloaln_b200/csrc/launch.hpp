@@ -13,9 +13,10 @@
 namespace pa {
 
 // msv_kernel<Q> (shared-memory DPX kernel) or msv_tmem_kernel<Q,2> (table in tensor memory; a.tab must point at the fp16 pool)
-cudaError_t launch_msv_q(int Q, bool tmem, MsvArgs &a, int nrows, int num_sms, cudaStream_t st, uint64_t *launched);
-cudaError_t launch_msv_pack(MsvPackArgs &pk, int ncols, int grid, cudaStream_t st, uint64_t *launched);
-cudaError_t launch_msv_wide(int QW, MsvWideArgs &wa, int ncols, int grid, size_t smem, cudaStream_t st, uint64_t *launched);
+// fullt: rows entirely in TMEM (Q 17..26 for small alphabets, msv_tmem_full_ok)
+cudaError_t launch_msv_q(int Q, bool tmem, bool fullt, MsvArgs &a, int nrows, int num_sms, cudaStream_t st, uint64_t *launched);
+cudaError_t launch_msv_pack(int QP, MsvPackArgs &pk, int ncols, int grid, cudaStream_t st, uint64_t *launched);
+cudaError_t launch_msv_wide(int QW, bool fullt, MsvWideArgs &wa, int ncols, int grid, size_t smem, cudaStream_t st, uint64_t *launched);
 cudaError_t launch_msv_exact_wide(MsvExactWideArgs &ex, int num_sms, cudaStream_t st, uint64_t *launched);
 
 // NW == 1: vit16_kernel<BH> / vit_kernel<Bv>; NW > 1: the multi-warp kernels of wide.cuh

@@ -20,28 +20,37 @@ static cudaError_t launch_msv(MsvArgs &a, int nrows_max, int num_sms, cudaStream
   return cudaGetLastError();
 }
 
-template <int Q>
+template <int Q, bool FT = false>
 static cudaError_t launch_msv_tmem(MsvArgs &a, int nrows, int num_sms, cudaStream_t st, uint64_t *launched) {
-  constexpr int G = 2;
-  const int need = msv_tmem_cols_needed(Q, nrows);
+  using Cfg = MsvTmemCfg<Q, FT>;
+  constexpr int G = Cfg::G;
+  const int need = msv_tmem_cols_needed(Q, nrows, FT);
   int ncols = 32;
   while (ncols < need) ncols *= 2;
   // resident CTAs per SM: fixed by the kernel's __launch_bounds__ (register cap) and by TMEM -- every
   // resident CTA must own its columns, or it would spin in tcgen05.alloc until a neighbour exits
-  const int bps = std::max(1, std::min(MsvTmemCfg<Q>::MINB, 512 / ncols));
-  const size_t smem = (size_t)(nrows + 1) * MsvTmemCfg<Q>::QS * 32 * 4;  // hybrid (Q > 16) only
+  const int bps = std::max(1, std::min(Cfg::MINB, 512 / ncols));
+  const size_t smem = (size_t)(nrows + 1) * Cfg::QS * 32 * 4;  // hybrid (Q > 16) only
   if (smem) {
-    cudaError_t e = cudaFuncSetAttribute(msv_tmem_kernel<Q, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(msv_tmem_kernel<Q, G, FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
   const uint32_t ntiles = (a.tg.n + a.tile - 1) / a.tile;
   const unsigned long long nitems = (unsigned long long)a.nlist * ntiles;
   const int grid = (int)std::min<unsigned long long>(nitems, (unsigned long long)num_sms * bps);
-  if (grid > 0) { msv_tmem_kernel<Q, G><<<grid, MsvTmemCfg<Q>::THREADS, smem, st>>>(a, ncols); ++*launched; }
+  if (grid > 0) { msv_tmem_kernel<Q, G, FT><<<grid, Cfg::THREADS, smem, st>>>(a, ncols); ++*launched; }
   return cudaGetLastError();
 }
 
-cudaError_t launch_msv_q(int Q, bool tmem, MsvArgs &a, int nrows, int num_sms, cudaStream_t st, uint64_t *launched) {
+cudaError_t launch_msv_q(int Q, bool tmem, bool fullt, MsvArgs &a, int nrows, int num_sms, cudaStream_t st, uint64_t *launched) {
+  if (tmem && fullt) {
+    switch (Q) {
+#define C_(q) case q: return launch_msv_tmem<q, true>(a, nrows, num_sms, st, launched);
+      C_(17) C_(18) C_(19) C_(20) C_(21) C_(22) C_(23) C_(24) C_(25) C_(26)
+#undef C_
+    }
+    return cudaErrorInvalidValue;
+  }
   if (tmem) {
     switch (Q) {
 #define C_(q) case q: return launch_msv_tmem<q>(a, nrows, num_sms, st, launched);
@@ -60,13 +69,29 @@ cudaError_t launch_msv_q(int Q, bool tmem, MsvArgs &a, int nrows, int num_sms, c
   return cudaErrorInvalidValue;
 }
 
-cudaError_t launch_msv_pack(MsvPackArgs &pk, int ncols, int grid, cudaStream_t st, uint64_t *launched) {
-  if (grid > 0) { msv_pack_kernel<2><<<grid, 1024, 0, st>>>(pk, ncols); ++*launched; }
+cudaError_t launch_msv_pack(int QP, MsvPackArgs &pk, int ncols, int grid, cudaStream_t st, uint64_t *launched) {
+  if (grid <= 0) return cudaSuccess;
+  if (QP == 16) msv_pack_kernel<16, 2><<<grid, 1024, 0, st>>>(pk, ncols);
+  else if (QP == PA_TMEM_FULLQ) msv_pack_kernel<PA_TMEM_FULLQ, 1><<<grid, 512, 0, st>>>(pk, ncols);
+  else return cudaErrorInvalidValue;
+  ++*launched;
   return cudaGetLastError();
 }
 
-cudaError_t launch_msv_wide(int QW, MsvWideArgs &wa, int ncols, int grid, size_t smem, cudaStream_t st, uint64_t *launched) {
+cudaError_t launch_msv_wide(int QW, bool fullt, MsvWideArgs &wa, int ncols, int grid, size_t smem, cudaStream_t st, uint64_t *launched) {
   if (grid <= 0) return cudaSuccess;
+  if (fullt) {
+    switch (QW) {
+#define C_(q)                                                \
+  case q:                                                    \
+    msv_wide_kernel<q, 1, true><<<grid, 512, 0, st>>>(wa, ncols); \
+    ++*launched;                                             \
+    return cudaGetLastError();
+      C_(17) C_(18) C_(19) C_(20) C_(21) C_(22) C_(23) C_(24) C_(25) C_(26)
+#undef C_
+    }
+    return cudaErrorInvalidValue;
+  }
   switch (QW) {
 #define C_(q)                                                                                                            \
   case q: {                                                                                                              \

@@ -87,6 +87,16 @@ __device__ __forceinline__ void tmem_ld<16>(uint32_t taddr, uint32_t (&r)[16]) {
                : "r"(taddr)
                : "memory");
 }
+template <>
+__device__ __forceinline__ void tmem_ld<32>(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                 "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]),
+                 "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]),
+                 "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+               : "r"(taddr)
+               : "memory");
+}
 // tcgen05.wait::ld: the PTX model leaves the destination registers undefined until this point; the
 // "+r" operands make every later use of the row depend on it.  ptxas turns it into scoreboard
 // waits on exactly those registers, so younger loads stay in flight.
@@ -112,26 +122,34 @@ __device__ __forceinline__ uint32_t h2_add_relu(uint32_t a, uint32_t c) {
 __device__ __forceinline__ int h16_bits_to_int(int bits) { return __half2int_rn(__ushort_as_half((unsigned short)bits)); }
 __device__ __forceinline__ uint32_t int_to_h16x2(int v) { return (uint32_t)__half_as_ushort(__int2half_rn(v)) * 0x10001u; }
 
-__host__ __device__ constexpr int msv_tmem_lw(int Q) { return Q <= 1 ? 1 : Q <= 2 ? 2 : Q <= 4 ? 4 : Q <= 8 ? 8 : 16; }
+__host__ __device__ constexpr int msv_tmem_lw(int Q) { return Q <= 1 ? 1 : Q <= 2 ? 2 : Q <= 4 ? 4 : Q <= 8 ? 8 : Q <= 16 ? 16 : 32; }
 #define PA_TMEM_MAXQ 32
+#define PA_TMEM_FULLQ 26   // widest all-TMEM row: 19 rows (DNA: Kp = 18 + the dead row) x 26 words + over-read <= 512 columns
 
 // Geometry per Q (words per lane, Q = M/64 + 1):
 //   Q <= 8    table needs <= 256 TMEM columns: two 512-thread CTAs per SM, 64 registers each
 //   Q 9..16   all 512 columns: one 1024-thread CTA per SM, 64 registers
 //   Q 17..32  hybrid: the first 16 words of every row come from TMEM, the other Q-16 from shared
 //             memory (LDS.128, the striped layout of msv_kernel); one 512-thread CTA per SM
-template <int Q>
+//   Q 17..26, FT ("full TMEM"): small alphabets (DNA: 19 rows) fit up to 26 words per row in the 512 columns, so the whole
+//             row is ONE LDTM.x32 and no shared-memory part exists; one 512-thread CTA per SM, one row of prefetch (G = 1)
+template <int Q, bool FT = false>
 struct MsvTmemCfg {
-  static constexpr int QT = Q <= 16 ? Q : 16;
+  static constexpr int QT = (Q <= 16 || FT) ? Q : 16;
   static constexpr int QS = Q - QT;
   static constexpr int LW = msv_tmem_lw(QT);
   static constexpr int THREADS = Q <= 8 ? 512 : Q <= 16 ? 1024 : 512;
   static constexpr int MINB = Q <= 8 ? 2 : 1;
+  static constexpr int G = (FT && Q > 16) ? 1 : 2;
 };
-__host__ __device__ constexpr int msv_tmem_qt(int Q) { return Q <= 16 ? Q : 16; }
+__host__ __device__ constexpr int msv_tmem_qt(int Q, bool ft = false) { return (Q <= 16 || ft) ? Q : 16; }
 // TMEM columns: (nrows + 1 dead row) * QT, plus the over-read of the last row's LDTM
-__host__ __device__ constexpr int msv_tmem_cols_needed(int Q, int nrows) {
-  return (nrows + 1) * msv_tmem_qt(Q) + (msv_tmem_lw(msv_tmem_qt(Q)) - msv_tmem_qt(Q));
+__host__ __device__ constexpr int msv_tmem_cols_needed(int Q, int nrows, bool ft = false) {
+  return (nrows + 1) * msv_tmem_qt(Q, ft) + (msv_tmem_lw(msv_tmem_qt(Q, ft)) - msv_tmem_qt(Q, ft));
+}
+// can rows of Q words live in TMEM entirely for an alphabet with `nrows` codes?
+__host__ __device__ constexpr bool msv_tmem_full_ok(int Q, int nrows) {
+  return Q > 16 && Q <= PA_TMEM_FULLQ && msv_tmem_cols_needed(Q, nrows, true) <= 512;
 }
 // words of the fp16x2 pool per profile: TMEM part [x][q < QT][lane], then the shared-memory part
 // [x][striped QS*32] (rows 0..nrows-1; the dead row is synthesised on the device)
@@ -198,9 +216,9 @@ __device__ __forceinline__ uint32_t row_max_bits(const uint32_t (&w)[Q]) {
 // is computed.  The residues of the next 32-row block (of this target or of the warp's next target)
 // and the next target's metadata are fetched one block ahead, so no global-memory latency sits on
 // the per-target critical path.
-template <int Q, int G>
-__global__ void __launch_bounds__(MsvTmemCfg<Q>::THREADS, MsvTmemCfg<Q>::MINB) msv_tmem_kernel(MsvArgs a, int ncols) {
-  using Cfg = MsvTmemCfg<Q>;
+template <int Q, int G, bool FT = false>
+__global__ void __launch_bounds__(MsvTmemCfg<Q, FT>::THREADS, MsvTmemCfg<Q, FT>::MINB) msv_tmem_kernel(MsvArgs a, int ncols) {
+  using Cfg = MsvTmemCfg<Q, FT>;
   constexpr int QT = Cfg::QT, QS = Cfg::QS, LW = Cfg::LW;
   constexpr int SROW = QS * 32;                       // words per shared-memory row
   extern __shared__ __align__(16) uint32_t s_tab[];  // (nrows + 1) * SROW words (hybrid only)
@@ -384,9 +402,11 @@ struct MsvPackArgs {
   int npacks;
 };
 
-template <int G>
-__global__ void __launch_bounds__(1024, 1) msv_pack_kernel(MsvPackArgs pa_, int ncols) {
-  constexpr int Q = 16, QT = 16, LW = 16;
+// QP = words per lane of the packed model = cells per half-lane: 16 (any alphabet, 1024 threads) or 26 (alphabets whose table
+// fits TMEM at that width, i.e. DNA: 1,664-cell packs, one LDTM.x32 per row, 512 threads with one row of prefetch)
+template <int QP, int G>
+__global__ void __launch_bounds__(QP <= 16 ? 1024 : 512, 1) msv_pack_kernel(MsvPackArgs pa_, int ncols) {
+  constexpr int Q = QP, QT = QP, LW = msv_tmem_lw(QP);
   const MsvArgs &a = pa_.a;
   __shared__ uint32_t s_slot;
   __shared__ unsigned long long s_item;
@@ -488,8 +508,8 @@ __global__ void __launch_bounds__(1024, 1) msv_pack_kernel(MsvPackArgs pa_, int 
       unsigned long long hot = 0;
       for (int b = 0; b < 32; b++) hot |= ((unsigned long long)((even >> b) & 1u) << (2 * b)) | ((unsigned long long)((odd >> b) & 1u) << (2 * b + 1));
       // an inf seen in cell c was born at most L-1 cells up the diagonal: a member owning half-lanes [hs, hs+hn) is a
-      // candidate iff some hot half-lane lies in [hs, hs + hn + ceil((L-1)/16)] (cyclic over the 64 half-lanes)
-      const int reach = (L + 14) / 16;
+      // candidate iff some hot half-lane lies in [hs, hs + hn + ceil((L-1)/QP)] (cyclic over the 64 half-lanes)
+      const int reach = (L + QP - 2) / QP;
       const int tjb = a.tjb_li[li];
       // ---- per member: candidate test, exact MSV re-run
       for (int mi = 0; mi < pack.nmem; mi++) {

@@ -42,10 +42,11 @@ struct MsvWideArgs {
   unsigned long long cand_cap;
 };
 
-template <int Q, int G>
+template <int Q, int G, bool FT = false>
 static __global__ void __launch_bounds__(512, 1) msv_wide_kernel(MsvWideArgs wa, int ncols) {
-  static_assert(Q >= 17 && Q <= 32, "tiles use the hybrid TMEM + shared-memory geometry");
-  constexpr int QT = 16, QS = Q - QT, LW = 16, SROW = QS * 32;
+  static_assert(Q >= 17 && Q <= 32 && (!FT || Q <= PA_TMEM_FULLQ), "tiles use the hybrid TMEM + shared-memory geometry, or all-TMEM rows (FT)");
+  using Cfg = MsvTmemCfg<Q, FT>;
+  constexpr int QT = Cfg::QT, QS = Cfg::QS, LW = Cfg::LW, SROW = QS * 32;
   const MsvArgs &a = wa.a;
   extern __shared__ __align__(16) uint32_t s_tab[];  // (nrows + 1) * SROW words
   __shared__ uint32_t s_slot;
@@ -85,9 +86,11 @@ static __global__ void __launch_bounds__(512, 1) msv_wide_kernel(MsvWideArgs wa,
           for (int q = 0; q < LW; q++) tmem_st1(lanebase + nrows * QT + q, dead);
           tmem_wait_st();
         }
-        const uint32_t *ssrc = src + (size_t)nrows * QT * 32;
-        for (int i = threadIdx.x; i < nrows * SROW; i += blockDim.x) s_tab[i] = __ldg(ssrc + i);
-        for (int i = threadIdx.x; i < SROW; i += blockDim.x) s_tab[nrows * SROW + i] = dead;
+        if constexpr (QS > 0) {
+          const uint32_t *ssrc = src + (size_t)nrows * QT * 32;
+          for (int i = threadIdx.x; i < nrows * SROW; i += blockDim.x) s_tab[i] = __ldg(ssrc + i);
+          for (int i = threadIdx.x; i < SROW; i += blockDim.x) s_tab[nrows * SROW + i] = dead;
+        }
       }
       tmem_cta_sync();
       const bool first = m == 0, last = m == nT - 1;
@@ -140,9 +143,8 @@ static __global__ void __launch_bounds__(512, 1) msv_wide_kernel(MsvWideArgs wa,
             }
 #pragma unroll
             for (int g = 0; g < G; g++) {
-              const uint32_t *srow = s_tab + __shfl_sync(PA_FULL, myx, r + g) * SROW;
-              uint32_t ds[QS];
-              msv_load_row<QS>(srow, lane, ds);
+              uint32_t ds[QS > 0 ? QS : 1];
+              if constexpr (QS > 0) msv_load_row<QS>(s_tab + __shfl_sync(PA_FULL, myx, r + g) * SROW, lane, ds);
               // word Q-1 of the left neighbour after the previous row; lane 0 sees the tile's last cell (lane 31, high half):
               // it leaves the tile here -- parked for the next tile (row i0 + r + g of its sweep) or, in the last tile, watched for +inf
               uint32_t tt = __shfl_sync(PA_FULL, w[Q - 1], lanem1);

@@ -205,7 +205,8 @@ def hmmsearch_step(outdir: str, groups, mol_type: str = "prot", gencode: int = 1
             src, mol_type=mol_type, gencode=gencode, no_reverse=no_reverse, codon=codon, chunk_reads=chunk_reads, want_pp=write_text)
         pp = searcher.last_pp
         invalid = searcher.last_invalid
-        stats = [c.stats() for c in searcher.ctxs]
+        stats = [c.stats() for c in searcher.ctxs if c is not None]
+        tm["setup"] = getattr(searcher, "setup_timing", None)
     finally:
         searcher.close()
     tm["search_s"] = time.perf_counter() - t0

@@ -373,54 +373,57 @@ class B200Searcher:
     """All profiles x one read set on one or more B200s (one context per GPU, reads sharded by chunk)."""
 
     def __init__(self, hmms, devices=(0,), options: SearchOptions | None = None, defer: bool = False):
-        """defer=True: the per-GPU contexts (CUDA context, profile configuration, table upload) are created by the worker
-        threads of the first search, each GPU starting on the reads as soon as ITS context is ready."""
+        """defer=True: the per-GPU contexts are created by the first search (so that a running ingest, the parsing of the
+        .hmm files and CUDA start-up overlap) instead of here."""
         self.opts = options or SearchOptions()
         self.hmms = [h if isinstance(h, HMM) else read_hmm(h) for h in hmms]
         self.devices = list(devices)
         self.ctxs = [None] * len(self.devices)
-        self._prepared = None
-        if defer:
-            return
-        errors = []
+        self._setup_lock = threading.Lock()
+        if not defer:
+            self._ensure_contexts()
 
-        def setup(k):
-            try:
-                self._setup(k)
-            except Exception as e:
-                errors.append(e)
-        if len(self.devices) == 1:
-            setup(0)
-        else:     # one thread per GPU: context creation, profile configuration and upload run side by side
-            th = [threading.Thread(target=setup, args=(k,)) for k in range(len(self.devices))]
+    def _ensure_contexts(self):
+        """One context per GPU (CUDA contexts come up in parallel threads); the profiles are added to the first one and
+        committed ONCE for all of them (pa_commit_hmms_multi: configuration and table layout on the host are not repeated
+        per GPU, only the upload is)."""
+        with self._setup_lock:
+            if all(c is not None for c in self.ctxs):
+                return
+            import time
+            errors = []
+            t0 = time.perf_counter()
+
+            def create(k):
+                try:
+                    self.ctxs[k] = capi.Context(self.devices[k])
+                except Exception as e:
+                    errors.append(e)
+            th = [threading.Thread(target=create, args=(k,)) for k in range(1, len(self.devices))]
             for t in th:
                 t.start()
+            create(0)
+            prepared = [capi.prepare_hmm(h) for h in self.hmms] if not errors else []
             for t in th:
                 t.join()
-        if errors:
-            self.close()
-            raise errors[0]
-
-    def _setup(self, k: int):
-        """Create context k (idempotent)."""
-        if self.ctxs[k] is not None:
-            return self.ctxs[k]
-        if self._prepared is None:      # benign race: two threads may both convert, the results are equal
-            self._prepared = [capi.prepare_hmm(h) for h in self.hmms]
-        c = capi.Context(self.devices[k])
-        self.ctxs[k] = c
-        c.set_opts(F1=self.opts.F1, F2=self.opts.F2, F3=self.opts.F3, do_bias=not self.opts.nobias,
-                   do_null2=not self.opts.nonull2, do_max=self.opts.max)
-        for p in self._prepared:
-            c.add_hmm(p)
-        c.commit()
-        return c
+            if errors:
+                self.close()
+                raise errors[0]
+            c0 = self.ctxs[0]
+            c0.set_opts(F1=self.opts.F1, F2=self.opts.F2, F3=self.opts.F3, do_bias=not self.opts.nobias,
+                        do_null2=not self.opts.nonull2, do_max=self.opts.max)
+            t1 = time.perf_counter()
+            for p in prepared:
+                c0.add_hmm(p)
+            t2 = time.perf_counter()
+            capi.commit_multi(self.ctxs)
+            self.setup_timing = {"create_contexts_s": t1 - t0, "add_profiles_s": t2 - t1, "commit_and_upload_s": time.perf_counter() - t2}
 
     def close(self):
         for c in self.ctxs:
             if c is not None:
                 c.close()
-        self.ctxs = []
+        self.ctxs = [None] * len(self.ctxs)
 
     def search_reads(self, nt: np.ndarray, off: np.ndarray, **kw):
         """Search concatenated ASCII reads (host arrays). See :meth:`search_source`."""
@@ -508,7 +511,7 @@ class B200Searcher:
 
         def work(k):
             try:
-                ctx = self._setup(k)      # deferred contexts: this GPU starts as soon as its own context is ready
+                ctx = self.ctxs[k]
                 while True:
                     r = next_range()
                     if r is None:
@@ -520,6 +523,8 @@ class B200Searcher:
             except Exception as e:  # surfaced after join
                 errors.append(e)
 
+        if any(c is None for c in self.ctxs):
+            self._ensure_contexts()
         threads = [threading.Thread(target=work, args=(k,)) for k in range(len(self.ctxs))]
         for t in threads:
             t.start()

@@ -96,7 +96,7 @@ class FakeCtx:
 
 def _searcher(ctxs):
     s = search.B200Searcher.__new__(search.B200Searcher)
-    s.opts, s.hmms, s.ctxs = search.SearchOptions(), [None], ctxs
+    s.opts, s.hmms, s.ctxs, s._setup_lock = search.SearchOptions(), [None], ctxs, threading.Lock()
     return s
 
 
