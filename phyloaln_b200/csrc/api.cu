@@ -11,12 +11,14 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/phyloaln_b200.h"
@@ -76,6 +78,7 @@ struct pa_ctx {
 
   std::vector<HostProfile> hmms;
   bool committed = false;
+  bool tables_shared = false;  // profiles came from pa_commit_hmms_multi: only a slim copy lives here, no re-commit
   std::vector<DevHmm> h_dev;
   DevBuf<DevHmm> d_hmms;
   DevBuf<uint32_t> d_msv, d_msvh;
@@ -235,8 +238,7 @@ extern "C" int pa_add_hmm(pa_ctx *ctx, const char *name, int abc, int M, const d
   if (!ctx->hmms.empty() && ctx->hmms[0].abc != abc) { ctx->err = "all profiles of a context must share one alphabet"; return -2; }
   if (ctx->hmms.size() >= 65535) { ctx->err = "too many profiles (max 65535)"; return -2; }
   HostProfile hp;
-  hp.from_file_numbers(name, abc, M, mat, ins, t, compo, cons, evparam);
-  hp.configure();
+  hp.from_file_numbers(name, abc, M, mat, ins, t, compo, cons, evparam);   // configured at commit time, all profiles in parallel
   ctx->hmms.push_back(std::move(hp));
   ctx->committed = false;
   return (int)ctx->hmms.size() - 1;
@@ -290,6 +292,24 @@ static inline bool msv_use_tmem(const pa_ctx *ctx, int Q, int nrows) {
   return ctx->msv_impl == 0 && Q <= PA_TMEM_MAXQ && msv_tmem_cols_needed(Q, nrows, msv_fullt(ctx, Q)) <= 512;
 }
 
+// fn(i) for i in [0, n) on the host's hardware threads (table building is independent per profile)
+template <class F>
+static void parallel_for(int n, F fn) {
+  const int nt = std::max(1, std::min<int>({n, (int)std::thread::hardware_concurrency(), 16}));
+  if (nt <= 1) {
+    for (int i = 0; i < n; i++) fn(i);
+    return;
+  }
+  std::atomic<int> next{0};
+  auto work = [&]() {
+    for (int i = next.fetch_add(1); i < n; i = next.fetch_add(1)) fn(i);
+  };
+  std::vector<std::thread> th;
+  for (int t = 1; t < nt; t++) th.emplace_back(work);
+  work();
+  for (auto &t : th) t.join();
+}
+
 // Host images of every per-profile device table (built once per profile set, uploaded to one or several GPUs)
 struct HostTables {
   std::vector<uint32_t> msv, msvh, v16;
@@ -300,6 +320,7 @@ struct HostTables {
 static int build_tables(pa_ctx *ctx, HostTables &T) {
   const int nh = (int)ctx->hmms.size();
   if (nh == 0) { ctx->err = "no profiles"; return -2; }
+  if (ctx->tables_shared) { ctx->err = "this context shares the profiles of another one (pa_commit_hmms_multi): change options or profiles on the first context and commit again"; return -2; }
   std::vector<uint32_t> &msv = T.msv, &msvh = T.msvh, &v16 = T.v16;
   std::vector<int> &vit = T.vit;
   std::vector<float> &fwd = T.fwd;
@@ -308,9 +329,17 @@ static int build_tables(pa_ctx *ctx, HostTables &T) {
   ctx->maxM = 1;
   std::map<int, std::vector<int>> byQ, byW;
   ctx->maxQ_wide = 0;
-  ctx->ftok = ctx->msv_impl == 0 && getenv("PA_MSV_NOFULLT") == nullptr && msv_tmem_full_ok(PA_TMEM_FULLQ, ctx->hmms[0].Kp);
+  // All-TMEM rows of up to 26 words for small alphabets are implemented and parity-tested, but OFF by default: measured on
+  // config 3 (DNA) they are 6 % slower than the hybrid rows (8,960 vs 8,462 ms of MSV per 500 k reads) -- one LDTM.x32 per
+  // 1,664-cell row is 4 KB, i.e. ~315 B/clk/SM at the FMA-bound rate, which is the measured TMEM read ceiling (270-400 B/clk/SM,
+  // tools/probe_sm100.cu), and the 128-register budget leaves a single row of prefetch.  PA_MSV_FULLT=1 switches them on.
+  ctx->ftok = ctx->msv_impl == 0 && getenv("PA_MSV_FULLT") != nullptr && atoi(getenv("PA_MSV_FULLT")) != 0 &&
+              msv_tmem_full_ok(PA_TMEM_FULLQ, ctx->hmms[0].Kp);
   ctx->pack_q = ctx->ftok ? PA_TMEM_FULLQ : 16;
   const bool maxmode = ctx->opts.do_max != 0;
+  parallel_for(nh, [&](int h) { if (!ctx->hmms[h].configured) { ctx->hmms[h].configure(); ctx->hmms[h].configured = true; } });
+  size_t n_msv = 0, n_msvh = 0, n_vit = 0, n_v16 = 0, n_fwd = 0;
+  std::vector<int> qw_of(nh, 0);
   for (int h = 0; h < nh; h++) {
     const HostProfile &hp = ctx->hmms[h];
     if (!hp.has_stats) { ctx->err = "profile '" + hp.name + "' has no STATS LOCAL (uncalibrated)"; return -2; }
@@ -344,11 +373,35 @@ static int build_tables(pa_ctx *ctx, HostTables &T) {
     memcpy(d.eo1, hp.eo1, sizeof(d.eo1));
     memcpy(d.ev, hp.ev, sizeof(d.ev));
 
+    // ---- sizes and offsets of this profile's tables (filled in parallel below)
+    auto take = [](size_t &total, size_t n) { total = (total + 3) & ~(size_t)3; const size_t o = total; total += n; return o; };
+    d.msv_off = take(n_msv, (size_t)Kp * d.Q * 32);
+    d.msvh_off = n_msvh;
+    if (wide) {
+      if (msv_tmem_cols_needed(QW, Kp, ctx->ftok) > 512) { ctx->err = "alphabet too large for the tiled MSV kernel"; return -2; }
+      n_msvh += (size_t)Kp * QW * 32 * d.nT;
+    } else if (msv_use_tmem(ctx, d.Q, Kp))
+      n_msvh += (size_t)Kp * d.Q * 32;
+    d.Bv = vit_class((M + 32 * d.NWv - 1) / (32 * d.NWv));
+    d.vit_off = take(n_vit, (size_t)d.Bv * 32 * d.NWv * (9 + Kp));
+    d.BH = v16_class((M + 64 * d.NW16 - 1) / (64 * d.NW16));
+    d.v16_off = take(n_v16, (size_t)d.BH * 32 * d.NW16 * (9 + Kp));
+    d.fwd_off = take(n_fwd, (size_t)d.B * 32 * (16 + Kp));
+    qw_of[h] = QW;
+  }
+  msv.assign(n_msv, 0u);
+  msvh.assign(n_msvh, 0u);
+  vit.assign(n_vit, PA_NEG16);
+  v16.assign(n_v16, 0u);
+  fwd.assign(n_fwd, 0.0f);
+  auto fill_profile = [&](int h) {
+    const HostProfile &hp = ctx->hmms[h];
+    DevHmm &d = ctx->h_dev[h];
+    const int M = hp.M, Kp = hp.Kp;
+    const bool wide = d.nT > 0;
+    const int QW = qw_of[h];
     // ---- MSV striped s16x2 table: delta = bias - rbv, dead padding beyond M (wide profiles: plain [x][q][lane] rows)
     const int Q = d.Q, roww = Q * 32;
-    while (msv.size() % 4) msv.push_back(0);
-    d.msv_off = msv.size();
-    msv.resize(msv.size() + (size_t)Kp * roww, 0);
     for (int x = 0; x < Kp; x++)
       for (int q = 0; q < Q; q++)
         for (int lane = 0; lane < 32; lane++) {
@@ -362,13 +415,10 @@ static int build_tables(pa_ctx *ctx, HostTables &T) {
 
     // ---- the same deltas as fp16x2 for the tensor-memory kernel (msv_tmem.cuh): words q < QT as
     // [x][q][lane] (TMEM part), words q >= QT striped like the s16 table (shared-memory part, Q > 16)
-    d.msvh_off = msvh.size();
     if (wide) {
       // nT tiles of 64*QW cells, each laid out like a profile with Q = QW: tile m holds model cells m*64*QW + (2*lane + hf)*QW + q
-      if (msv_tmem_cols_needed(QW, Kp, ctx->ftok) > 512) { ctx->err = "alphabet too large for the tiled MSV kernel"; return -2; }
       const int QT = msv_tmem_qt(QW, ctx->ftok), QS = QW - QT;
       const size_t tilew = (size_t)Kp * QW * 32;
-      msvh.resize(msvh.size() + tilew * d.nT, 0);
       for (int m = 0; m < d.nT; m++) {
         uint32_t *tpart = msvh.data() + d.msvh_off + tilew * m, *spart = tpart + (size_t)Kp * QT * 32;
         for (int x = 0; x < Kp; x++)
@@ -386,7 +436,6 @@ static int build_tables(pa_ctx *ctx, HostTables &T) {
       }
     } else if (msv_use_tmem(ctx, Q, Kp)) {
       const int QT = msv_tmem_qt(Q, msv_fullt(ctx, Q)), QS = Q - QT;
-      msvh.resize(msvh.size() + (size_t)Kp * roww, 0);
       uint32_t *tpart = msvh.data() + d.msvh_off, *spart = tpart + (size_t)Kp * QT * 32;
       for (int x = 0; x < Kp; x++)
         for (int q = 0; q < Q; q++)
@@ -406,11 +455,7 @@ static int build_tables(pa_ctx *ctx, HostTables &T) {
     // (tid < NT: one warp, or the NWv warps of a CTA for wide profiles)
     {
       const int NT = 32 * d.NWv;
-      d.Bv = vit_class((M + NT - 1) / NT);
       const int Bv = d.Bv, Wv = Bv * NT;
-      while (vit.size() % 4) vit.push_back(0);
-      d.vit_off = vit.size();
-      vit.resize(vit.size() + (size_t)Wv * (9 + Kp), PA_NEG16);
       int *vA = vit.data() + d.vit_off, *vI = vA + 4 * Wv, *vD = vI + 2 * Wv, *vps = vD + 2 * Wv, *vem = vps + Wv;
       for (int c = 0; c < Wv; c++) {
         const int k = (c % NT) * Bv + (c / NT) + 1;
@@ -434,11 +479,7 @@ static int build_tables(pa_ctx *ctx, HostTables &T) {
     // ---- packed tables of the 16-bit upper-bound pass: half-lane hl = 2*tid + hf owns k = hl*BH + j + 1; every entry >= -16384
     {
       const int NT = 32 * d.NW16;
-      d.BH = v16_class((M + 2 * NT - 1) / (2 * NT));
       const int BH = d.BH, W16 = BH * NT;
-      while (v16.size() % 4) v16.push_back(0);
-      d.v16_off = v16.size();
-      v16.resize(v16.size() + (size_t)W16 * (9 + Kp), 0u);
       uint32_t *wA = v16.data() + d.v16_off, *wI = wA + 4 * W16, *wD = wI + 2 * W16, *wps = wD + 2 * W16, *wem = wps + W16;
       int guard = 0;
       auto put = [](uint32_t *w, int hf, int v) { *w = hf ? ((*w & 0x0000ffffu) | ((uint32_t)(v & 0xffff) << 16)) : ((*w & 0xffff0000u) | (uint32_t)(v & 0xffff)); };
@@ -475,9 +516,6 @@ static int build_tables(pa_ctx *ctx, HostTables &T) {
     // ---- float tables, lane-blocked [j][lane] with the canonical B = ceil(M/32): k = lane*B + j + 1
     const int B = d.B, W = B * 32;
     auto cellk = [&](int c) { return (c % 32) * B + (c / 32) + 1; };
-    while (fwd.size() % 4) fwd.push_back(0.f);
-    d.fwd_off = fwd.size();
-    fwd.resize(fwd.size() + (size_t)W * (16 + Kp), 0.0f);
     float *fA = fwd.data() + d.fwd_off, *fB = fA + 4 * W, *bA = fB + 4 * W, *bB = bA + 4 * W, *fem = bB + 4 * W;
     for (int c = 0; c < W; c++) {
       const int k = cellk(c);
@@ -490,7 +528,8 @@ static int build_tables(pa_ctx *ctx, HostTables &T) {
         for (int x = 0; x < Kp; x++) fem[(size_t)x * W + c] = hp.rfv[(size_t)x * (M + 1) + k];
       }
     }
-  }
+  };
+  parallel_for(nh, fill_profile);
   {  // profile rank in (M, index) order: the sorted survivor list is then contiguous per Viterbi class and per Forward block size
     std::vector<int> ord(nh);
     for (int h = 0; h < nh; h++) ord[h] = h;
@@ -638,7 +677,20 @@ extern "C" int pa_commit_hmms_multi(pa_ctx **ctxs, int n) {
     if (!c) { c0->err = "pa_commit_hmms_multi: null context"; return -1; }
     if (k) {
       c->opts = c0->opts;
-      c->hmms = c0->hmms;
+      // the other contexts only need what the search reads after the commit (widths, E-value parameters, consensus, scales)
+      c->hmms.clear();
+      c->hmms.reserve(c0->hmms.size());
+      for (const HostProfile &hp : c0->hmms) {
+        HostProfile sl;
+        sl.name = hp.name; sl.abc = hp.abc; sl.M = hp.M; sl.K = hp.K; sl.Kp = hp.Kp; sl.cons = hp.cons;
+        memcpy(sl.ev, hp.ev, sizeof(sl.ev));
+        sl.has_stats = hp.has_stats; sl.configured = true;
+        sl.tbm_b = hp.tbm_b; sl.tec_b = hp.tec_b; sl.base_b = hp.base_b; sl.bias_b = hp.bias_b;
+        sl.scale_b = hp.scale_b; sl.scale_w = hp.scale_w; sl.base_w = hp.base_w; sl.xw_E = hp.xw_E;
+        memcpy(sl.eo1, hp.eo1, sizeof(sl.eo1));
+        c->hmms.push_back(std::move(sl));
+      }
+      c->tables_shared = true;
       c->h_dev = c0->h_dev;
       c->v16_classes = c0->v16_classes;
       c->vit_classes = c0->vit_classes;

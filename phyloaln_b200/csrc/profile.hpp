@@ -31,6 +31,7 @@ struct HostProfile {
   std::string cons;                // index 1..M (cons[0] unused)
   float ev[6] = {0, 0, 0, 0, 0, 0};
   bool has_stats = false;
+  bool configured = false;   // configure() has run (done lazily, in parallel, by the commit)
 
   // configured profile (natural layouts, index [x*(M+1)+k] and [k*8+t])
   std::vector<float> tsc, msc, rfv, tfv, bgf;

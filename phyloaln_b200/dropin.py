@@ -157,6 +157,8 @@ def hmmsearch_step(outdir: str, groups, mol_type: str = "prot", gencode: int = 1
             _finish_prepare_target(outdir, ingest)
         return counts
     t0 = time.perf_counter()
+    searcher = B200Searcher([], devices=devices, options=opts, defer=True)
+    searcher.start_contexts()          # CUDA start-up on every GPU runs while the profiles are parsed
     hmms, kept = [], []
     from concurrent.futures import ThreadPoolExecutor
     with ThreadPoolExecutor(min(8, os.cpu_count() or 1)) as ex:     # the native reader releases the GIL
@@ -173,6 +175,9 @@ def hmmsearch_step(outdir: str, groups, mol_type: str = "prot", gencode: int = 1
     if codon:
         no_reverse = True
     if not todo:
+        for t in searcher._ctx_threads or []:
+            t.join()
+        searcher.close()
         if ingest is not None:
             _finish_prepare_target(outdir, ingest)
         return counts
@@ -197,7 +202,7 @@ def hmmsearch_step(outdir: str, groups, mol_type: str = "prot", gencode: int = 1
         src = ArraySource(nt, off)
     tm["load_reads_s"] = time.perf_counter() - t0
     t0 = time.perf_counter()
-    searcher = B200Searcher(hmms, devices=devices, options=opts, defer=True)   # contexts come up inside the search workers
+    searcher.hmms = hmms               # configured, laid out and uploaded once for all GPUs when the search starts
     tm["upload_profiles_s"] = time.perf_counter() - t0
     t0 = time.perf_counter()
     try:

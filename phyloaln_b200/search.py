@@ -380,8 +380,25 @@ class B200Searcher:
         self.devices = list(devices)
         self.ctxs = [None] * len(self.devices)
         self._setup_lock = threading.Lock()
+        self._ctx_threads, self._ctx_errors = None, []
         if not defer:
             self._ensure_contexts()
+
+    def start_contexts(self):
+        """Begin creating the CUDA contexts in background threads (CUDA start-up takes ~0.7 s per process and overlaps with
+        whatever the caller does next, e.g. parsing the .hmm files); _ensure_contexts() joins them."""
+        if getattr(self, "_ctx_threads", None) is not None or all(c is not None for c in self.ctxs):
+            return
+        self._ctx_errors = []
+
+        def create(k):
+            try:
+                self.ctxs[k] = capi.Context(self.devices[k])
+            except Exception as e:
+                self._ctx_errors.append(e)
+        self._ctx_threads = [threading.Thread(target=create, args=(k,)) for k in range(len(self.devices))]
+        for t in self._ctx_threads:
+            t.start()
 
     def _ensure_contexts(self):
         """One context per GPU (CUDA contexts come up in parallel threads); the profiles are added to the first one and
@@ -391,24 +408,15 @@ class B200Searcher:
             if all(c is not None for c in self.ctxs):
                 return
             import time
-            errors = []
             t0 = time.perf_counter()
-
-            def create(k):
-                try:
-                    self.ctxs[k] = capi.Context(self.devices[k])
-                except Exception as e:
-                    errors.append(e)
-            th = [threading.Thread(target=create, args=(k,)) for k in range(1, len(self.devices))]
-            for t in th:
-                t.start()
-            create(0)
-            prepared = [capi.prepare_hmm(h) for h in self.hmms] if not errors else []
-            for t in th:
+            self.start_contexts()
+            prepared = [capi.prepare_hmm(h) for h in self.hmms]
+            for t in self._ctx_threads or []:
                 t.join()
-            if errors:
+            self._ctx_threads = None
+            if self._ctx_errors:
                 self.close()
-                raise errors[0]
+                raise self._ctx_errors[0]
             c0 = self.ctxs[0]
             c0.set_opts(F1=self.opts.F1, F2=self.opts.F2, F3=self.opts.F3, do_bias=not self.opts.nobias,
                         do_null2=not self.opts.nonull2, do_max=self.opts.max)

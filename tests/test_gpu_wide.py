@@ -66,12 +66,15 @@ def _funnel(oracle, hmms, seqs, opts=None):
     return want[1:].sum(), want[2:].sum(), want[3:].sum(), want[4:].sum()
 
 
-def test_search_wide_dna_profiles_nucleotide_reads(oracle, gpu_ctx_factory):
+@pytest.mark.parametrize("fullt", [False, True])
+def test_search_wide_dna_profiles_nucleotide_reads(oracle, gpu_ctx_factory, fullt, monkeypatch):
     """Config 3 as SURVEY 8(d) defines it: DNA profiles of M = 3 x the protein widths (up to 6,000) next to narrow ones,
     read-sized nucleotide targets + reverse complements.  Hits, strings, scores and every funnel count equal the oracle's,
     so the tiled SSV pass flags a superset of the exact candidates and the 16-bit Viterbi bound drops no passing pair."""
+    if fullt:   # the all-TMEM variant of the MSV rows (Q up to 26 words, 1,664-cell packs, all-TMEM tiles): off by default, kept exact
+        monkeypatch.setenv("PA_MSV_FULLT", "1")
     rng = np.random.default_rng(2048)
-    Ms = [300, 2047, 2048, 2500, 3500, 4100, 6000]
+    Ms = [300, 1100, 1500, 1663, 1664, 2047, 2048, 2500, 3500, 4100, 6000] if fullt else [300, 2047, 2048, 2500, 3500, 4100, 6000]
     hmms = [helpers.calibrated_hmm(f"wd{M}", M, seed=5000 + M, abc="dna", n=16, bg_mix=0.1) for M in Ms]
     reads = _targets("dna", hmms, 700, rng, 40, 260, plant_every=3)
     for i in range(0, len(reads), 6):
