@@ -380,7 +380,7 @@ class B200Searcher:
         self.devices = list(devices)
         self.ctxs = [None] * len(self.devices)
         self._setup_lock = threading.Lock()
-        self._ctx_threads, self._ctx_errors = None, []
+        self._ctx_threads, self._ctx_errors, self._committed = None, [], False
         if not defer:
             self._ensure_contexts()
 
@@ -405,7 +405,7 @@ class B200Searcher:
         committed ONCE for all of them (pa_commit_hmms_multi: configuration and table layout on the host are not repeated
         per GPU, only the upload is)."""
         with self._setup_lock:
-            if all(c is not None for c in self.ctxs):
+            if self._committed:
                 return
             import time
             t0 = time.perf_counter()
@@ -425,6 +425,7 @@ class B200Searcher:
                 c0.add_hmm(p)
             t2 = time.perf_counter()
             capi.commit_multi(self.ctxs)
+            self._committed = True
             self.setup_timing = {"create_contexts_s": t1 - t0, "add_profiles_s": t2 - t1, "commit_and_upload_s": time.perf_counter() - t2}
 
     def close(self):
@@ -432,6 +433,7 @@ class B200Searcher:
             if c is not None:
                 c.close()
         self.ctxs = [None] * len(self.ctxs)
+        self._committed = False
 
     def search_reads(self, nt: np.ndarray, off: np.ndarray, **kw):
         """Search concatenated ASCII reads (host arrays). See :meth:`search_source`."""
@@ -531,8 +533,7 @@ class B200Searcher:
             except Exception as e:  # surfaced after join
                 errors.append(e)
 
-        if any(c is None for c in self.ctxs):
-            self._ensure_contexts()
+        self._ensure_contexts()
         threads = [threading.Thread(target=work, args=(k,)) for k in range(len(self.ctxs))]
         for t in threads:
             t.start()

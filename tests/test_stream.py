@@ -96,7 +96,7 @@ class FakeCtx:
 
 def _searcher(ctxs):
     s = search.B200Searcher.__new__(search.B200Searcher)
-    s.opts, s.hmms, s.ctxs, s._setup_lock = search.SearchOptions(), [None], ctxs, threading.Lock()
+    s.opts, s.hmms, s.ctxs, s._setup_lock, s._committed = search.SearchOptions(), [None], ctxs, threading.Lock(), True
     return s
 
 
