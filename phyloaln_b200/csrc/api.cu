@@ -706,9 +706,15 @@ extern "C" int pa_commit_hmms_multi(pa_ctx **ctxs, int n) {
       c->pack_q = c0->pack_q;
       c->msv_impl = c0->msv_impl;
     }
-    rc = upload_tables(c, T);
-    if (rc) { if (k) c0->err = c->err; return rc; }
   }
+  // uploads run side by side, one host thread per GPU (pageable-memory copies are staged by the driver per device)
+  std::vector<int> rcs(n, 0);
+  std::vector<std::thread> th;
+  for (int k = 1; k < n; k++) th.emplace_back([&, k] { rcs[k] = upload_tables(ctxs[k], T); });
+  rcs[0] = upload_tables(c0, T);
+  for (auto &t : th) t.join();
+  for (int k = 0; k < n; k++)
+    if (rcs[k]) { if (k) c0->err = ctxs[k]->err; return rcs[k]; }
   return 0;
 }
 

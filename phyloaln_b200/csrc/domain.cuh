@@ -18,6 +18,9 @@
 
 namespace pa {
 
+#ifndef PA_DOM_MINB
+#define PA_DOM_MINB 4   // resident 128-thread blocks per SM the register budget must allow (4: 128 registers, 16 warps)
+#endif
 #define PA_MAXREG 64
 #define PA_NSAMPLES 200   // stochastic tracebacks per multi-domain region (HMMER: 200)
 #define PA_MAXSEG 16     // domain segments per sampled trace; more is an error (status bit 1), never a silent drop
@@ -482,7 +485,7 @@ __device__ int resolve_multidomain(const FwdTabs &T, const uint8_t *sub, int Lr,
   return nenv;
 }
 
-static __global__ void __launch_bounds__(128) domain_kernel(DomArgs a) {
+static __global__ void __launch_bounds__(128, PA_DOM_MINB) domain_kernel(DomArgs a) {
   const int lane = threadIdx.x & 31;
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   float *slab = a.scratch + (size_t)gw * a.slab_floats;

@@ -466,7 +466,10 @@ class B200Searcher:
                     avail = src.available()
                     a = cursor[0]
                     if avail - a >= min_chunk or (fin and avail > a):
-                        b = min(avail, a + chunk_reads)
+                        step = chunk_reads
+                        if fin:    # the end is known: finer ranges so that all GPUs finish together
+                            step = max(min_chunk, min(chunk_reads, -(-(avail - a) // (2 * len(self.ctxs)))))
+                        b = min(avail, a + step)
                         while b - a > 1 and 2 * src.nbytes(a, b) + 32 * (b - a) + 64 >= CHUNK_BYTE_LIMIT:
                             b = a + (b - a) // 2
                         cursor[0] = b
