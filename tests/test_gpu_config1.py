@@ -153,3 +153,50 @@ def test_two_gpu_searcher_gives_the_one_gpu_report():
         reports.append([[(r["name"], r["dom_idx"], r["hmmfrom"], r["hmmto"], r["alifrom"], r["alito"], r["model"], r["aligned"],
                           round(r["seq_bits"], 3)) for r in rep[hi]] for hi in range(len(GROUPS))])
     assert reports[0] == reports[1] and sum(map(len, reports[0])) == 777
+
+
+def test_config1_uniquified_ids_variant(oracle):
+    """config 1 repeats read ids, which the reference's read_fastx dictionary collapses (first position, last
+    sequence: 2,481 of 9,930 records survive -- the variant every other test pins).  The uniquified variant makes the harness
+    append #n to repeated ids BEFORE both pipelines see them, so every record is a target of its own (nothing is dropped
+    silently): GPU and oracle must then agree on all of them.  Records whose 'sequence' is not nucleotides (a FASTQ quirk of
+    the reference's 4-line parser; Biopython would raise on them) are set aside explicitly and counted."""
+    from phyloaln_b200 import hmmio, ingest, search
+    rd = os.path.join(C1, "reads")
+    rawdata = {"DMELA": [os.path.join(rd, "DMELA_1.fq.gz"), os.path.join(rd, "DMELA_2.fq.gz")],
+               "DWILL": [os.path.join(rd, "DWILL_1.fq.gz"), os.path.join(rd, "DWILL_2.fq.gz")]}
+    ing = ingest.Ingest(rawdata, merge_len=250, threads=4)
+    ids, seen = [], {}
+    for i in ing.ids():
+        n = seen.get(i, 0)
+        seen[i] = n + 1
+        ids.append(i if n == 0 else f"{i}#{n}")
+    assert len(set(ids)) == len(ids) == 9930
+    nt, off = ing.pack()
+    ing.close()
+    valid = search.valid_reads_mask(nt, off)
+    assert 0 < int((~valid).sum()) < 20                      # the junk records: reported, not dropped silently
+    keep = np.flatnonzero(valid)
+    raw = nt.tobytes().decode()
+    reads = [raw[int(off[k]):int(off[k + 1])] for k in keep]
+    kept_ids = [ids[k] for k in keep]
+    sub_off = np.zeros(len(reads) + 1, dtype=np.uint64)
+    sub_off[1:] = np.cumsum([len(r) for r in reads])
+    sub_nt = np.frombuffer("".join(reads).encode(), dtype=np.uint8)
+    hmms = [hmmio.read_hmm(os.path.join(C1, "ref_hmm", g + ".hmm")) for g in GROUPS]
+    s = search.B200Searcher(hmms)
+    rep, nframes, translated = s.search_and_report(sub_nt, sub_off, kept_ids, mol_type="codon", chunk_reads=4000)
+    s.close()
+    assert nframes == 6 and s.last_Z == 6 * len(reads)       # Z of the uniquified variant: every record counts
+    frames = [p for r in reads for _, p in oracle.six_frames(r, 1)]
+    names = [i + suf for i in kept_ids for suf in ("_pos1", "_pos2", "_pos3", "_rev_pos1", "_rev_pos2", "_rev_pos3")]
+    from oracle import report as orep
+    total = 0
+    for hi, h in enumerate(hmms):
+        ohits, _ = oracle.Profile.from_hmm(h).search(frames, nthreads=8, want_trace=False)
+        want = orep.apply_report(ohits, names, len(frames))
+        got = rep[hi]
+        assert [(w["name"], w["dom_idx"], w["hmmfrom"], w["hmmto"], w["iali"], w["jali"], w["model"], w["aligned"]) for w in want] == \
+               [(g["name"], g["dom_idx"], g["hmmfrom"], g["hmmto"], g["alifrom"], g["alito"], g["model"], g["aligned"]) for g in got], GROUPS[hi]
+        total += len(got)
+    assert total > 777                                       # more rows than the dictionary variant: no record was collapsed
