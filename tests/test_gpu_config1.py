@@ -196,7 +196,7 @@ def test_config1_uniquified_ids_variant(oracle):
         ohits, _ = oracle.Profile.from_hmm(h).search(frames, nthreads=8, want_trace=False)
         want = orep.apply_report(ohits, names, len(frames))
         got = rep[hi]
-        assert [(w["name"], w["dom_idx"], w["hmmfrom"], w["hmmto"], w["iali"], w["jali"], w["model"], w["aligned"]) for w in want] == \
+        assert [(names[w["target"]], w["dom_idx"], w["hmmfrom"], w["hmmto"], w["iali"], w["jali"], w["model"], w["aligned"]) for w in want] == \
                [(g["name"], g["dom_idx"], g["hmmfrom"], g["hmmto"], g["alifrom"], g["alito"], g["model"], g["aligned"]) for g in got], GROUPS[hi]
         total += len(got)
     assert total > 777                                       # more rows than the dictionary variant: no record was collapsed
