@@ -101,7 +101,7 @@ struct pa_ctx {
   int maxQ_wide = 0;         // widest striped state (words per lane) of msv_exact_wide_kernel
   DevBuf<uint16_t> d_bnd;    // tile-boundary scratch of msv_wide_kernel
   DevBuf<Pass1> d_wcand;     // its candidate list
-  DevBuf<float> d_fwdw;      // row scratch of fwd_wide_kernel
+  DevBuf<float> d_fwdw;      // per-CTA P rows of fwd_wide_kernel
   std::vector<DevPack> h_packs;   // packed narrow profiles (msv_pack_kernel)
   DevBuf<DevPack> d_packs;
   DevBuf<int> d_packmem;
@@ -964,10 +964,13 @@ static cudaError_t side_join(pa_ctx *ctx) {
 
 static cudaError_t dispatch_fwd_t(pa_ctx *ctx, int B, FwdTArgs &a, cudaStream_t st) {
   float *scratch = nullptr;
-  if (B > 64 && a.end > a.begin) {  // fwd_wide_kernel: rows in a per-warp global scratch sized for the widest profile
-    cudaError_t e = ctx->d_fwdw.ensure(fwd_wide_per_warp(ctx->maxB) * 4 * (size_t)fwd_wide_grid(a.end - a.begin, ctx->num_sms));
+  if (B > 64 && a.end > a.begin) {  // fwd_wide_kernel: one row of P per CTA, sized for the widest profile; the launches of the
+    // size classes run side by side on different streams, so each class has its own region
+    const size_t region = fwd_wide_per_cta(ctx->maxB) * (size_t)fwd_wide_grid_cap(ctx->num_sms);
+    cudaError_t e = ctx->d_fwdw.ensure(region * 4);
     if (e != cudaSuccess) return e;
-    scratch = ctx->d_fwdw.p;
+    const int cls = fwd_wide_class(B);
+    scratch = ctx->d_fwdw.p + region * (size_t)(cls == 96 ? 0 : cls == 128 ? 1 : cls == 192 ? 2 : 3);
   }
   return launch_fwd_b(B, a, ctx->num_sms, scratch, ctx->maxB, st, &ctx->stats.kernel_launches);
 }

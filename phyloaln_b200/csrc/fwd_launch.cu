@@ -25,15 +25,25 @@ static cudaError_t launch_fwd_t(FwdTArgs &a, int num_sms, cudaStream_t st, uint6
 }
 
 cudaError_t launch_fwd_b(int B, FwdTArgs &a, int num_sms, float *scratch, int maxB, cudaStream_t st, uint64_t *launched) {
-  if (B > 64) {  // wide profiles: run-time block size, one launch for all of them
+  if (B > 64) {  // wide profiles: run-time block size, rows of 3 x class x 32 floats in shared memory, one warp per CTA
     const unsigned long long n = a.end - a.begin;
     if (n == 0) return cudaSuccess;
     if (!scratch) return cudaErrorInvalidValue;
+    const size_t smem = (size_t)3 * fwd_wide_class(B) * 32 * sizeof(float);
+    cudaError_t e = cudaFuncSetAttribute(fwd_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(fwd_wide_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fwd_wide_kernel, 32, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) return cudaErrorInvalidConfiguration;
+    const unsigned long long cap = (unsigned long long)std::min(fwd_wide_grid_cap(num_sms), num_sms * per_sm);
     FwdWideArgs w;
     w.ft = a;
-    w.per_warp = fwd_wide_per_warp(maxB);
+    w.per_cta = fwd_wide_per_cta(maxB);
     w.scratch = scratch;
-    fwd_wide_kernel<<<fwd_wide_grid(n, num_sms), 128, 0, st>>>(w);
+    fwd_wide_kernel<<<(unsigned)std::min(n, cap), 32, smem, st>>>(w);
     ++*launched;
     return cudaGetLastError();
   }

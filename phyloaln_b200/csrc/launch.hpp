@@ -23,12 +23,11 @@ cudaError_t launch_msv_exact_wide(MsvExactWideArgs &ex, int num_sms, cudaStream_
 cudaError_t launch_vit16_class(int BH, int NW, Vit16Args &v, int num_sms, cudaStream_t st, uint64_t *launched);
 cudaError_t launch_vit_class(int Bv, int NW, VitArgs &v, int num_sms, cudaStream_t st, uint64_t *launched);
 
-// B <= 64: fwd_kernel_t<B>.  B > 64: fwd_wide_kernel over `scratch` (fwd_wide_grid(n) * 4 warps * fwd_wide_per_warp(maxB) floats)
+// B <= 64: fwd_kernel_t<B>.  B > 64: fwd_wide_kernel, one launch per size class (fwd_wide_class: what sets the shared-memory
+// rows and so the CTAs per SM); `scratch` holds fwd_wide_grid_cap(num_sms) rows of fwd_wide_per_cta(maxB) floats
 cudaError_t launch_fwd_b(int B, FwdTArgs &a, int num_sms, float *scratch, int maxB, cudaStream_t st, uint64_t *launched);
-inline size_t fwd_wide_per_warp(int maxB) { return (size_t)7 * maxB * 32; }
-inline int fwd_wide_grid(unsigned long long n, int num_sms) {
-  const unsigned long long g = (n + 3) / 4, cap = (unsigned long long)num_sms * 4;
-  return (int)(g < cap ? g : cap);
-}
+inline int fwd_wide_class(int B) { return B <= 64 ? B : B <= 96 ? 96 : B <= 128 ? 128 : B <= 192 ? 192 : 256; }
+inline size_t fwd_wide_per_cta(int maxB) { return (size_t)maxB * 32; }
+inline int fwd_wide_grid_cap(int num_sms) { return num_sms * 8; }
 
 }  // namespace pa

@@ -20,7 +20,7 @@
 //                         max-plus scan -- two CTA barriers per row.  Max-plus is order-independent, so the results
 //                         equal the single-warp kernels' bit for bit.
 //  fwd_wide_kernel        Forward filter with the canonical 32-lane blocked float order and a
-//                         run-time block size: rows in a per-warp global scratch (L1/L2-resident).
+//                         run-time block size: one warp per CTA, rows in shared memory, table reads batched.
 #pragma once
 #include "kernels.cuh"
 #include "msv_tmem.cuh"
@@ -526,31 +526,164 @@ static __global__ void __launch_bounds__(256, 1) vit_wide_kernel(VitArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Forward filter, run-time block size (B = ceil(M/32) > 64): fwd_parser over rows in global scratch
+// Forward filter, run-time block size (B = ceil(M/32) > 64)
+//
+// The arithmetic and its order are fwd_pair_t's (kernels.cuh), so scores are bit-identical to the oracle's; what
+// is specific to wide profiles is where the data sits.  One warp per CTA; the M, I, D rows of the pair live in
+// shared memory as [j][lane] blocks updated in place (3 x B x 128 bytes: as many CTAs per SM as that allows), the
+// D->D prefix products P(j) -- a property of the profile, not of the row -- are computed once per profile into a
+// per-CTA global row (each lane reads back only what it wrote), and the table reads of a row are issued
+// PA_FWDW_U cells deep before the dependent arithmetic, because with 2-6 resident warps per SM the L2 latency of
+// the transition/emission tables is what the kernel waits on (profiles/r2_ncu_config3_vit_fwd_domain.md: the
+// previous global-scratch version moved 232 GB of DRAM traffic per launch for its seven rows per warp).
 // ---------------------------------------------------------------------------------------------
+#define PA_FWDW_U 8
 struct FwdWideArgs {
   FwdTArgs ft;
-  float *scratch;     // per resident warp: 7 * maxW floats
-  size_t per_warp;
+  float *scratch;     // per CTA: per_cta floats (P row of the profile in hand)
+  size_t per_cta;
 };
 
-static __global__ void __launch_bounds__(128) fwd_wide_kernel(FwdWideArgs w) {
+static __global__ void __launch_bounds__(32) fwd_wide_kernel(FwdWideArgs w) {
+  extern __shared__ __align__(16) float s_fww[];
+  constexpr int U = PA_FWDW_U;
   const FwdTArgs &a = w.ft;
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-  const unsigned long long gw = (unsigned long long)blockIdx.x * wpb + wib;
-  float *sm = w.scratch + gw * w.per_warp;
-  for (unsigned long long i = a.begin + gw; i < a.end; i += (unsigned long long)gridDim.x * wpb) {
+  const int lane = threadIdx.x;
+  float *Pg = w.scratch + (size_t)blockIdx.x * w.per_cta + lane;  // P(j) = Pg[j * 32]
+  int last_h = -1;
+  float LPtot = 1.0f;
+  for (unsigned long long i = a.begin + blockIdx.x; i < a.end; i += gridDim.x) {
     const Pass2 r = a.f.in[i];
     const DevHmm &hm = a.f.hmms[r.h];
     const FwdTabs T = fwd_tabs(hm, a.f.tab);
+    const int B = T.B, W = T.W;
     const int L = (int)a.f.tg.len[r.t];
-    float mant;
-    const int e = fwd_parser(T, a.f.tg.dsq + a.f.tg.off[r.t], L, L, 1, sm, lane, &mant, nullptr, nullptr);
-    const float fwdsc = (float)((double)e * PA_LN2 + log((double)mant));
+    const uint8_t *p = a.f.tg.dsq + a.f.tg.off[r.t];
+    const int nv = min(B, max(0, T.M - lane * B));  // valid cells of this lane
+    float *Mr = s_fww + lane, *Ir = Mr + W, *Dr = Ir + W;
+    if ((int)r.h != last_h) {  // running products of DD along the lane's block, in fwd_pair_t's order
+      float LP = 1.0f;
+      for (int j = 0; j < nv; j++) {
+        const float y = __ldg(&T.trB[j * 32 + lane].y);
+        LP = j ? __fmul_rn(LP, y) : y;
+        Pg[j * 32] = LP;
+      }
+      LPtot = LP;
+      last_h = (int)r.h;
+    }
+    for (int j = 0; j < B; j++) { Mr[j * 32] = 0.0f; Ir[j * 32] = 0.0f; Dr[j * 32] = 0.0f; }
+    const XF xf = xf_config(L, 1);
+    float xN = 1.0f, xB = xf.tNB, xE = 0.0f, xJ = 0.0f, xC = 0.0f;
+    int etot = 0;
+    int xnext = L > 0 ? (int)p[0] : 0;
+    for (int row = 0; row < L; row++) {
+      const float *em = T.em + (size_t)xnext * W + lane;
+      if (row + 1 < L) xnext = (int)p[row + 1];
+      float mL = __shfl_up_sync(PA_FULL, Mr[(B - 1) * 32], 1), iL = __shfl_up_sync(PA_FULL, Ir[(B - 1) * 32], 1),
+            dL = __shfl_up_sync(PA_FULL, Dr[(B - 1) * 32], 1);
+      if (lane == 0) mL = iL = dL = 0.0f;
+      // M and I, in place: descending j reads the previous row's j-1 before it is overwritten
+      for (int jb = B - 1; jb >= 0; jb -= U) {
+        float4 A[U];
+        float2 Bz[U];
+        float e[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          const int j = jb - u;
+          if (j >= 0 && j < nv) {
+            const int c = j * 32 + lane;
+            A[u] = __ldg(T.trA + c);
+            const float4 q = __ldg(T.trB + c);
+            Bz[u] = make_float2(q.z, q.w);
+            e[u] = __ldg(em + j * 32);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          const int j = jb - u;
+          if (j >= 0 && j < nv) {
+            const int jm = j > 0 ? j - 1 : 0;
+            const float pm = j ? Mr[jm * 32] : mL, pi = j ? Ir[jm * 32] : iL, pd = j ? Dr[jm * 32] : dL;
+            float t = __fmul_rn(xB, A[u].x);
+            t = __fadd_rn(t, __fmul_rn(pm, A[u].y));
+            t = __fadd_rn(t, __fmul_rn(pi, A[u].z));
+            t = __fadd_rn(t, __fmul_rn(pd, A[u].w));
+            const float ni = __fadd_rn(__fmul_rn(Mr[j * 32], Bz[u].x), __fmul_rn(Ir[j * 32], Bz[u].y));
+            Mr[j * 32] = __fmul_rn(t, e[u]);
+            Ir[j * 32] = ni;
+          }
+        }
+      }
+      // D chain: in-lane serial prefix, scan across lanes, fix-up
+      float mcL = __shfl_up_sync(PA_FULL, Mr[(B - 1) * 32], 1);
+      if (lane == 0) mcL = 0.0f;
+      float LA = 0.0f;
+      for (int jb = 0; jb < B; jb += U) {
+        float2 Bx[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          const int j = jb + u;
+          if (j < nv) {
+            const float4 q = __ldg(T.trB + j * 32 + lane);
+            Bx[u] = make_float2(q.x, q.y);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          const int j = jb + u;
+          if (j < nv) {
+            const float av = __fmul_rn(j ? Mr[(j > 0 ? j - 1 : 0) * 32] : mcL, Bx[u].x);
+            LA = j ? __fadd_rn(av, __fmul_rn(LA, Bx[u].y)) : av;
+            Dr[j * 32] = LA;
+          }
+        }
+      }
+      float LP = nv > 0 ? LPtot : 1.0f;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const float a2 = __shfl_up_sync(PA_FULL, LA, o), p2 = __shfl_up_sync(PA_FULL, LP, o);
+        if (lane >= o) { LA = __fadd_rn(LA, __fmul_rn(LP, a2)); LP = __fmul_rn(LP, p2); }
+      }
+      float cin = __shfl_up_sync(PA_FULL, LA, 1);
+      if (lane == 0) cin = 0.0f;
+      float sacc = 0.0f;
+      for (int jb = 0; jb < B; jb += U) {
+        float P[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          const int j = jb + u;
+          if (j < nv) P[u] = Pg[j * 32];
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          const int j = jb + u;
+          if (j < nv) {
+            const float d = __fadd_rn(Dr[j * 32], __fmul_rn(P[u], cin));
+            Dr[j * 32] = d;
+            sacc = __fadd_rn(sacc, __fadd_rn(Mr[j * 32], d));
+          }
+        }
+      }
+      xE = lane_sum(sacc);
+      xN = __fmul_rn(xN, xf.tNN);
+      xJ = __fadd_rn(__fmul_rn(xJ, xf.tJJ), __fmul_rn(xE, xf.tEJ));
+      xC = __fadd_rn(__fmul_rn(xC, xf.tCC), __fmul_rn(xE, xf.tEC));
+      xB = __fadd_rn(__fmul_rn(xJ, xf.tJB), __fmul_rn(xN, xf.tNB));
+      if (xE > PA_RESCALE) {
+        const int e = ilogbf(xE);
+        for (int j = 0; j < B; j++) {
+          Mr[j * 32] = scalbnf(Mr[j * 32], -e); Ir[j * 32] = scalbnf(Ir[j * 32], -e); Dr[j * 32] = scalbnf(Dr[j * 32], -e);
+        }
+        xN = scalbnf(xN, -e); xJ = scalbnf(xJ, -e); xC = scalbnf(xC, -e); xB = scalbnf(xB, -e); xE = scalbnf(xE, -e);
+        etot += e;
+      }
+    }
+    const float mant = __fmul_rn(xC, xf.tCT);
+    const float fwdsc = (float)((double)etot * PA_LN2 + log((double)mant));
     const float seq = (float)((double)(fwdsc - r.filtersc) / PA_LN2);
     if (lane == 0 && (a.f.all_pairs || seq >= hm.thrF3)) {
       Pass4 o;
-      o.t = r.t; o.h = r.h; o.pad = 0; o.filtersc = r.filtersc; o.fexp = e; o.fmant = mant;
+      o.t = r.t; o.h = r.h; o.pad = 0; o.filtersc = r.filtersc; o.fexp = etot; o.fmant = mant;
       if (a.f.all_pairs) a.f.out[i] = o;
       else {
         unsigned long long idx = atomicAdd(a.f.out_count, 1ull);
