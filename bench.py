@@ -346,14 +346,15 @@ def main():
             # The dominant kernel is bound by instruction issue on the FMA + ALU pipes, not by HBM or the tensor cores
             # (max-plus recurrence with loop-carried dependences; emission table resident in TMEM).  achieved / peak are
             # in the SURVEY 8d unit: algorithmic 4 integer lane-ops per DP cell.
-            "roofline": {"bound": "int_dpx", "kernel": "msv_pack_kernel<2> + msv_tmem_kernel<17..32,2> (sticky-inf SSV: one fp16x2 HFMA2.RELU per two cells, no running maximum; packed profile tables in TMEM; inline exact MSV)",
+            "roofline": {"bound": "int_dpx", "kernel": "msv_pack_kernel<16,2> + msv_tmem_kernel<17..32,2> (sticky-inf SSV: one fp16x2 HFMA2.RELU per two cells, no running maximum; packed profile tables in TMEM; inline exact MSV)",
                          "achieved": 4.0 * msv_cells_s / 1e12, "peak": 4.0 * peak_cells / 1e12,
                          "unit": "T 16-bit lane-op/s (algorithmic 4 per DP cell)",
                          "frac": msv_cells_s / peak_cells,
                          # dram__bytes_read.sum + dram__bytes_write.sum of msv_pack_kernel from ncu captures of this command
                          # (profiles/r1d_ncu_full_kernels.md): 131,072 reads/step 128.0 MB + 20.8 MB (--set full); 524,288 reads/step
-                         # 1,426.3 MB + 83.9 MB with the L2 super-tile work order (metrics-only pass; 87.9 GB before it)
-                         "traffic": {131072: 148.8e6, 524288: 1510.2e6}.get(args.reads_per_step), "traffic_unit": "bytes per msv_pack_kernel launch",
+                         # 1,426.3 MB + 83.9 MB with the L2 super-tile work order (metrics-only pass; 87.9 GB before it);
+                         # 32,768 reads/step 38.6 MB (profiles/r2_ncu_msv_pack.md, --set full)
+                         "traffic": {32768: 38.6e6, 131072: 148.8e6, 524288: 1510.2e6}.get(args.reads_per_step), "traffic_unit": "bytes per msv_pack_kernel launch",
                          "msv_gcups": msv_cells_s / 1e9,
                          "useful_cells_per_clk_per_sm": msv_cells_s / sm_clk / 148.0,
                          "padded_cells_per_clk_per_sm": padded_cells_per_step / (ms_msv * 1e-3) / sm_clk / 148.0,
@@ -363,7 +364,7 @@ def main():
                          "frac_of_dpx_only_mix_peak": msv_cells_s / peak_cells_dpx,
                          "tmem_read_B_per_clk_per_sm": 2.0 * padded_cells_per_step / (ms_msv * 1e-3) / sm_clk / 148.0,
                          "binding_resource": "the half-rate HFMA2 pipe (16 HFMA2.RELU per 1,024-cell warp row = 32 pipe cycles) and warp "
-                                             "instruction issue (profiles/r1d_ncu_full_kernels.md)",
+                                             "instruction issue (profiles/r2_ncu_msv_pack.md: fp16 pipe 86.7 %, issue active 76 %)",
                          "traffic_note": "DRAM traffic is not the bound (1.5 GB per 2.19 s launch at 524,288 reads/step, 149 MB per 0.55 s at 131,072): "
                                          "targets (one L2-sized super-tile at a time) + tables in, candidate records out; emission tables live in TMEM",
                          "ginstr_per_s": dpx},
