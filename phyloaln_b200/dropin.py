@@ -24,7 +24,7 @@ import numpy as np
 from . import capi
 from .hmmer_text import write_text_report
 from .hmmio import read_hmm
-from .search import (ArraySource, B200Searcher, IngestSource, frame_suffix, parse_hmmsearch_parameters, report_index,
+from .search import (ArraySource, B200Searcher, IngestSource, frame_suffix, parse_hmmsearch_parameters, report_index, resolve_cutoffs,
                      rows_from_index, write_tblout)
 
 MAX_M = 8192   # widest profile of libphyloaln_b200 (csrc/wide.cuh); wider groups are left to the reference's own hmmsearch
@@ -170,6 +170,7 @@ def hmmsearch_step(outdir: str, groups, mol_type: str = "prot", gencode: int = 1
         hmms.append(h)
         kept.append(g)
     todo = kept
+    resolve_cutoffs(opts, hmms)        # --cut_ga / --cut_tc / --cut_nc: every profile's own thresholds, or an error
     tm["read_hmms_s"] = time.perf_counter() - t0
     # '--codon' forces no_reverse in the reference (lib/main.py:196-198)
     if codon:

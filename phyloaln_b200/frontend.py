@@ -17,7 +17,7 @@ import numpy as np
 from . import capi
 from .hmmer_text import write_text_report
 from .hmmio import read_hmm
-from .search import SearchParameterError, parse_hmmsearch_parameters, report, write_domtblout, write_tblout
+from .search import SearchParameterError, parse_hmmsearch_parameters, report, resolve_cutoffs, write_domtblout, write_tblout
 
 _WITH_ARG = {"-o", "--tblout", "--domtblout", "--pfamtblout", "-A", "--cpu", "--seed", "--textw", "--tformat", "-E", "--domE", "-T",
              "--domT", "--incE", "--incdomE", "-Z", "--domZ", "--F1", "--F2", "--F3"}
@@ -75,6 +75,7 @@ def hmmsearch_main(argv, device: int = 0) -> int:
     try:
         opts = parse_hmmsearch_parameters(opts_toks)
         hmm = read_hmm(pos[0])
+        resolve_cutoffs(opts, [hmm])
         names, seqs = read_fasta(pos[1])
         ctx = capi.Context(device)
         try:

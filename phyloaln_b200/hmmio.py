@@ -40,6 +40,7 @@ class HMM:
     effn: float = 1.0
     rf: str | None = None
     map: list | None = None
+    cutoffs: dict = field(default_factory=dict)  # {"GA": (per-seq bits, per-dom bits), "TC": ..., "NC": ...} when the file has them
 
     @property
     def M(self) -> int:
@@ -105,7 +106,29 @@ def read_hmm(path: str) -> HMM:
             st[tag] = (float(stats[2 * k]), float(stats[2 * k + 1]))
     return HMM(name=name.value.decode(), abc="amino" if abc.value == 0 else "dna", mat=mat, ins=ins, t=t,
                compo=None if np.isnan(compo).any() else compo, cons=cons.value.decode() or None, stats=st, nseq=nseq.value,
-               effn=effn.value, rf=rf.value.decode() or None, map=None if mp[0] < 0 else [int(x) for x in mp[:m]])
+               effn=effn.value, rf=rf.value.decode() or None, map=None if mp[0] < 0 else [int(x) for x in mp[:m]],
+               cutoffs=read_cutoffs(path))
+
+
+def _cutoff_line(tok):
+    """'GA 25.00 20.00;' -> (25.0, 20.0): Pfam-style per-sequence and per-domain bit-score thresholds."""
+    return float(tok[1].rstrip(";")), float(tok[2].rstrip(";"))
+
+
+def read_cutoffs(path: str) -> dict:
+    """GA / TC / NC header lines of the first model of an HMMER3 ASCII file (the native reader does not return them)."""
+    out = {}
+    with open(path) as fh:
+        for line in fh:
+            if line.startswith("HMM "):
+                break
+            tok = line.split()
+            if len(tok) >= 3 and tok[0] in ("GA", "TC", "NC"):
+                try:
+                    out[tok[0]] = _cutoff_line(tok)
+                except ValueError:
+                    raise HMMFormatError(f"{path}: bad {tok[0]} line") from None
+    return out
 
 
 def read_hmm_py(path: str) -> HMM:
@@ -116,12 +139,18 @@ def read_hmm_py(path: str) -> HMM:
         raise HMMFormatError(f"{path}: not a HMMER3 ASCII file")
     hdr = {}
     stats = {}
+    cutoffs = {}
     i = 1
     while i < len(lines) and not lines[i].startswith("HMM "):
         tok = lines[i].split()
         if len(tok) >= 2:
             if tok[0] == "STATS" and len(tok) >= 5:
                 stats[tok[2]] = (float(tok[3]), float(tok[4]))
+            elif tok[0] in ("GA", "TC", "NC") and len(tok) >= 3:
+                try:
+                    cutoffs[tok[0]] = _cutoff_line(tok)
+                except ValueError:
+                    raise HMMFormatError(f"{path}: bad {tok[0]} line") from None
             else:
                 hdr[tok[0]] = tok[1]
         i += 1
@@ -173,7 +202,7 @@ def read_hmm_py(path: str) -> HMM:
     return HMM(name=hdr.get("NAME", "unnamed"), abc=abc, mat=mat, ins=ins, t=t, compo=compo,
                cons="".join(cons) if len(cons) == M else None, stats=stats,
                nseq=int(hdr.get("NSEQ", 1)), effn=float(hdr.get("EFFN", 1.0)),
-               rf="".join(rf) if len(rf) == M else None, map=mp if len(mp) == M else None)
+               rf="".join(rf) if len(rf) == M else None, map=mp if len(mp) == M else None, cutoffs=cutoffs)
 
 
 def _fmt(v: float) -> str:
@@ -188,6 +217,10 @@ def write_hmm(hmm: HMM, path: str) -> None:
            f"ALPH  {'amino' if hmm.abc == 'amino' else 'DNA'}", f"RF    {'yes' if hmm.rf else 'no'}", "MM    no",
            "CONS  yes", "CS    no", f"MAP   {'yes' if hmm.map else 'no'}", f"NSEQ  {hmm.nseq}",
            f"EFFN  {hmm.effn:f}"]
+    for key in ("GA", "TC", "NC"):
+        if key in hmm.cutoffs:
+            a, b = hmm.cutoffs[key]
+            out.append(f"{key}    {a:.2f} {b:.2f};")
     for key in ("MSV", "VITERBI", "FORWARD"):
         if key in hmm.stats:
             a, b = hmm.stats[key]

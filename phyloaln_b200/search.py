@@ -49,6 +49,8 @@ class SearchOptions:
     nobias: bool = False
     nonull2: bool = False
     max: bool = False
+    cut: str | None = None        # "GA" | "TC" | "NC": --cut_ga / --cut_tc / --cut_nc, the profile's own bit-score thresholds
+    cutoffs: np.ndarray | None = None   # (n_hmm, 2) per-sequence / per-domain bits, filled by resolve_cutoffs()
     ignored: list = field(default_factory=list)
 
 
@@ -56,7 +58,9 @@ _FLOAT_OPTS = {"-E": "E", "--domE": "domE", "-T": "T", "--domT": "domT", "--incE
                "-Z": "Z", "--domZ": "domZ", "--F1": "F1", "--F2": "F2", "--F3": "F3"}
 _FLAG_OPTS = {"--nobias": "nobias", "--nonull2": "nonull2", "--max": "max"}
 _IGNORED_WITH_ARG = {"--cpu", "--seed", "-o", "-A", "--tblout", "--domtblout", "--pfamtblout", "--textw", "--tformat"}
-_IGNORED_FLAGS = {"--acc", "--noali", "--notextw", "--cut_ga", "--cut_nc", "--cut_tc"}
+_IGNORED_FLAGS = {"--acc", "--noali", "--notextw"}
+_CUT_OPTS = {"--cut_ga": "GA", "--cut_tc": "TC", "--cut_nc": "NC"}
+_CUT_EXCLUDES = ("-E", "-T", "--domE", "--domT", "--incE", "--incT", "--incdomE", "--incdomT")   # as HMMER's option table
 
 
 def parse_hmmsearch_parameters(params) -> SearchOptions:
@@ -82,14 +86,35 @@ def parse_hmmsearch_parameters(params) -> SearchOptions:
         elif t in _IGNORED_WITH_ARG:
             o.ignored.append(t)
             i += 2
+        elif t in _CUT_OPTS:
+            if o.cut is not None and o.cut != _CUT_OPTS[t]:
+                raise SearchParameterError(f"{t} is incompatible with --cut_{o.cut.lower()}")
+            o.cut = _CUT_OPTS[t]
+            i += 1
         elif t in _IGNORED_FLAGS:
-            if t.startswith("--cut"):
-                raise SearchParameterError(f"{t}: bit-score cutoffs (GA/TC/NC) are not supported by the B200 search path")
             o.ignored.append(t)
             i += 1
         else:
             raise SearchParameterError(f"unsupported hmmsearch option for the B200 search path: {t}")
+    if o.cut is not None:
+        for t in toks:
+            if t in _CUT_EXCLUDES:
+                raise SearchParameterError(f"--cut_{o.cut.lower()} is incompatible with option {t}")
     return o
+
+
+def resolve_cutoffs(opts: SearchOptions, hmms) -> None:
+    """--cut_ga / --cut_tc / --cut_nc: take every profile's own thresholds (HMMER's p7_pli_NewModelThresholds: per-sequence
+    score >= GA1, per-domain score >= GA2, E-values no longer decide).  A profile without them is an error, as in HMMER."""
+    if opts.cut is None:
+        opts.cutoffs = None
+        return
+    c = np.empty((len(hmms), 2), dtype=np.float64)
+    for i, h in enumerate(hmms):
+        if opts.cut not in h.cutoffs:
+            raise SearchParameterError(f"--cut_{opts.cut.lower()}: {opts.cut} bit thresholds unavailable on model {h.name}")
+        c[i] = h.cutoffs[opts.cut]
+    opts.cutoffs = c
 
 
 def frame_suffix(frame: int, nframes: int, translated: bool):
@@ -127,7 +152,11 @@ def report_index(hits: np.ndarray, target_names, Z: float, opts: SearchOptions, 
     ends = np.r_[starts[1:], len(order)]
     s_hmm = hh[starts]
     s_lnP = hits["seq_lnP"][order[starts]]
-    if opts.T is not None:
+    if opts.cut is not None:
+        if opts.cutoffs is None or len(opts.cutoffs) != n_hmm:
+            raise SearchParameterError(f"--cut_{opts.cut.lower()}: thresholds not resolved for these profiles (resolve_cutoffs)")
+        s_ok = hits["seq_bits"][order[starts]].astype(np.float64) >= opts.cutoffs[s_hmm, 0]
+    elif opts.T is not None:
         s_ok = hits["seq_bits"][order[starts]].astype(np.float64) >= opts.T
     else:
         s_ok = _exp_times(s_lnP, Zeff, opts.E)
@@ -161,7 +190,9 @@ def report_index(hits: np.ndarray, target_names, Z: float, opts: SearchOptions, 
         # all domains of the selected sequences, sequence by sequence
         cnt = ends[sel] - starts[sel]
         pos = np.repeat(starts[sel] - np.r_[0, np.cumsum(cnt)[:-1]], cnt) + np.arange(int(cnt.sum()))
-        if opts.domT is not None:
+        if opts.cut is not None:
+            d_ok = d_bits[pos] >= opts.cutoffs[h, 1]
+        elif opts.domT is not None:
             d_ok = d_bits[pos] >= opts.domT
         else:
             d_ok = _exp_times(d_lnP[pos], domZ, opts.domE)
@@ -377,6 +408,8 @@ class B200Searcher:
         .hmm files and CUDA start-up overlap) instead of here."""
         self.opts = options or SearchOptions()
         self.hmms = [h if isinstance(h, HMM) else read_hmm(h) for h in hmms]
+        if self.hmms:
+            resolve_cutoffs(self.opts, self.hmms)
         self.devices = list(devices)
         self.ctxs = [None] * len(self.devices)
         self._setup_lock = threading.Lock()

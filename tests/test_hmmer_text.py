@@ -164,9 +164,10 @@ def test_hmmsearch_front_end_on_the_gpu(tmp_path, oracle):
         sys.path.remove(SHIM)
     assert got == [(names[w["target"]], w["hmmfrom"], w["hmmto"], w["iali"], w["jali"], w["model"], w["aligned"], w["pp"]) for w in want]
     assert len(got) > 30
-    # unsupported option -> exit status 1 (the reference then reports "Error in hmmsearch command")
+    # an option that cannot be honoured -> exit status 1 (the reference then reports "Error in hmmsearch command"):
+    # --cut_ga on a profile without GA lines, as in HMMER
     rc = subprocess.run([sys.executable, exe, "--cut_ga", str(tmp_path / "g.hmm"), str(tmp_path / "t.fasta")], capture_output=True, text=True)
-    assert rc.returncode == 1 and "cut" in rc.stderr
+    assert rc.returncode == 1 and "GA bit thresholds unavailable" in rc.stderr
 
 
 def test_front_end_argument_errors_without_a_gpu(tmp_path, capsys):
@@ -175,7 +176,7 @@ def test_front_end_argument_errors_without_a_gpu(tmp_path, capsys):
     from phyloaln_b200 import frontend
     assert frontend.hmmsearch_main([]) == 1
     assert frontend.hmmsearch_main(["--cpu"]) == 1
-    assert frontend.hmmsearch_main(["--cut_ga", "a.hmm", "b.fa"]) == 1
+    assert frontend.hmmsearch_main(["--cut_ga", "-E", "1", "a.hmm", "b.fa"]) == 1
     assert frontend.hmmsearch_main(["--frobnicate", "a.hmm", "b.fa"]) == 1
     assert frontend.hmmsearch_main(["-o", str(tmp_path / "o.txt"), str(tmp_path / "missing.hmm"), str(tmp_path / "missing.fa")]) == 1
     err = capsys.readouterr().err

@@ -46,9 +46,65 @@ def test_parse_hmmsearch_parameters():
     o = p(["-T 25 --domT 20 -Z 1000 --domZ 10 --F1 0.1 --F2 0.01 --F3 1e-4 --max --nonull2"])
     assert (o.T, o.domT, o.Z, o.domZ, o.F1, o.F2, o.F3, o.max, o.nonull2) == (25, 20, 1000, 10, 0.1, 0.01, 1e-4, True, True)
     assert p([]).E == 10.0 and p(None).domE == 10.0
-    for bad in (["--cut_ga"], ["-E"], ["-E", "abc"], ["--bogus"]):
+    assert (p(["--cut_ga"]).cut, p([" --cut_tc", "--cpu", "2"]).cut, p(["--cut_nc --nobias"]).cut, p([]).cut) == ("GA", "TC", "NC", None)
+    for bad in (["--cut_ga", "-E", "1"], ["--cut_ga --cut_tc"], ["--domT", "3", "--cut_nc"], ["-E"], ["-E", "abc"], ["--bogus"]):
         with pytest.raises(SearchParameterError):
             p(bad)
+
+
+def test_model_cutoffs_replace_the_evalue_thresholds(tmp_path):
+    """--cut_ga / --cut_tc / --cut_nc (HMMER's p7_pli_NewModelThresholds): every profile reports with ITS OWN per-sequence and
+    per-domain bit-score thresholds, read from the GA / TC / NC lines of its file -- the same selection as -T / --domT with
+    those values, profile by profile; a profile without the lines is an error."""
+    from phyloaln_b200 import capi, hmmio, search, synth
+    rng = np.random.default_rng(12)
+    hmms = []
+    for i, cut in enumerate([{"GA": (25.0, 20.5), "TC": (30.0, 28.0)}, {"GA": (12.25, 3.0), "TC": (40.0, 1.0)}, {"GA": (60.0, 0.0), "TC": (0.0, 50.0)}]):
+        h = synth.random_hmm(f"c{i}", 20 + i, rng)
+        h.stats = {"MSV": (-8.0, 0.71), "VITERBI": (-9.0, 0.71), "FORWARD": (-4.0, 0.71)}
+        h.cutoffs = cut
+        path = str(tmp_path / f"c{i}.hmm")
+        hmmio.write_hmm(h, path)
+        for rd in (hmmio.read_hmm(path), hmmio.read_hmm_py(path)):      # native reader + header scan, and the Python statement
+            assert rd.cutoffs == cut
+        hmms.append(hmmio.read_hmm(path))
+    n = 600
+    hits = np.zeros(n, dtype=capi.HIT_DTYPE)
+    hits["hmm"] = rng.integers(0, 3, n)
+    hits["target"] = rng.integers(0, 150, n)
+    order = np.lexsort((hits["target"], hits["hmm"]))
+    hits = hits[order]
+    key = hits["hmm"].astype(np.int64) * 1000 + hits["target"]
+    first = np.r_[True, key[1:] != key[:-1]]
+    grp = np.cumsum(first) - 1
+    hits["dom_idx"] = np.arange(n) - np.flatnonzero(first)[grp]
+    seq_bits = rng.uniform(0, 70, grp.max() + 1).astype(np.float32)
+    seq_bits[:6] = [25.0, 12.25, 60.0, 30.0, 24.99, 12.24]            # values sitting on the thresholds
+    hits["seq_bits"] = seq_bits[grp]
+    hits["seq_lnP"] = -hits["seq_bits"]
+    hits["dom_bits"] = rng.uniform(-5, 60, n).astype(np.float32)
+    hits["dom_bits"][:4] = [20.5, 3.0, 0.0, 28.0]
+    hits["dom_lnP"] = -hits["dom_bits"]
+    name = lambda t: f"t{t:04d}"
+    for flag, tag in (("--cut_ga", "GA"), ("--cut_tc", "TC")):
+        o = search.parse_hmmsearch_parameters([flag])
+        search.resolve_cutoffs(o, hmms)
+        _, got = search.report_index(hits, name, 150, o, 3)
+        assert sum(len(v[0]) for v in got.values()) > 20
+        for h in range(3):
+            a, b = hmms[h].cutoffs[tag]
+            ot = search.parse_hmmsearch_parameters(["-T", repr(a), "--domT", repr(b)])
+            _, want = search.report_index(hits[hits["hmm"] == h], name, 150, ot, 3)
+            base = np.flatnonzero(hits["hmm"] == h)
+            if h in want:
+                assert np.array_equal(got[h][0], base[want[h][0]]) and got[h][1] == want[h][1]
+            else:
+                assert h not in got
+    o = search.parse_hmmsearch_parameters(["--cut_nc"])
+    with pytest.raises(search.SearchParameterError, match="NC bit thresholds unavailable on model c0"):
+        search.resolve_cutoffs(o, hmms)
+    with pytest.raises(search.SearchParameterError, match="not resolved"):
+        search.report_index(hits, name, 150, o, 3)
 
 
 def test_frame_naming_and_rows():
