@@ -848,6 +848,10 @@ extern "C" pa_fasta *pa_fasta_open(const char *path, char *err, int errlen) {
       size_t b = i + 1;
       while (b < r && t[b] != ' ') b++;
       const std::string_view id(t.data() + i + 1, b - i - 1);
+      if (recs.size() >= 0xfffffffeull || id.size() > 0xffffffffull) {   // 32-bit slots / id lengths: say so, never wrap
+        if (err && errlen > 0) snprintf(err, (size_t)errlen, "%s: more than 4,294,967,294 records or an id longer than 4 GiB", fj.path.c_str());
+        return nullptr;
+      }
       bool found = false;
       const size_t at = find_or_add(id, recs.size(), found);
       if (!found) {
