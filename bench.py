@@ -177,6 +177,7 @@ def cpu_reference_run(hmms, reads, threads: int, seconds_target: float = 15.0, s
             f"full pipeline in C, one OpenMP region over {threads} threads; MSV and Viterbi filters striped AVX2 "
             f"({'on' if O.lib().orc_have_avx2() else 'OFF - scalar'}), Forward/domain definition scalar; same STATS lines as the GPU arm; "
             f"{dt:.1f}s, {gcups / max(1, threads):.1f} GCUPS per thread, {int(ndom)} domains")
+    cpu_reference_run.last_seconds = dt
     return reads_per_s, desc, gcups
 
 
@@ -209,16 +210,18 @@ def main():
         threads = os.cpu_count() or 1
         reads = make_reads(max(2000, min(args.reads_per_step, 65536)), hmms, seed=1002)
         setup = cpu_reference_setup(hmms, threads)
-        vals, gcs = [], []
+        vals, gcs, secs = [], [], []
         desc = ""
         for s in range(args.warmup + args.steps):
             v, desc, gc = cpu_reference_run(hmms, reads, threads, seconds_target=max(4.0, 60.0 / max(1, args.warmup + args.steps)), setup=setup)
             if s >= args.warmup:
                 vals.append(v)
                 gcs.append(gc)
+                secs.append(cpu_reference_run.last_seconds)
         v = float(np.mean(vals)) if vals else 0.0
         line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(secs)) if secs else None,   # one step = the bounded sample in cpu_baseline.sample
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u8/s16/f32", "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc,
                                  "gcups": float(np.mean(gcs)) if gcs else None,
