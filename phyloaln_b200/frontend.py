@@ -164,7 +164,7 @@ def write_stockholm(path: str, name: str, rows: dict, mcols) -> None:
     is_match = [False] * alen
     for c in mcols:
         is_match[c] = True
-    width = max(len(k) for k in rows) + 2
+    width = max(len("#=GC RF"), max(len(k) for k in rows)) + 2     # the annotation label must not touch its text
     with open(path, "w") as fh:
         fh.write(f"# STOCKHOLM 1.0\n#=GF ID {name}\n\n")
         for sid, s in rows.items():
