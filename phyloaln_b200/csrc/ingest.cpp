@@ -285,7 +285,15 @@ struct Builder {
     if ((int64_t)n <= S.merge_len) __builtin_prefetch(&table[hash_bytes(p, n) & (table.size() - 1)]);
   }
 
-  explicit Builder(pa_ingest &s) : S(s) { chunks.emplace_back(); }
+  explicit Builder(pa_ingest &s) : S(s) {
+    chunks.emplace_back();
+    // test knob: the reference's chunk size (10 MB, lib/aln.py:283) scaled down so that the >1000-chunk fold can be
+    // checked against the reference on kilobytes of input (tests/golden/make_ingest_golden.py patches the same constant)
+    if (const char *e = getenv("PA_INGEST_EACH_SIZE")) {
+      const unsigned long long v = strtoull(e, nullptr, 10);
+      if (v > 0) each_size = v;
+    }
+  }
 
   void rotate_if_full() {  // lib/aln.py:313-318 + check_file_num
     if (data_size >= each_size) {

@@ -94,11 +94,54 @@ def make_cases(base):
                                     args=dict(file_format="guess", split_len=33, split_slide=10, merge_len=20), share="fasta_multi")
     cases["fastq_split"] = dict(rawdata={"SPA": ["A_1.fq.gz", "A_2.fq"], "SPB": ["B_1.fastq.gz"]},
                                 args=dict(file_format="guess", split_len=16, split_slide=8, merge_len=250), share="fastq_quirks")
+
+    # ---- the >1000-chunk fold (check_file_num, lib/aln.py:261-271): the reference starts a new chunk file every 10 MB of
+    # sequence and, at the 1000th, appends files 100..999 to files 0..99 and multiplies the chunk size by 10, so the final
+    # concatenation is no longer in emission order.  Reaching that with real sizes takes 10 GB of reads; here the SAME code runs
+    # with its constant `each_size = 10000000` replaced by a few bytes (run_reference(each_size=...)); the native ingest takes the
+    # same number through PA_INGEST_EACH_SIZE.  Up to three folds per case.
+    d = os.path.join(base, "fold_fastq", "in")
+    os.makedirs(d)
+    pool = [rnd_seq(rng, int(n)) for n in rng.integers(20, 41, 900)]
+    def reads(prefix, n):
+        return [(f"{prefix}{k}", pool[int(rng.integers(len(pool)))] if rng.random() < 0.25 else rnd_seq(rng, int(rng.integers(20, 41)))) for k in range(n)]
+    write(os.path.join(d, "X_1.fq.gz"), fq(reads("x", 3200)), gz=True)
+    write(os.path.join(d, "X_2.fq.gz"), fq(reads("y", 2400)), gz=True)
+    write(os.path.join(d, "Y_1.fq"), fq(reads("z", 1900)))
+    cases["fold_fastq"] = dict(rawdata={"SX": ["X_1.fq.gz", "X_2.fq.gz"], "SY": ["Y_1.fq"]}, each_size=1,
+                               args=dict(file_format="guess", split_len=None, split_slide=None, merge_len=250))
+    d = os.path.join(base, "fold_fasta", "in")
+    os.makedirs(d)
+    contigs = [(f"ctg{k} len", rnd_seq(rng, int(rng.integers(30, 90)))) for k in range(1500)]
+    for k in range(0, 1500, 7):
+        contigs[k] = (contigs[k][0], contigs[(k * 3) % 1500][1])          # duplicates: merge groups, no size added
+    write(os.path.join(d, "asm.fa"), fa(contigs, width=40))
+    cases["fold_fasta_split"] = dict(rawdata={"SP": ["asm.fa"]}, each_size=50, share="fold_fasta",
+                                     args=dict(file_format="fasta", split_len=16, split_slide=8, merge_len=250))
+    cases["fold_fasta_fastpath"] = dict(rawdata={"SP": ["asm.fa"], "SQ": ["asm.fa"]}, each_size=30, share="fold_fasta",
+                                        args=dict(file_format="guess", split_len=None, split_slide=None, merge_len=0))
+    cases["fold_fasta_merge"] = dict(rawdata={"SP": ["asm.fa"], "SQ": ["asm.fa"]}, each_size=64, share="fold_fasta",
+                                     args=dict(file_format="guess", split_len=None, split_slide=None, merge_len=60))
     return cases
 
 
-def run_reference(indir, rawdata, args, outdir):
-    import lib.aln as al
+def reference_aln(each_size=None):
+    """The reference's lib/aln.py as a module; with each_size, the same source with its chunk-size constant replaced."""
+    if each_size is None:
+        import lib.aln as al
+        return al
+    import types
+    path = os.path.join(REF, "lib", "aln.py")
+    src = open(path).read()
+    assert src.count("each_size = 10000000") == 1
+    mod = types.ModuleType(f"aln_each_size_{each_size}")
+    mod.__file__ = path
+    exec(compile(src.replace("each_size = 10000000", f"each_size = {int(each_size)}"), path, "exec"), mod.__dict__)
+    return mod
+
+
+def run_reference(indir, rawdata, args, outdir, each_size=None):
+    al = reference_aln(each_size)
     ns = Namespace(mol_type="dna", gencode=1, no_reverse=True, codon=False, cpu=1, **args)
     rd = {sp: [os.path.join(indir, f) for f in fs] for sp, fs in rawdata.items()}
     cwd = os.getcwd()
@@ -123,10 +166,18 @@ def main():
         cdir = os.path.join(base, name)
         os.makedirs(cdir, exist_ok=True)
         indir = os.path.join(base, c.get("share", name), "in")
-        run_reference(indir, c["rawdata"], c["args"], cdir)
-        json.dump(dict(rawdata=c["rawdata"], args=c["args"], indir=os.path.join(c.get("share", name), "in")),
-                  open(os.path.join(cdir, "case.json"), "w"), indent=1)
-        print(name, os.path.getsize(os.path.join(cdir, "all.raw.fasta")), "bytes")
+        run_reference(indir, c["rawdata"], c["args"], cdir, c.get("each_size"))
+        meta = dict(rawdata=c["rawdata"], args=c["args"], indir=os.path.join(c.get("share", name), "in"))
+        if c.get("each_size"):
+            meta["each_size"] = c["each_size"]
+        json.dump(meta, open(os.path.join(cdir, "case.json"), "w"), indent=1)
+        size = os.path.getsize(os.path.join(cdir, "all.raw.fasta"))
+        if c.get("each_size"):                     # the fold cases are larger: keep their raw fasta compressed
+            data = open(os.path.join(cdir, "all.raw.fasta"), "rb").read()
+            with gzip.GzipFile(os.path.join(cdir, "all.raw.fasta.gz"), "wb", mtime=0) as g:
+                g.write(data)
+            os.remove(os.path.join(cdir, "all.raw.fasta"))
+        print(name, size, "bytes")
 
 
 if __name__ == "__main__":

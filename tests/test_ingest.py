@@ -17,24 +17,40 @@ GOLD = os.path.join(HERE, "golden")
 CASES = sorted(os.path.basename(os.path.dirname(p)) for p in glob.glob(os.path.join(GOLD, "ingest", "*", "case.json")))
 
 
+def _golden_bytes(path):
+    import gzip
+    if os.path.exists(path):
+        return open(path, "rb").read()
+    return gzip.open(path + ".gz", "rb").read()
+
+
 def test_cases_exist():
-    assert len(CASES) >= 7
+    assert len(CASES) >= 11 and sum(c.startswith("fold_") for c in CASES) == 4
 
 
 @pytest.mark.parametrize("case", CASES)
-def test_ingest_matches_reference_prepare_target(case, tmp_path):
+def test_ingest_matches_reference_prepare_target(case, tmp_path, monkeypatch):
     cdir = os.path.join(GOLD, "ingest", case)
     c = json.load(open(os.path.join(cdir, "case.json")))
     indir = os.path.join(GOLD, "ingest", c["indir"])
     rawdata = {sp: [os.path.join(indir, f) for f in fs] for sp, fs in c["rawdata"].items()}
     args = Namespace(cpu=3, **c["args"])
+    if "each_size" in c:     # the >1000-chunk fold cases: the reference ran with its 10 MB chunk constant replaced by this
+        monkeypatch.setenv("PA_INGEST_EACH_SIZE", str(c["each_size"]))
     ing = ingest.prepare_target(rawdata, args, outdir=str(tmp_path))
     for f in ("all.raw.fasta", "total_counts.tsv", "merged_redundance.txt"):
-        assert open(os.path.join(tmp_path, f), "rb").read() == open(os.path.join(cdir, f), "rb").read(), (case, f)
+        assert open(os.path.join(tmp_path, f), "rb").read() == _golden_bytes(os.path.join(cdir, f)), (case, f)
     # record table is consistent with the text
-    want = open(os.path.join(cdir, "all.raw.fasta")).read()
+    want = _golden_bytes(os.path.join(cdir, "all.raw.fasta")).decode()
     ids = [line[1:] for line in want.splitlines() if line.startswith(">")]
     assert ing.ids() == ids
+    if "each_size" in c:
+        # the fold really happened: the file order is a non-trivial permutation of the emission order, and the ids the
+        # search path reads in emission order (pa_ingest_emitted_ids) map onto the file through pa_ingest_final_order
+        perm = ing.final_order()
+        assert sorted(perm.tolist()) == list(range(len(ids))) and not (perm == np.arange(len(ids))).all()
+        emitted = ing.ids_of(np.arange(len(ids)))
+        assert [emitted[int(k)] for k in perm] == ids
     ing.close()
 
 
