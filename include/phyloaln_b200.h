@@ -222,7 +222,9 @@ int pa_merge_hists(pa_ctx *ctx, int32_t nchains, const int32_t *chain_off, const
 /* ---- native target preparation (host only; replaces the body of prepare_target(), lib/aln.py:274-433,
  * and the text iteration of read_fastx(return_iter=True), lib/library.py:157-176).  Files are inflated and
  * parsed in parallel; tagging, sliding-window splitting, exact-duplicate merging and the 10 MB chunk order are
- * reproduced byte for byte (all.raw.fasta, total_counts.tsv, merged_redundance.txt). ---- */
+ * reproduced byte for byte (all.raw.fasta, total_counts.tsv, merged_redundance.txt).  Test knob: the environment
+ * variable PA_INGEST_EACH_SIZE replaces the 10,000,000-byte chunk size (lib/aln.py:283) so that the >1000-chunk fold can
+ * be compared with the reference on small inputs; leave it unset in production. ---- */
 typedef struct pa_ingest pa_ingest;
 pa_ingest *pa_ingest_create(int merge_len, int split_len /* 0 = off */, int split_slide /* 0 = split_len/2 */, int nthreads);
 void pa_ingest_destroy(pa_ingest *ing);
