@@ -17,6 +17,8 @@
 //   * chunks of >= 10 MB of sequence; past 1000 chunks, chunks 100..999 fold into chunk (i % 100) and the
 //     chunk size grows tenfold, which permutes the final record order exactly as the reference does
 // Host-only code (zlib); lives in libphyloaln_b200.so behind the pa_ingest_* C ABI.
+#include <sys/mman.h>
+#include <sys/stat.h>
 #include <zlib.h>
 
 #include <atomic>
@@ -28,6 +30,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <new>
 #include <string>
 #include <string_view>
 #include <thread>
@@ -45,6 +48,13 @@ struct FileJob {
   std::string text;
   std::vector<std::pair<uint64_t, uint64_t>> lines;  // (offset, length after rstrip)
   std::string error;
+  // unsplit FASTQ (preformat): every record the pass can emit, already written as '>' tag '\n' seq '\n' into one
+  // buffer that outlives the file text, with the hashes of its sequence and tag; the serial pass then only decides
+  struct PreRec { uint64_t off, seq_len, hseq, hid; uint32_t tag_len; };
+  std::vector<PreRec> pre;
+  char *fmt = nullptr;
+  size_t fmt_bytes = 0;
+  bool preformatted = false;
 };
 
 bool inflate_file(FileJob &fj) {
@@ -100,16 +110,66 @@ void split_lines(FileJob &fj) {
   }
 }
 
+// Large, long-lived buffers (record texts, hash tables, record tables) come straight from mmap with transparent huge
+// pages requested: the single pass touches gigabytes of fresh memory and random table slots, and 4 KB pages make that one
+// page fault per ~20 records plus a TLB miss per probe.
+constexpr size_t HUGE_MIN = (size_t)2 << 20;
+inline void *big_alloc(size_t bytes) {
+  bytes = (bytes + HUGE_MIN - 1) & ~(HUGE_MIN - 1);
+  // over-allocate by one huge page and give the unaligned head and the tail back: the region is 2 MB-aligned
+  char *raw = static_cast<char *>(mmap(nullptr, bytes + HUGE_MIN, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0));
+  if (raw == MAP_FAILED) throw std::bad_alloc();
+  char *p = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(raw) + HUGE_MIN - 1) & ~(uintptr_t)(HUGE_MIN - 1));
+  if (p > raw) munmap(raw, (size_t)(p - raw));
+  const size_t tail = (size_t)((raw + bytes + HUGE_MIN) - (p + bytes));
+  if (tail) munmap(p + bytes, tail);
+#ifdef MADV_HUGEPAGE
+  madvise(p, bytes, MADV_HUGEPAGE);
+#endif
+  return p;
+}
+inline void big_free(void *p, size_t bytes) {
+  bytes = (bytes + HUGE_MIN - 1) & ~(HUGE_MIN - 1);
+  munmap(p, bytes);
+}
+template <class T>
+struct BigAlloc {   // std::vector allocator: mmap above 2 MB, malloc below
+  using value_type = T;
+  BigAlloc() = default;
+  template <class U> BigAlloc(const BigAlloc<U> &) {}
+  T *allocate(size_t n) {
+    const size_t b = n * sizeof(T);
+    if (b >= HUGE_MIN) return static_cast<T *>(big_alloc(b));
+    void *p = malloc(b ? b : 1);
+    if (!p) throw std::bad_alloc();
+    return static_cast<T *>(p);
+  }
+  void deallocate(T *p, size_t n) {
+    const size_t b = n * sizeof(T);
+    if (b >= HUGE_MIN) big_free(p, b);
+    else free(p);
+  }
+  template <class U> bool operator==(const BigAlloc<U> &) const { return true; }
+  template <class U> bool operator!=(const BigAlloc<U> &) const { return false; }
+};
+template <class T> using BigVec = std::vector<T, BigAlloc<T>>;
+
 // bump allocator: keys, tags and record texts are never freed individually; pointers stay valid until the ingest is destroyed
 struct Arena {
-  std::vector<std::unique_ptr<char[]>> slabs;
+  std::vector<std::pair<char *, size_t>> slabs;
   size_t left = 0;
   char *cur = nullptr;
+  Arena() = default;
+  Arena(const Arena &) = delete;
+  Arena &operator=(const Arena &) = delete;
+  ~Arena() {
+    for (auto &sl : slabs) big_free(sl.first, sl.second);
+  }
   char *alloc(size_t n) {
     if (n > left) {
-      const size_t sz = std::max<size_t>(n, (size_t)16 << 20);
-      slabs.emplace_back(new char[sz]);
-      cur = slabs.back().get();
+      const size_t sz = std::max<size_t>(n, (size_t)32 << 20);
+      slabs.emplace_back(static_cast<char *>(big_alloc(sz)), sz);
+      cur = slabs.back().first;
       left = sz;
     }
     char *d = cur;
@@ -138,6 +198,60 @@ inline uint64_t hash_bytes(const char *p, size_t n) {  // 8 bytes at a time, mul
   memcpy(&w, p, n);
   h = (h ^ w ^ (n << 56)) * 0xFF51AFD7ED558CCDull;
   return h ^ (h >> 32);
+}
+
+// FASTQ id: header line without its first '@', ' ' -> '_' (lib/aln.py:296: line.replace('@', '', 1).replace(' ', '_'))
+inline void put_fastq_id(char *d, const char *id, size_t n) {
+  for (size_t i = 0; i < n; i++) d[i] = id[i] == ' ' ? '_' : id[i];
+}
+
+// Unsplit FASTQ, on the file's worker thread: what the reference's loop does with such a file is fixed by the line
+// numbers alone -- record r is emitted iff line 4r starts with '@' and has an id, and line 4r+1 exists (lib/aln.py:
+// 293-318 with line_num % 4; the state `seqid` never survives a record) -- so every candidate record is written here in
+// its final form '>' id suffix '\n' seq '\n' and hashed, and the order-dependent pass is left with the merge decisions.
+void preformat(FileJob &fj, int merge_len) {
+  const std::string &T = fj.text;
+  const std::string suffix = "_PhAlTag_" + fj.species + "_fastx" + std::to_string(fj.file_index);
+  const size_t nlines = fj.lines.size();
+  size_t bytes = 0, nvalid = 0;
+  for (size_t r = 0; 4 * r + 1 < nlines; r++) {
+    const auto &hl = fj.lines[4 * r];
+    if (hl.second > 1 && T[hl.first] == '@') {
+      if (hl.second - 1 + suffix.size() >= (1ull << 32)) { fj.error = "FASTQ identifier longer than 4 GiB in " + fj.path; return; }
+      bytes += (hl.second - 1) + suffix.size() + fj.lines[4 * r + 1].second + 3;
+      nvalid++;
+    }
+  }
+  fj.pre.reserve(nvalid);
+  if (bytes) {
+    fj.fmt = static_cast<char *>(big_alloc(bytes));
+    fj.fmt_bytes = bytes;
+  }
+  size_t pos = 0;
+  for (size_t r = 0; 4 * r + 1 < nlines; r++) {
+    const auto &hl = fj.lines[4 * r];
+    if (!(hl.second > 1 && T[hl.first] == '@')) continue;
+    const auto &sl = fj.lines[4 * r + 1];
+    const size_t idl = hl.second - 1, tl = idl + suffix.size();
+    char *d = fj.fmt + pos;
+    d[0] = '>';
+    put_fastq_id(d + 1, T.data() + hl.first + 1, idl);
+    memcpy(d + 1 + idl, suffix.data(), suffix.size());
+    d[1 + tl] = '\n';
+    memcpy(d + 2 + tl, T.data() + sl.first, sl.second);
+    d[2 + tl + sl.second] = '\n';
+    FileJob::PreRec R;
+    R.off = pos;
+    R.tag_len = (uint32_t)tl;
+    R.seq_len = sl.second;
+    R.hseq = (int64_t)sl.second <= merge_len ? hash_bytes(d + 2 + tl, sl.second) : 0;
+    R.hid = hash_bytes(d + 1, tl);
+    fj.pre.push_back(R);
+    pos += tl + sl.second + 3;
+  }
+  std::string().swap(fj.text);
+  std::vector<std::pair<uint64_t, uint64_t>>().swap(fj.lines);
+  fj.preformatted = true;
 }
 
 // one duplicate group: the sequence, the representative's tag, then a chain of further tags
@@ -170,12 +284,12 @@ struct RecStore {
   uint64_t n = 0;
   std::atomic<uint64_t> published{0};
   ~RecStore() {
-    for (uint64_t b = 0; b * BLK < n; b++) delete[] blocks[b];
+    for (uint64_t b = 0; b * BLK < n; b++) big_free(blocks[b], BLK * sizeof(Rec));
   }
   bool push(const Rec &r) {
     if (n % BLK == 0) {
       if (n / BLK >= (1u << 16)) return false;
-      blocks[n / BLK] = new Rec[BLK];
+      blocks[n / BLK] = static_cast<Rec *>(big_alloc(BLK * sizeof(Rec)));
     }
     blocks[n / BLK][n % BLK] = r;
     n++;
@@ -198,6 +312,7 @@ struct pa_ingest {
   std::mutex wait_mu;
   // results
   Arena text;       // record texts
+  std::vector<std::pair<char *, size_t>> fmt_bufs;   // preformatted record texts of the unsplit FASTQ files (FileJob::fmt)
   RecStore recs;    // emission order
   std::vector<uint64_t> final_order;  // emission index of every final position; empty = identity (no chunk fold happened)
   uint64_t id_dups = 0;               // records whose id repeats an earlier record's id (read_fastx keeps one entry per id)
@@ -209,6 +324,9 @@ struct pa_ingest {
   std::vector<uint64_t> id_off, id_len, seq_off, seq_len;
   ~pa_ingest() {
     if (runner.joinable()) runner.join();
+    for (auto &b : fmt_bufs) big_free(b.first, b.second);
+    for (auto &f : files)
+      if (f.fmt) big_free(f.fmt, f.fmt_bytes);     // a file that was formatted but never reached by the pass (error exit)
   }
 };
 
@@ -222,12 +340,12 @@ struct Builder {
   size_t cur = 0;
   uint64_t data_size = 0, each_size = 10000000;
   // open-addressing table (hash, group index + 1); groups in insertion order == Python dict order
-  std::vector<std::pair<uint64_t, uint64_t>> table = std::vector<std::pair<uint64_t, uint64_t>>(1 << 16);
-  std::vector<MergeGroup> groups;
-  std::vector<ExtraTag> extras;
+  BigVec<std::pair<uint64_t, uint64_t>> table = BigVec<std::pair<uint64_t, uint64_t>>(1 << 16);
+  BigVec<MergeGroup> groups;
+  BigVec<ExtraTag> extras;
   Arena arena;
   // hashes of the ids seen so far: counts the records whose id is (very probably) not new
-  std::vector<uint64_t> idtab = std::vector<uint64_t>(1 << 16, 0);
+  BigVec<uint64_t> idtab = BigVec<uint64_t>(1 << 16, 0);
   uint64_t n_ids = 0;
 
   int64_t find(std::string_view seq, uint64_t h) const {
@@ -243,7 +361,7 @@ struct Builder {
   }
   void insert(uint64_t h, uint64_t gi) {
     if ((groups.size() + 1) * 2 > table.size()) {
-      std::vector<std::pair<uint64_t, uint64_t>> nt(table.size() * 2);
+      BigVec<std::pair<uint64_t, uint64_t>> nt(table.size() * 2);
       const size_t mask = nt.size() - 1;
       for (const auto &e : table)
         if (e.second) {
@@ -260,11 +378,11 @@ struct Builder {
   }
   // Set of 64-bit id hashes (0 = empty slot).  A hit counts as "this id was seen before"; the rare false positive of a
   // hash collision only sends the caller down the exact path (dropin._dictionary_view compares the ids themselves).
-  void note_id(const char *id, uint32_t len) {
-    uint64_t h = hash_bytes(id, len);
+  void note_id(const char *id, uint32_t len) { note_id_hash(hash_bytes(id, len)); }
+  void note_id_hash(uint64_t h) {
     if (h == 0) h = 1;
     if ((n_ids + 1) * 2 > idtab.size()) {
-      std::vector<uint64_t> nt(idtab.size() * 2, 0);
+      BigVec<uint64_t> nt(idtab.size() * 2, 0);
       const size_t mask = nt.size() - 1;
       for (const uint64_t e : idtab)
         if (e) {
@@ -280,11 +398,52 @@ struct Builder {
       if (idtab[i] == h) { S.id_dups++; return; }
     }
   }
-  // look-ahead of the single pass: pull the table slot of an upcoming sequence into the cache
-  void prefetch_seq(const char *p, size_t n) const {
-    if ((int64_t)n <= S.merge_len) __builtin_prefetch(&table[hash_bytes(p, n) & (table.size() - 1)]);
+  // look-ahead of the single pass: pull the table slots of an upcoming record into the cache
+  void prefetch_hashes(uint64_t hseq, uint64_t hid) const {
+    __builtin_prefetch(&table[hseq & (table.size() - 1)]);
+    __builtin_prefetch(&idtab[(hid ? hid : 1) & (idtab.size() - 1)]);
   }
-
+  // size the tables for about n records before the pass starts, so that they are not rebuilt log2(n) times on the way
+  void reserve(uint64_t n, bool with_groups) {
+    if (!groups.empty() || n_ids) return;
+    n = std::min<uint64_t>(n, 1ull << 31);
+    size_t cap = idtab.size();
+    while (cap < 2 * (n + 1)) cap <<= 1;
+    if (cap > idtab.size()) idtab.assign(cap, 0);
+    if (with_groups && cap > table.size()) {
+      table.assign(cap, {0, 0});
+      groups.reserve((size_t)n);
+    }
+  }
+  // emit() for a preformatted record (FileJob::pre): same decisions in the same order; the text is already final and
+  // stays where it is -- an emitted record points at it, a merged one contributes its tag from it
+  bool emit_pre(char *d, uint32_t tl, uint64_t sl, uint64_t hseq, uint64_t hid) {
+    const bool small = (int64_t)sl <= S.merge_len;
+    if (small) {
+      const int64_t gi = find(std::string_view(d + 2 + tl, sl), hseq);
+      if (gi >= 0) {
+        extras.push_back({d + 1, tl, -1});
+        MergeGroup &g = groups[(size_t)gi];
+        if (g.extra_tail >= 0) extras[(size_t)g.extra_tail].next = (int64_t)extras.size() - 1;
+        else g.extra_head = (int64_t)extras.size() - 1;
+        g.extra_tail = (int64_t)extras.size() - 1;
+        return true;
+      }
+    }
+    if (!add_record(cur, d, tl, sl, true, &hid)) return false;
+    data_size += sl;
+    rotate_if_full();
+    if (small) {
+      MergeGroup g;
+      g.key = d + 2 + tl;
+      g.key_len = (uint32_t)sl;
+      g.tag = d + 1;
+      g.tag_len = tl;
+      insert(hseq, groups.size());
+      groups.push_back(g);
+    }
+    return true;
+  }
   explicit Builder(pa_ingest &s) : S(s) {
     chunks.emplace_back();
     // test knob: the reference's chunk size (10 MB, lib/aln.py:283) scaled down so that the >1000-chunk fold can be
@@ -310,9 +469,10 @@ struct Builder {
     }
   }
   // append a finished record (text already in S.text) to chunk `ch`
-  bool add_record(size_t ch, const char *text, uint32_t id_len, uint64_t body_len, bool has_body) {
+  bool add_record(size_t ch, const char *text, uint32_t id_len, uint64_t body_len, bool has_body, const uint64_t *id_hash = nullptr) {
     const uint64_t idx = S.recs.n;
-    note_id(text + 1, id_len);
+    if (id_hash) note_id_hash(*id_hash);
+    else note_id(text + 1, id_len);
     auto &runs = chunks[ch];
     if (!runs.empty() && runs.back().first + runs.back().second == idx) runs.back().second++;
     else runs.emplace_back(idx, 1);
@@ -382,7 +542,10 @@ int run_pipeline(pa_ingest *S) {
         cv.wait(lk, [&] { return stop || i < consumed + ahead; });
         if (stop) break;
       }
-      if (inflate_file(S->files[i])) split_lines(S->files[i]);
+      if (inflate_file(S->files[i])) {
+        split_lines(S->files[i]);
+        if (S->files[i].format == 1 && !S->split_len) preformat(S->files[i], S->merge_len);
+      }
       {
         std::lock_guard<std::mutex> lk(mu);
         ready[i] = 1;
@@ -428,6 +591,14 @@ int run_pipeline(pa_ingest *S) {
       t_wait += now() - w0;
     }
     if (!fj.error.empty()) { S->err = fj.error; ok = false; break; }
+    if (fi == 0) {  // records expected over all files, from the first file's record density per input byte
+      struct stat st;
+      double first = 0, total = 0;
+      for (size_t k = 0; k < nfiles; k++)
+        if (stat(S->files[k].path.c_str(), &st) == 0) { total += (double)st.st_size; if (k == 0) first = (double)st.st_size; }
+      const size_t nrec0 = fj.preformatted ? fj.pre.size() : fj.lines.size() / (fj.format == 1 ? 4 : 2);
+      if (first > 0) B.reserve((uint64_t)((double)nrec0 * (total / first) * 1.05), S->merge_len > 0);
+    }
     int64_t *count = nullptr;
     for (auto &kv : S->counts)
       if (kv.first == fj.species) count = &kv.second;
@@ -455,16 +626,21 @@ int run_pipeline(pa_ingest *S) {
       }
       if (pos) s.erase(0, pos);
     };
+    if (fj.preformatted) {   // unsplit FASTQ: texts and hashes come from the worker thread (preformat), table slots prefetched
+      const size_t n = fj.pre.size();
+      for (size_t k = 0; k < n && ok; k++) {
+        if (k + 12 < n) B.prefetch_hashes(fj.pre[k + 12].hseq, fj.pre[k + 12].hid);
+        const FileJob::PreRec &R = fj.pre[k];
+        ok = B.emit_pre(fj.fmt + R.off, R.tag_len, R.seq_len, R.hseq, R.hid);
+        (*count)++;
+      }
+      if (fj.fmt) { S->fmt_bufs.emplace_back(fj.fmt, fj.fmt_bytes); fj.fmt = nullptr; }
+      std::vector<FileJob::PreRec>().swap(fj.pre);
+    }
     uint64_t line_num = 0;
-    const size_t nlines = fj.lines.size();
-    constexpr size_t AHEAD = 48;   // lines: 12 FASTQ records ahead of the pass
     for (const auto &ln : fj.lines) {
       const char *lp = T.data() + ln.first;
       const uint64_t ll = ln.second;
-      if (fj.format == 1 && !split_len && (line_num & 3) == 1 && line_num + AHEAD < nlines) {
-        const auto &la = fj.lines[line_num + AHEAD];
-        B.prefetch_seq(T.data() + la.first, la.second);
-      }
       if (fj.format == 1 && ll > 0 && lp[0] == '@' && line_num % 4 == 0) {
         seqid.assign(lp + 1, ll - 1);
         for (char &c : seqid)
