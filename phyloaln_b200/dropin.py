@@ -161,7 +161,7 @@ def hmmsearch_step(outdir: str, groups, mol_type: str = "prot", gencode: int = 1
     searcher.start_contexts()          # CUDA start-up on every GPU runs while the profiles are parsed
     hmms, kept = [], []
     from concurrent.futures import ThreadPoolExecutor
-    with ThreadPoolExecutor(min(8, os.cpu_count() or 1)) as ex:     # the native reader releases the GIL
+    with ThreadPoolExecutor(min(16, os.cpu_count() or 1)) as ex:    # the native reader releases the GIL
         parsed = list(ex.map(lambda g: read_hmm(os.path.join(outdir, "ref_hmm", g + ".hmm")), todo))
     for g, h in zip(todo, parsed):
         if h.M > MAX_M:
