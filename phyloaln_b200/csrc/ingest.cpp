@@ -957,8 +957,8 @@ extern "C" int64_t pa_ingest_emitted_seqs(pa_ingest *S, const uint64_t *idx, uin
 // keeps its FIRST position but its LAST sequence.
 // ---------------------------------------------------------------------------------------------------------------------
 struct pa_fasta {
-  std::string ids, nt;
-  std::vector<uint64_t> id_off, off;
+  BigVec<char> ids, nt;          // untouched until the pack threads write them (no serial zero fill)
+  BigVec<uint64_t> id_off, off;
   std::string err;
 };
 
@@ -986,96 +986,141 @@ extern "C" pa_fasta *pa_fasta_open(const char *path, char *err, int errlen) {
   auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   const double tt0 = now();
   const std::string &t = fj.text;
-  struct Rec { uint64_t id_off, seq_off, seq_len; uint32_t id_len; int32_t multi; };   // multi: index into `joined`, -1 = one line
-  std::vector<std::string> joined;
-  std::vector<Rec> recs;
-  recs.reserve(t.size() / 160 + 16);
-  // open-addressing id table (FNV-1a): slot = record index + 1
-  size_t tcap = 1024;
-  while (tcap < 2 * (t.size() / 96 + 16)) tcap <<= 1;
-  std::vector<uint32_t> slots(tcap, 0u);
-  auto find_or_add = [&](std::string_view id, size_t next_index, bool &found) -> size_t {
-    if (2 * (next_index + 1) > tcap) {   // grow: re-insert every record
-      tcap <<= 1;
-      std::vector<uint32_t> bigger(tcap, 0u);
-      for (size_t k = 0; k < recs.size(); k++) {
-        uint64_t h = 1469598103934665603ull;
-        for (uint32_t z = 0; z < recs[k].id_len; z++) { h ^= (unsigned char)t[recs[k].id_off + z]; h *= 1099511628211ull; }
-        size_t p = (size_t)(h ^ (h >> 32)) & (tcap - 1);
-        while (bigger[p]) p = (p + 1) & (tcap - 1);
-        bigger[p] = (uint32_t)k + 1;
-      }
-      slots.swap(bigger);
-    }
-    uint64_t h = 1469598103934665603ull;
-    for (unsigned char c : id) { h ^= c; h *= 1099511628211ull; }
-    size_t p = (size_t)(h ^ (h >> 32)) & (tcap - 1);
-    while (slots[p]) {
-      const Rec &R = recs[slots[p] - 1];
-      if (R.id_len == id.size() && memcmp(t.data() + R.id_off, id.data(), id.size()) == 0) { found = true; return slots[p] - 1; }
-      p = (p + 1) & (tcap - 1);
-    }
-    slots[p] = (uint32_t)next_index + 1;
-    found = false;
-    return next_index;
-  };
-  size_t i = 0;
   const size_t n = t.size();
-  long cur = -1;
-  int nparts = 0;
-  while (i < n) {
-    const void *nl = memchr(t.data() + i, '\n', n - i);
-    const size_t e = nl ? (size_t)((const char *)nl - t.data()) : n;
-    size_t r = e;
-    while (r > i && (t[r - 1] == '\r' || t[r - 1] == '\n')) r--;   // rstrip(b"\r\n") as in dropin.read_raw_fasta
-    if (r > i && t[i] == '>') {
-      size_t b = i + 1;
-      while (b < r && t[b] != ' ') b++;
-      const std::string_view id(t.data() + i + 1, b - i - 1);
-      if (recs.size() >= 0xfffffffeull || id.size() > 0xffffffffull) {   // 32-bit slots / id lengths: say so, never wrap
-        if (err && errlen > 0) snprintf(err, (size_t)errlen, "%s: more than 4,294,967,294 records or an id longer than 4 GiB", fj.path.c_str());
-        return nullptr;
+  // ---- 1. the file cut at header lines into one range per thread; every range lists its records as they stand in the
+  // text (no dictionary yet): id, first sequence line, further lines joined on the side, hash of the id
+  struct Raw { uint64_t id_off, seq_off, seq_len, hash; uint32_t id_len; int32_t multi; };   // multi: index into the range's `joined`, -1 = one line
+  struct Range { size_t begin = 0, end = 0; std::vector<Raw> recs; std::vector<std::string> joined; };
+  int nth = (int)std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+  if (n < ((size_t)1 << 20)) nth = 1;
+  if (const char *e = getenv("PA_INGEST_THREADS")) nth = std::max(1, std::min(256, atoi(e)));   // tests: several ranges on small files
+  std::vector<Range> ranges((size_t)nth);
+  for (int k = 0; k < nth; k++) {
+    size_t pos = k == 0 ? 0 : n / (size_t)nth * (size_t)k;
+    if (k > 0) {   // forward to the next line that starts with '>'
+      for (;;) {
+        const void *nl = pos < n ? memchr(t.data() + pos, '\n', n - pos) : nullptr;
+        if (!nl) { pos = n; break; }
+        pos = (size_t)((const char *)nl - t.data()) + 1;
+        if (pos < n && t[pos] == '>') break;
       }
-      bool found = false;
-      const size_t at = find_or_add(id, recs.size(), found);
-      if (!found) {
-        recs.push_back(Rec{(uint64_t)(i + 1), 0, 0, (uint32_t)(b - i - 1), -1});
-        cur = (long)recs.size() - 1;
-      } else {
-        cur = (long)at;                    // the later record replaces the sequence, the position stays
-        recs[(size_t)cur].seq_len = 0;
-        recs[(size_t)cur].multi = -1;
-      }
-      nparts = 0;
-    } else if (cur >= 0) {
-      Rec &R = recs[(size_t)cur];
-      if (nparts == 0) { R.seq_off = i; R.seq_len = r - i; }
-      else if (r > i) {
-        if (R.multi < 0) { R.multi = (int32_t)joined.size(); joined.emplace_back(t.data() + R.seq_off, R.seq_len); }
-        joined[(size_t)R.multi].append(t.data() + i, r - i);
-      }
-      nparts++;
     }
-    i = e + 1;
+    ranges[(size_t)k].begin = pos;
+  }
+  for (int k = 0; k < nth; k++) ranges[(size_t)k].end = k + 1 < nth ? ranges[(size_t)k + 1].begin : n;
+  auto parse_range = [&](Range &R) {
+    R.recs.reserve((R.end - R.begin) / 160 + 16);
+    size_t i = R.begin;
+    long cur = -1;
+    int nparts = 0;
+    while (i < R.end) {
+      const void *nl = memchr(t.data() + i, '\n', R.end - i);
+      const size_t e = nl ? (size_t)((const char *)nl - t.data()) : R.end;
+      size_t r = e;
+      while (r > i && (t[r - 1] == '\r' || t[r - 1] == '\n')) r--;   // rstrip(b"\r\n") as in dropin.read_raw_fasta
+      if (r > i && t[i] == '>') {
+        size_t b = i + 1;
+        while (b < r && t[b] != ' ') b++;
+        R.recs.push_back(Raw{(uint64_t)(i + 1), 0, 0, hash_bytes(t.data() + i + 1, b - i - 1), (uint32_t)(b - i - 1), -1});
+        if (b - i - 1 > 0xffffffffull) R.recs.back().id_len = 0xffffffffu;   // reported below
+        cur = (long)R.recs.size() - 1;
+        nparts = 0;
+      } else if (cur >= 0) {
+        Raw &W = R.recs[(size_t)cur];
+        if (nparts == 0) { W.seq_off = i; W.seq_len = r - i; }
+        else if (r > i) {
+          if (W.multi < 0) { W.multi = (int32_t)R.joined.size(); R.joined.emplace_back(t.data() + W.seq_off, W.seq_len); }
+          R.joined[(size_t)W.multi].append(t.data() + i, r - i);
+        }
+        nparts++;
+      }
+      i = e + 1;
+    }
+  };
+  {
+    std::vector<std::thread> th;
+    for (int k = 1; k < nth; k++) th.emplace_back([&, k] { parse_range(ranges[(size_t)k]); });
+    parse_range(ranges[0]);
+    for (auto &x : th) x.join();
   }
   const double tt1 = now();
-  pa_fasta *F = new pa_fasta();
-  size_t idb = 0, ntb = 0;
-  for (auto &R : recs) { idb += R.id_len; ntb += R.multi >= 0 ? joined[(size_t)R.multi].size() : R.seq_len; }
-  F->ids.reserve(idb);
-  F->nt.reserve(ntb + 16);
-  F->id_off.reserve(recs.size() + 1);
-  F->off.reserve(recs.size() + 1);
-  F->id_off.push_back(0);
-  F->off.push_back(0);
-  for (auto &R : recs) {
-    F->ids.append(t.data() + R.id_off, R.id_len);
-    if (R.multi >= 0) F->nt.append(joined[(size_t)R.multi]);
-    else F->nt.append(t.data() + R.seq_off, R.seq_len);
-    F->id_off.push_back(F->ids.size());
-    F->off.push_back(F->nt.size());
+  // ---- 2. read_fastx's dictionary, in file order: a repeated id keeps its position and takes the later record's sequence
+  size_t nraw = 0;
+  for (auto &R : ranges) nraw += R.recs.size();
+  if (nraw >= 0xfffffffeull) {   // 32-bit slots: say so, never wrap
+    if (err && errlen > 0) snprintf(err, (size_t)errlen, "%s: more than 4,294,967,294 records", fj.path.c_str());
+    return nullptr;
   }
-  if (dbg) fprintf(stderr, "pa_fasta_open: parse %.3f s, pack %.3f s\n", tt1 - tt0, now() - tt1);
+  struct Ent { uint32_t range, idx; };      // the raw record an entry takes its id from / its sequence from
+  BigVec<Ent> id_src, seq_src;
+  id_src.reserve(nraw);
+  seq_src.reserve(nraw);
+  size_t tcap = 1024;
+  while (tcap < 2 * (nraw + 16)) tcap <<= 1;
+  BigVec<uint32_t> slots(tcap, 0u);        // open addressing: entry index + 1
+  for (size_t k = 0; k < ranges.size(); k++) {
+    const auto &recs = ranges[k].recs;
+    for (size_t j = 0; j < recs.size(); j++) {
+      if (j + 16 < recs.size()) __builtin_prefetch(&slots[(size_t)(recs[j + 16].hash ^ (recs[j + 16].hash >> 32)) & (tcap - 1)]);
+      const Raw &W = recs[j];
+      size_t p = (size_t)(W.hash ^ (W.hash >> 32)) & (tcap - 1);
+      bool found = false;
+      while (slots[p]) {
+        const Ent &E = id_src[slots[p] - 1];
+        const Raw &O = ranges[E.range].recs[E.idx];
+        if (O.hash == W.hash && O.id_len == W.id_len && memcmp(t.data() + O.id_off, t.data() + W.id_off, W.id_len) == 0) { found = true; break; }
+        p = (p + 1) & (tcap - 1);
+      }
+      if (found) seq_src[slots[p] - 1] = Ent{(uint32_t)k, (uint32_t)j};
+      else {
+        id_src.push_back(Ent{(uint32_t)k, (uint32_t)j});
+        seq_src.push_back(Ent{(uint32_t)k, (uint32_t)j});
+        slots[p] = (uint32_t)id_src.size();
+      }
+    }
+  }
+  const double tt2 = now();
+  // ---- 3. pack ids and sequences: offsets by prefix sum, the copies on all threads
+  pa_fasta *F = new pa_fasta();
+  const size_t nent = id_src.size();
+  F->id_off.resize(nent + 1);
+  F->off.resize(nent + 1);
+  auto seq_of = [&](const Ent &E, const char *&ptr) -> uint64_t {
+    const Range &R = ranges[E.range];
+    const Raw &W = R.recs[E.idx];
+    if (W.multi >= 0) { ptr = R.joined[(size_t)W.multi].data(); return R.joined[(size_t)W.multi].size(); }
+    ptr = t.data() + W.seq_off;
+    return W.seq_len;
+  };
+  uint64_t idb = 0, ntb = 0;
+  for (size_t e = 0; e < nent; e++) {
+    F->id_off[e] = idb;
+    F->off[e] = ntb;
+    idb += ranges[id_src[e].range].recs[id_src[e].idx].id_len;
+    const char *ptr;
+    ntb += seq_of(seq_src[e], ptr);
+  }
+  F->id_off[nent] = idb;
+  F->off[nent] = ntb;
+  F->ids.reserve(idb + 1);       // capacity only: BigVec memory above 2 MB is fresh mmap, first touched by the pack threads
+  F->nt.reserve(ntb + 16);
+  auto pack_part = [&](size_t e0, size_t e1) {
+    for (size_t e = e0; e < e1; e++) {
+      const Raw &W = ranges[id_src[e].range].recs[id_src[e].idx];
+      memcpy(F->ids.data() + F->id_off[e], t.data() + W.id_off, W.id_len);
+      const char *ptr;
+      const uint64_t len = seq_of(seq_src[e], ptr);
+      if (len) memcpy(F->nt.data() + F->off[e], ptr, len);
+    }
+  };
+  {
+    std::vector<std::thread> th;
+    const size_t per = (nent + (size_t)nth - 1) / (size_t)nth;
+    for (int k = 1; k < nth; k++) th.emplace_back([&, k] { pack_part(std::min(nent, per * (size_t)k), std::min(nent, per * (size_t)(k + 1))); });
+    pack_part(0, std::min(nent, per));
+    for (auto &x : th) x.join();
+  }
+  if (dbg) fprintf(stderr, "pa_fasta_open: parse %.3f s (%d threads), dictionary %.3f s, pack %.3f s\n", tt1 - tt0, nth, tt2 - tt1, now() - tt2);
   return F;
 }
 extern "C" int64_t pa_fasta_num_records(pa_fasta *F) { return F ? (int64_t)F->off.size() - 1 : -1; }

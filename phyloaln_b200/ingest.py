@@ -62,7 +62,7 @@ def _lib():
 class LazyIds:
     """Sequence of record ids decoded on demand from one byte blob (10 M ids are never all needed: only reads with hits)."""
 
-    def __init__(self, blob: bytes, off: np.ndarray):
+    def __init__(self, blob, off: np.ndarray):     # blob: bytes or a uint8 array
         self._blob, self._off = blob, off
 
     def __len__(self):
@@ -73,7 +73,7 @@ class LazyIds:
             return [self[k] for k in range(*i.indices(len(self)))]
         if i < 0:
             i += len(self)
-        return self._blob[int(self._off[i]):int(self._off[i + 1])].decode()
+        return bytes(self._blob[int(self._off[i]):int(self._off[i + 1])]).decode()
 
     def __iter__(self):
         return (self[k] for k in range(len(self)))
@@ -87,18 +87,36 @@ def load_raw_fasta(path: str):
     h = L.pa_fasta_open(path.encode(), err, 512)
     if not h:
         raise OSError(err.value.decode() or f"cannot read {path}")
-    try:
-        n = L.pa_fasta_num_records(h)
-        p_ids, p_idoff, p_nt, p_off = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
-        L.pa_fasta_views(h, C.byref(p_ids), C.byref(p_idoff), C.byref(p_nt), C.byref(p_off))
-        id_off = np.ctypeslib.as_array(C.cast(p_idoff, C.POINTER(C.c_uint64)), shape=(n + 1,)).copy()
-        off = np.ctypeslib.as_array(C.cast(p_off, C.POINTER(C.c_uint64)), shape=(n + 1,)).copy()
-        blob = C.string_at(p_ids, int(id_off[-1])) if n else b""
-        total = int(off[-1])
-        nt = np.ctypeslib.as_array(C.cast(p_nt, C.POINTER(C.c_uint8)), shape=(max(total, 1),)).copy() if total else np.zeros(1, np.uint8)
-    finally:
-        L.pa_fasta_close(h)
-    return LazyIds(blob, id_off), nt[:total] if total else nt[:0], off
+    holder = _FastaHandle(L, h)
+    n = L.pa_fasta_num_records(h)
+    p_ids, p_idoff, p_nt, p_off = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+    L.pa_fasta_views(h, C.byref(p_ids), C.byref(p_idoff), C.byref(p_nt), C.byref(p_off))
+
+    def view(ptr, ctype, count, dtype):      # zero-copy: the array keeps the native handle alive through its base
+        if count == 0 or not ptr.value:
+            return np.zeros(0, dtype=dtype)
+        raw = (ctype * count).from_address(ptr.value)
+        raw._holder = holder
+        return np.frombuffer(raw, dtype=dtype)
+    id_off = view(p_idoff, C.c_uint64, n + 1, np.uint64)
+    off = view(p_off, C.c_uint64, n + 1, np.uint64)
+    if n == 0:
+        return LazyIds(b"", np.zeros(1, np.uint64)), np.zeros(0, np.uint8), np.zeros(1, np.uint64)
+    blob = view(p_ids, C.c_uint8, int(id_off[-1]), np.uint8)
+    nt = view(p_nt, C.c_uint8, int(off[-1]), np.uint8)
+    return LazyIds(blob, id_off), nt, off
+
+
+class _FastaHandle:
+    """Owner of a pa_fasta: closed when the last array viewing its buffers is gone."""
+
+    def __init__(self, L, h):
+        self.L, self.h = L, h
+
+    def __del__(self):
+        if self.h:
+            self.L.pa_fasta_close(self.h)
+            self.h = None
 
 
 class Ingest:

@@ -131,3 +131,33 @@ def test_native_raw_fasta_loader_equals_python_statement(tmp_path):
     ids0, nt0, off0 = dropin.read_raw_fasta(str(tmp_path / "tiny.fasta"))
     ids1, nt1, off1 = load_raw_fasta(str(tmp_path / "tiny.fasta"))
     assert list(ids1) == ids0 and len(ids0) == 6000 and nt1.tobytes() == nt0.tobytes() and np.array_equal(off1, off0)
+
+
+@pytest.mark.parametrize("threads", [1, 2, 3, 7, 16])
+def test_native_raw_fasta_loader_parallel_ranges(tmp_path, monkeypatch, threads):
+    """The loader parses the file in byte ranges cut at header lines, one per thread, and applies read_fastx's dictionary in a
+    serial pass over the ranges: the result must not depend on where the cuts fall -- repeated ids on both sides of a cut,
+    multi-line and empty sequences, CRLF, '>' only at line starts, text before the first header, a file without trailing
+    newline.  Random files against the plain-Python statement, for several thread counts."""
+    from phyloaln_b200 import dropin
+    from phyloaln_b200.ingest import load_raw_fasta
+    monkeypatch.setenv("PA_INGEST_THREADS", str(threads))
+    rng = np.random.default_rng(100 + threads)
+    for case in range(12):
+        nrec = int(rng.integers(1, 400))
+        names = [f"id{int(rng.integers(0, max(2, nrec // 2)))}" for _ in range(nrec)]       # about half the ids repeat
+        out = ["leading text\n"] if case % 3 == 0 else []
+        for nm in names:
+            out.append(">" + nm + (" description > with a bracket" if rng.random() < 0.3 else "") + ("\r\n" if rng.random() < 0.1 else "\n"))
+            for _ in range(int(rng.integers(0, 4))):
+                line = "".join("ACGTN"[int(x)] for x in rng.integers(0, 5, int(rng.integers(0, 30))))
+                out.append(line + ("\r\n" if rng.random() < 0.1 else "\n"))
+        text = "".join(out)
+        if case % 4 == 1:
+            text = text.rstrip("\r\n")
+        p = tmp_path / f"c{case}.fasta"
+        p.write_bytes(text.encode())
+        ids0, nt0, off0 = dropin.read_raw_fasta(str(p))
+        ids1, nt1, off1 = load_raw_fasta(str(p))
+        assert list(ids1) == ids0, (threads, case)
+        assert np.array_equal(off1, off0) and nt1.tobytes() == nt0.tobytes(), (threads, case)
