@@ -248,9 +248,8 @@ def hmmsearch_step(outdir: str, groups, mol_type: str = "prot", gencode: int = 1
         id_of = dict(zip(hit_reads.tolist(), ingest.ids_of(recs)))
         seq_of = dict(zip(hit_reads.tolist(), ingest.seqs_of(recs)))
     else:
-        raw = nt.tobytes()
         id_of = {int(r): ids[int(r)] for r in hit_reads}
-        seq_of = {int(r): raw[int(off[r]):int(off[r + 1])].decode() for r in hit_reads}
+        seq_of = {int(r): nt[int(off[r]):int(off[r + 1])].tobytes().decode() for r in hit_reads}     # no copy of the whole read set
     suffixes = [frame_suffix(f, nframes, translated) for f in range(nframes)]
 
     def tname(t):
