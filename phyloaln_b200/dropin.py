@@ -170,7 +170,13 @@ def hmmsearch_step(outdir: str, groups, mol_type: str = "prot", gencode: int = 1
         hmms.append(h)
         kept.append(g)
     todo = kept
-    resolve_cutoffs(opts, hmms)        # --cut_ga / --cut_tc / --cut_nc: every profile's own thresholds, or an error
+    try:
+        resolve_cutoffs(opts, hmms)    # --cut_ga / --cut_tc / --cut_nc: every profile's own thresholds, or an error
+    except Exception:
+        for t in searcher._ctx_threads or []:      # the contexts being created beside the parsing are not left behind
+            t.join()
+        searcher.close()
+        raise
     tm["read_hmms_s"] = time.perf_counter() - t0
     # '--codon' forces no_reverse in the reference (lib/main.py:196-198)
     if codon:
