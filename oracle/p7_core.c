@@ -203,7 +203,7 @@ ORC_HMM *orc_hmm_read(const char *path, char *err, int errlen) {
   (void)map_flag;
   if (M < 1 || abc < 0) FAIL("%s: missing LENG/ALPH", path);
   h = hmm_alloc(M, abc);
-  strncpy(h->name, name, 255);
+  snprintf(h->name, sizeof(h->name), "%s", name);
   if (got[0] && got[1] && got[2]) {
     memcpy(h->ev, ev, sizeof(ev));
     h->has_stats = 1;
