@@ -1,3 +1,6 @@
+"""Issue-rate microbenchmarks of the instructions the filter kernels are built from (pa_microbench_dpx modes 0-7, run on the
+B200 box): the ceilings the roofline of bench.py is quoted against, and the co-issue experiments of DESIGN.md section 5c
+(profiles/r2_microbench_pipes.txt)."""
 import sys; sys.path.insert(0,'.')
 from phyloaln_b200 import capi
 c=capi.Context(0)
