@@ -118,11 +118,13 @@ def _cutoff_line(tok):
 def read_cutoffs(path: str) -> dict:
     """GA / TC / NC header lines of the first model of an HMMER3 ASCII file (the native reader does not return them)."""
     out = {}
-    with open(path) as fh:
-        for line in fh:
-            if line.startswith("HMM "):
+    with open(path, "rb") as fh:          # bytes: a DESC line in some other encoding must not stop the header scan
+        for raw in fh:
+            if raw.startswith(b"HMM "):
                 break
-            tok = line.split()
+            if raw[:2] not in (b"GA", b"TC", b"NC"):
+                continue
+            tok = raw.decode("latin-1").split()
             if len(tok) >= 3 and tok[0] in ("GA", "TC", "NC"):
                 try:
                     out[tok[0]] = _cutoff_line(tok)
